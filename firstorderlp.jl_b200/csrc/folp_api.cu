@@ -1,0 +1,1010 @@
+// folp_api.cu -- host side of libfolp_b200.so: the C ABI of include/folp_b200.h.
+//
+// Replaces the while-loop of optimize(::PdhgParameters, qp)
+// (src/primal_dual_hybrid_gradient.jl:862-1048). The host keeps only scalar
+// control flow (evaluation cadence :892-895, termination term.jl:233-273, restart
+// decisions sp.jl:688-846, primal weight sp.jl:862-891); every vector lives in
+// HBM and every O(n), O(m), O(nnz) operation is a kernel in folp_kernels.cu.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <new>
+
+#include "folp_kernels.cuh"
+
+using namespace folp;
+
+namespace {
+thread_local std::string g_create_error;
+
+double now_sec() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+struct folp_handle {
+  std::string err;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t n = 0, m = 0, nnz = 0, neq = 0;
+  folp_params prm{};
+  double cache[4] = {0, 0, 0, 0};
+  double objective_constant = 0.0;
+  SpmvMat A, At;
+  Bufs B;
+  std::vector<void*> allocs;
+  // pinned host mirrors
+  DevState* hs = nullptr;
+  double* h_red = nullptr;   // 4 * kMaxScalars
+  TrState* h_trs = nullptr;
+  TrState* d_trs = nullptr;
+  // RestartInfo (sp.jl:158-197), scalars
+  int has_last_gap = 0;
+  double last_gap = 0.0;
+  int64_t last_restart_length = 1;
+  double pd_last = 0.0, dd_last = 0.0, gap_reduction_ratio_last_trial = 1.0;
+  // loop bookkeeping (the reference's `iteration`, pdhg.jl:885-887)
+  int64_t iteration = 0;
+  int need_step = 0, terminated = 0;
+  double start_time = 0.0, basic_time = 0.0;
+  folp_eval last_eval{};
+  int64_t launches = 0;
+  int64_t tr_passes = 0, tr_solves = 0;
+  std::map<int, cudaGraphExec_t> step_graphs;
+  bool use_graphs = true;
+};
+
+#define TRY(expr) FOLP_CUDA_TRY(h, expr)
+#define CHECK_LAUNCH() TRY(cudaGetLastError())
+
+// ---------------------------------------------------------------------------
+// setup helpers
+// ---------------------------------------------------------------------------
+template <class T>
+static int dev_alloc(folp_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  TRY(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return FOLP_OK;
+}
+static int dev_zeros(folp_handle* h, double** p, size_t count) {
+  int rc = dev_alloc(h, p, count);
+  if (rc) return rc;
+  TRY(cudaMemsetAsync(*p, 0, std::max<size_t>(count, 1) * sizeof(double), h->stream));
+  return FOLP_OK;
+}
+static int dev_upload(folp_handle* h, double** p, const double* src, size_t count, double fill) {
+  int rc = dev_alloc(h, p, count);
+  if (rc) return rc;
+  if (src) {
+    TRY(cudaMemcpyAsync(*p, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    launch_fill(*p, fill, static_cast<int64_t>(count), h->stream);
+  }
+  return FOLP_OK;
+}
+
+// Packs rows into tiles (see folp_internal.cuh) and uploads the CSR arrays.
+static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
+                        const std::vector<int>& rowptr, const std::vector<int>& colidx,
+                        const std::vector<double>& vals) {
+  M->rows = rows;
+  M->cols = cols;
+  M->nnz = rowptr[rows];
+  std::vector<Tile> tiles;
+  int nlong = 0, nchunks_total = 0;
+  int r = 0;
+  while (r < rows) {
+    const int len = rowptr[r + 1] - rowptr[r];
+    if (len > kTileNnz) {
+      const int nch = (len + kTileNnz - 1) / kTileNnz;
+      for (int c = 0; c < nch; ++c) {
+        Tile t{};
+        t.row_begin = r; t.row_end = r + 1;
+        t.nnz_begin = rowptr[r] + c * kTileNnz;
+        t.nnz_end = std::min(rowptr[r + 1], t.nnz_begin + kTileNnz);
+        t.kind = kTileLongChunk;
+        t.long_id = nlong; t.chunk_first = nchunks_total; t.chunk_count = nch; t.chunk_index = c;
+        tiles.push_back(t);
+      }
+      nlong += 1;
+      nchunks_total += nch;
+      r += 1;
+      continue;
+    }
+    Tile t{};
+    t.row_begin = r;
+    t.nnz_begin = rowptr[r];
+    int nnz = 0, maxlen = 0;
+    while (r < rows && r - t.row_begin < kTileRows) {
+      const int l2 = rowptr[r + 1] - rowptr[r];
+      if (l2 > kTileNnz || nnz + l2 > kTileNnz) break;
+      nnz += l2;
+      maxlen = std::max(maxlen, l2);
+      r += 1;
+    }
+    t.row_end = r;
+    t.nnz_end = t.nnz_begin + nnz;
+    t.kind = maxlen > 32 ? kTileWarpPerRow : kTileThreadPerRow;
+    tiles.push_back(t);
+  }
+  M->ntiles = static_cast<int>(tiles.size());
+  M->nlong = nlong;
+  const size_t pad = 16;
+  int rc;
+  if ((rc = dev_alloc(h, &M->rowptr, static_cast<size_t>(rows) + 1))) return rc;
+  if ((rc = dev_alloc(h, &M->colidx, static_cast<size_t>(M->nnz) + pad))) return rc;
+  if ((rc = dev_alloc(h, &M->vals, static_cast<size_t>(M->nnz) + pad))) return rc;
+  if ((rc = dev_alloc(h, &M->tiles, tiles.size()))) return rc;
+  if ((rc = dev_alloc(h, &M->long_partials, static_cast<size_t>(nchunks_total)))) return rc;
+  if ((rc = dev_alloc(h, &M->long_tickets, static_cast<size_t>(nlong)))) return rc;
+  TRY(cudaMemsetAsync(M->colidx, 0, (static_cast<size_t>(M->nnz) + pad) * sizeof(int), h->stream));
+  TRY(cudaMemsetAsync(M->vals, 0, (static_cast<size_t>(M->nnz) + pad) * sizeof(double), h->stream));
+  TRY(cudaMemsetAsync(M->long_tickets, 0, std::max(nlong, 1) * sizeof(unsigned), h->stream));
+  TRY(cudaMemcpyAsync(M->rowptr, rowptr.data(), (static_cast<size_t>(rows) + 1) * sizeof(int),
+                      cudaMemcpyHostToDevice, h->stream));
+  if (M->nnz) {
+    TRY(cudaMemcpyAsync(M->colidx, colidx.data(), static_cast<size_t>(M->nnz) * sizeof(int),
+                        cudaMemcpyHostToDevice, h->stream));
+    TRY(cudaMemcpyAsync(M->vals, vals.data(), static_cast<size_t>(M->nnz) * sizeof(double),
+                        cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!tiles.empty())
+    TRY(cudaMemcpyAsync(M->tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice,
+                        h->stream));
+  TRY(cudaStreamSynchronize(h->stream));  // host vectors die with the caller's scope
+  return FOLP_OK;
+}
+
+static void free_handle(folp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->step_graphs) cudaGraphExecDestroy(kv.second);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->hs) cudaFreeHost(h->hs);
+  if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->h_trs) cudaFreeHost(h->h_trs);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int push_state(folp_handle* h) {
+  TRY(cudaMemcpyAsync(h->B.st, h->hs, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+  return FOLP_OK;
+}
+static int pull_state(folp_handle* h) {
+  TRY(cudaMemcpyAsync(h->hs, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  return FOLP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// folp_create
+// ---------------------------------------------------------------------------
+static int create_impl(folp_handle* h, const folp_problem* p, const folp_params* q,
+                       const folp_dist* dist) {
+  if (dist && dist->world_size > 1) {
+    h->err = "multi-GPU row partition is not built into this library version";
+    return FOLP_UNSUPPORTED;
+  }
+  const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
+  if (n < 0 || m < 0 || nnz < 0 || p->num_equalities < 0 || p->num_equalities > m ||
+      (p->index_base != 0 && p->index_base != 1)) {
+    h->err = "invalid problem dimensions";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  if (nnz > 0 && (!p->colptr || !p->rowval || !p->nzval)) {
+    h->err = "null matrix arrays";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  if ((n > 0 && (!p->objective_vector || !p->variable_lower_bound || !p->variable_upper_bound)) ||
+      (m > 0 && !p->right_hand_side)) {
+    h->err = "null problem vectors";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  if (n + m >= (int64_t{1} << 31) - 64 || nnz >= (int64_t{1} << 31) - 64) {
+    h->err = "per-GPU shard exceeds 32-bit indexing (n+m or nnz >= 2^31)";
+    return FOLP_UNSUPPORTED;
+  }
+  for (int64_t k = 0; k < p->q_num_nonzeros; ++k)
+    if (p->q_nzval && p->q_nzval[k] != 0.0) {
+      h->err = "quadratic objectives are not supported by the B200 path yet (LP only)";
+      return FOLP_UNSUPPORTED;
+    }
+  if (q->termination_evaluation_frequency < 1) {
+    h->err = "termination_evaluation_frequency must be >= 1";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  if (!(q->initial_step_size > 0.0) || !(q->initial_primal_weight > 0.0)) {
+    h->err = "initial_step_size and initial_primal_weight must be positive";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
+  h->prm = *q;
+  h->cache[0] = p->l_inf_norm_primal_linear_objective;
+  h->cache[1] = p->l_inf_norm_primal_right_hand_side;
+  h->cache[2] = p->l2_norm_primal_linear_objective;
+  h->cache[3] = p->l2_norm_primal_right_hand_side;
+  h->objective_constant = p->objective_constant;
+
+  if (dist) h->device = dist->device;
+  else TRY(cudaGetDevice(&h->device));
+  TRY(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  TRY(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) {
+    h->err = std::string("libfolp_b200 is built for sm_100a only; device is ") + prop.name;
+    return FOLP_UNSUPPORTED;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  TRY(cudaEventCreate(&h->ev0));
+  TRY(cudaEventCreate(&h->ev1));
+  TRY(static_cast<cudaError_t>(spmv_configure()));
+  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->hs), sizeof(DevState)));
+  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_red), sizeof(double) * 4 * kMaxScalars));
+  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_trs), sizeof(TrState)));
+
+  // ---- matrices: A' in CSR is the caller's CSC; A in CSR by counting sort ----
+  const int base = p->index_base;
+  {
+    std::vector<int> rp(static_cast<size_t>(n) + 1), ci(static_cast<size_t>(nnz));
+    std::vector<double> v(static_cast<size_t>(nnz));
+    for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - base) : 0;
+    for (int64_t k = 0; k < nnz; ++k) {
+      const int64_t r = p->rowval[k] - base;
+      if (r < 0 || r >= m) { h->err = "row index out of range"; return FOLP_INVALID_ARGUMENT; }
+      ci[k] = static_cast<int>(r);
+      v[k] = p->nzval[k];
+    }
+    for (int64_t j = 0; j < n; ++j)
+      if (rp[j] > rp[j + 1] || rp[j] < 0 || rp[j + 1] > nnz) {
+        h->err = "colptr is not monotone";
+        return FOLP_INVALID_ARGUMENT;
+      }
+    int rc = build_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp, ci, v);
+    if (rc) return rc;
+    // transpose
+    std::vector<int> rp2(static_cast<size_t>(m) + 1, 0), ci2(static_cast<size_t>(nnz));
+    std::vector<double> v2(static_cast<size_t>(nnz));
+    for (int64_t k = 0; k < nnz; ++k) rp2[ci[k] + 1] += 1;
+    for (int64_t i = 0; i < m; ++i) rp2[i + 1] += rp2[i];
+    std::vector<int> fillp(rp2.begin(), rp2.end() - 1);
+    for (int64_t j = 0; j < n; ++j)
+      for (int k = rp[j]; k < rp[j + 1]; ++k) {
+        const int pos = fillp[ci[k]]++;
+        ci2[pos] = static_cast<int>(j);  // ascending j inside each row
+        v2[pos] = v[k];
+      }
+    rc = build_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, ci2, v2);
+    if (rc) return rc;
+  }
+
+  // ---- vectors ----
+  Bufs& B = h->B;
+  B.n = static_cast<int>(n); B.m = static_cast<int>(m); B.neq = static_cast<int>(h->neq);
+  B.grid_spmv = h->sm_count * 4;
+  B.grid_vec = h->sm_count * 8;
+  int rc;
+  if ((rc = dev_alloc(h, &B.st, 1))) return rc;
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = dev_zeros(h, &B.x[k], n))) return rc;
+    if ((rc = dev_zeros(h, &B.y[k], m))) return rc;
+    if ((rc = dev_zeros(h, &B.aty[k], n))) return rc;
+  }
+  if ((rc = dev_zeros(h, &B.xbar, n))) return rc;
+  if ((rc = dev_upload(h, &B.c, p->objective_vector, n, 0.0))) return rc;
+  if ((rc = dev_upload(h, &B.l, p->variable_lower_bound, n, 0.0))) return rc;
+  if ((rc = dev_upload(h, &B.u, p->variable_upper_bound, n, 0.0))) return rc;
+  if ((rc = dev_upload(h, &B.b, p->right_hand_side, m, 0.0))) return rc;
+  if ((rc = dev_zeros(h, &B.sum_x, n))) return rc;
+  if ((rc = dev_zeros(h, &B.sum_y, m))) return rc;
+  if ((rc = dev_zeros(h, &B.avg_x, n))) return rc;
+  if ((rc = dev_zeros(h, &B.avg_y, m))) return rc;
+  if ((rc = dev_zeros(h, &B.ax_avg, m))) return rc;
+  if ((rc = dev_zeros(h, &B.aty_avg, n))) return rc;
+  if ((rc = dev_zeros(h, &B.ax_cur, m))) return rc;
+  if ((rc = dev_zeros(h, &B.last_x, n))) return rc;   // create_last_restart_info, sp.jl:199-213
+  if ((rc = dev_zeros(h, &B.last_y, m))) return rc;
+  if ((rc = dev_zeros(h, &B.last_ax, m))) return rc;
+  if ((rc = dev_zeros(h, &B.last_aty, n))) return rc;
+  if ((rc = dev_upload(h, &B.D, p->variable_rescaling, n, 1.0))) return rc;
+  if ((rc = dev_upload(h, &B.E, p->constraint_rescaling, m, 1.0))) return rc;
+  if ((rc = dev_upload(h, &B.c_orig,
+                       p->orig_objective_vector ? p->orig_objective_vector : p->objective_vector, n,
+                       0.0)))
+    return rc;
+  if ((rc = dev_upload(h, &B.l_orig,
+                       p->orig_variable_lower_bound ? p->orig_variable_lower_bound
+                                                    : p->variable_lower_bound, n, 0.0)))
+    return rc;
+  if ((rc = dev_upload(h, &B.u_orig,
+                       p->orig_variable_upper_bound ? p->orig_variable_upper_bound
+                                                    : p->variable_upper_bound, n, 0.0)))
+    return rc;
+  if ((rc = dev_upload(h, &B.b_orig,
+                       p->orig_right_hand_side ? p->orig_right_hand_side : p->right_hand_side, m,
+                       0.0)))
+    return rc;
+  if ((rc = dev_zeros(h, &B.tr_t, n + m))) return rc;
+  if ((rc = dev_zeros(h, &B.tr_d, n + m))) return rc;
+  if ((rc = dev_zeros(h, &B.part, static_cast<size_t>(kNumSlots) * kMaxScalars * kMaxPartialBlocks)))
+    return rc;
+  if ((rc = dev_zeros(h, &B.red, static_cast<size_t>(4) * kMaxScalars))) return rc;
+  if ((rc = dev_alloc(h, &B.counters, 8))) return rc;
+  TRY(cudaMemsetAsync(B.counters, 0, 8 * sizeof(unsigned), h->stream));
+  if ((rc = dev_alloc(h, &h->d_trs, 1))) return rc;
+
+  // ---- PdhgSolverState scalars, pdhg.jl:805-819 ----
+  DevState s;
+  memset(&s, 0, sizeof(s));
+  s.step_size = q->initial_step_size;
+  s.trial_step = q->initial_step_size;
+  s.avg_weight = q->initial_step_size;
+  s.primal_weight = q->initial_primal_weight;
+  s.kkt_passes = q->initial_kkt_passes;
+  s.ratio_step_sizes = 1.0;
+  s.mp_need_primal = 1;
+  s.policy = q->step_size_policy;
+  s.reduction_exponent = q->reduction_exponent;
+  s.growth_exponent = q->growth_exponent;
+  s.downscaling_factor = q->downscaling_factor;
+  s.breaking_factor = q->breaking_factor;
+  s.interpolation_coefficient = q->interpolation_coefficient;
+  *h->hs = s;
+  if ((rc = push_state(h))) return rc;
+  TRY(cudaStreamSynchronize(h->stream));
+  h->start_time = now_sec();
+  return FOLP_OK;
+}
+
+extern "C" int folp_create(const folp_problem* problem, const folp_params* params,
+                           const folp_dist* dist, folp_handle** out) {
+  if (!problem || !params || !out) {
+    g_create_error = "null argument";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  folp_handle* h = new (std::nothrow) folp_handle();
+  if (!h) {
+    g_create_error = "host allocation failed";
+    return FOLP_OUT_OF_MEMORY;
+  }
+  int rc;
+  try {
+    rc = create_impl(h, problem, params, dist);
+  } catch (const std::bad_alloc&) {
+    h->err = "host allocation failed";
+    rc = FOLP_OUT_OF_MEMORY;
+  }
+  if (rc) {
+    g_create_error = h->err;
+    free_handle(h);
+    return rc;
+  }
+  *out = h;
+  return FOLP_OK;
+}
+
+extern "C" void folp_destroy(folp_handle* h) { free_handle(h); }
+
+extern "C" const char* folp_last_error(const folp_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" const char* folp_build_info(void) {
+  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;tile_nnz=2048;tile_rows=512";
+}
+
+extern "C" int folp_nccl_unique_id(void* out128) {
+  if (out128) memset(out128, 0, 128);
+  return FOLP_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------
+// take_step batches
+// ---------------------------------------------------------------------------
+static int enqueue_attempts(folp_handle* h, int attempts) {
+  if (attempts <= 0) return FOLP_OK;
+  if (!h->use_graphs || attempts < 2) {
+    launch_step_attempts(h->B, h->A, h->At, attempts, h->stream);
+    CHECK_LAUNCH();
+  } else {
+    auto it = h->step_graphs.find(attempts);
+    if (it == h->step_graphs.end()) {
+      cudaGraph_t g = nullptr;
+      cudaGraphExec_t ge = nullptr;
+      TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      launch_step_attempts(h->B, h->A, h->At, attempts, h->stream);
+      TRY(cudaStreamEndCapture(h->stream, &g));
+      TRY(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = h->step_graphs.emplace(attempts, ge).first;
+    }
+    TRY(cudaGraphLaunch(it->second, h->stream));
+  }
+  h->launches += 3 * static_cast<int64_t>(attempts);
+  return FOLP_OK;
+}
+
+// Runs take_step until `target` iterations are complete or numerical_error.
+static int run_steps(folp_handle* h, int64_t target) {
+  DevState* s = h->hs;
+  int rc;
+  s->target_iterations = target;
+  s->active = (s->iterations < target && !s->numerical_error) ? 1 : 0;
+  if ((rc = push_state(h))) return rc;
+  TRY(cudaEventRecord(h->ev0, h->stream));
+  while (s->active) {
+    const int64_t remaining = target - s->iterations;
+    int64_t attempts = remaining + (remaining >= 8 ? remaining / 16 + 1 : 0);
+    if (s->policy == FOLP_STEP_CONSTANT) attempts = remaining;
+    attempts = std::min<int64_t>(attempts, 512);
+    if ((rc = enqueue_attempts(h, static_cast<int>(attempts)))) return rc;
+    if ((rc = pull_state(h))) return rc;
+  }
+  TRY(cudaEventRecord(h->ev1, h->stream));
+  TRY(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->basic_time += 1e-3 * ms;
+  return FOLP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// evaluation block helpers
+// ---------------------------------------------------------------------------
+static double jl_max(double a, double b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  return a > b ? a : b;
+}
+
+struct BoundResult {
+  double lagrangian_value, lower_bound_value, upper_bound_value;
+};
+static double get_gap(const BoundResult& r) { return r.upper_bound_value - r.lower_bound_value; }
+
+// One trust-region solve on device; *out receives the final TrState.
+static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
+  launch_tr(h->B, P, h->d_trs, 10, true, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 12;
+  h->tr_solves += 1;
+  for (int round = 0;; ++round) {
+    TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState), cudaMemcpyDeviceToHost, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+    if (h->h_trs->done) break;
+    if (round > 40) {
+      h->err = "trust-region search did not converge";
+      return FOLP_CUDA_ERROR;
+    }
+    launch_tr(h->B, P, h->d_trs, 16, false, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 17;
+  }
+  *out = *h->h_trs;
+  h->tr_passes += out->passes;
+  return FOLP_OK;
+}
+
+// bound_optimal_objective (tr.jl:271-360), EUCLIDEAN_NORM, at a point whose
+// products A*x and A'*y are already in HBM.
+static int euclidean_gap(folp_handle* h, const double* px, const double* atp, const double* py,
+                         const double* axp, double wp, double wd, double radius,
+                         BoundResult* out) {
+  TrProblem P{px, atp, py, axp, wp, wd, radius, 1, 1,
+              h->prm.use_approximate_localized_duality_gap};
+  TrState t;
+  int rc = tr_solve(h, P, &t);
+  if (rc) return rc;
+  out->lagrangian_value = ((0.0 + t.cx) - t.x_aty) + t.y_b + h->objective_constant;
+  out->lower_bound_value = out->lagrangian_value + t.v_primal;
+  out->upper_bound_value = out->lagrangian_value - t.v_dual;
+  return FOLP_OK;
+}
+
+// check_termination_criteria, term.jl:233-273
+static int check_termination(const folp_params* c, const double cache[4], const folp_eval* s) {
+  const double abs_obj = fabs(s->primal_objective) + fabs(s->dual_objective);
+  const double gap = fabs(s->primal_objective - s->dual_objective);
+  double perr, pbase, derr, dbase;
+  if (c->optimality_norm == FOLP_L_INF) {
+    perr = s->l_inf_primal_residual; pbase = cache[1];
+    derr = s->l_inf_dual_residual; dbase = cache[0];
+  } else {
+    perr = s->l2_primal_residual; pbase = cache[3];
+    derr = s->l2_dual_residual; dbase = cache[2];
+  }
+  const double ea = c->eps_optimal_absolute, er = c->eps_optimal_relative;
+  if (derr < ea + er * dbase && perr < ea + er * pbase && gap < ea + er * abs_obj)
+    return FOLP_TERMINATION_REASON_OPTIMAL;
+  if (s->dual_ray_objective > 0.0 &&
+      s->max_dual_ray_infeasibility / s->dual_ray_objective <= c->eps_primal_infeasible)
+    return FOLP_TERMINATION_REASON_PRIMAL_INFEASIBLE;
+  if (s->primal_ray_linear_objective < 0.0 &&
+      s->max_primal_ray_infeasibility / (-s->primal_ray_linear_objective) <= c->eps_dual_infeasible &&
+      s->primal_ray_quadratic_norm / (-s->primal_ray_linear_objective) <= c->eps_dual_infeasible)
+    return FOLP_TERMINATION_REASON_DUAL_INFEASIBLE;
+  if (s->iteration_number >= c->iteration_limit) return FOLP_TERMINATION_REASON_ITERATION_LIMIT;
+  if (s->cumulative_kkt_matrix_passes >= c->kkt_matrix_pass_limit)
+    return FOLP_TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT;
+  if (s->cumulative_time_sec >= c->time_sec_limit) return FOLP_TERMINATION_REASON_TIME_LIMIT;
+  return 0;
+}
+
+// run_restart_scheme, sp.jl:688-846. wp/wd are the constant norm weights of
+// define_norms (pdhg.jl:265-276).
+static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, double wp, double wd,
+                              const BoundResult& gap_at_avg_seed, int* choice_out) {
+  (void)gap_at_avg_seed;
+  DevState* s = h->hs;
+  const folp_params* rp = &h->prm;
+  Bufs& B = h->B;
+  if (!(s->count_x > 0 && s->count_y > 0)) {
+    *choice_out = FOLP_RESTART_CHOICE_NO_RESTART;
+    return FOLP_OK;
+  }
+  int rc;
+  const int64_t restart_length = s->count_x;
+  int do_restart = 0;
+  if (static_cast<double>(restart_length) >=
+      rp->artificial_restart_threshold * static_cast<double>(iterations_completed))
+    do_restart = 1;
+  // distances to the last restart point (needed by every branch that restarts)
+  double* red = B.red + 2 * kMaxScalars;
+  launch_dist(B, red, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 1;
+  TRY(cudaMemcpyAsync(h->h_red + 2 * kMaxScalars, red, sizeof(double) * SD_TOTAL,
+                      cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  const double* dist = h->h_red + 2 * kMaxScalars;
+  const double avg_px = sqrt(wp * dist[SD_avg_x]), avg_dy = sqrt(wd * dist[SD_avg_y]);
+  const double cur_px = sqrt(wp * dist[SD_cur_x]), cur_dy = sqrt(wd * dist[SD_cur_y]);
+
+  int reset_to_average;
+  int have_candidate = 0, have_ax_cur = 0;
+  BoundResult candidate_gap{0, 0, 0};
+  double candidate_distance = 0.0;
+  if (rp->restart_scheme == FOLP_NO_RESTARTS) {
+    reset_to_average = 0;
+  } else {
+    // compute_localized_duality_gaps, sp.jl:432-496
+    const double d_avg = sqrt(avg_px * avg_px + avg_dy * avg_dy);
+    const double d_cur = sqrt(cur_px * cur_px + cur_dy * cur_dy);
+    BoundResult g_avg, g_cur;
+    if ((rc = euclidean_gap(h, B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, d_avg, &g_avg)))
+      return rc;
+    launch_spmv_plain(h->A, B.x[s->cur], B.ax_cur, B.grid_spmv, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 1;
+    have_ax_cur = 1;
+    if ((rc = euclidean_gap(h, B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, d_cur,
+                            &g_cur)))
+      return rc;
+    // should_reset_to_average, sp.jl:530-547
+    const double cur_ng = get_gap(g_cur) / d_cur, avg_ng = get_gap(g_avg) / d_avg;
+    if (rp->restart_to_current_metric == FOLP_GAP_OVER_DISTANCE_SQUARED)
+      reset_to_average = (cur_ng / d_cur >= avg_ng / d_avg);
+    else if (rp->restart_to_current_metric == FOLP_GAP_OVER_DISTANCE)
+      reset_to_average = (cur_ng >= avg_ng);
+    else
+      reset_to_average = 1;
+    have_candidate = 1;
+    if (reset_to_average) { candidate_gap = g_avg; candidate_distance = d_avg; }
+    else { candidate_gap = g_cur; candidate_distance = d_cur; }
+  }
+  if (!do_restart) {
+    const double pw = s->primal_weight;
+    if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) {  // sp.jl:549-593
+      const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);
+      BoundResult g_last;
+      if ((rc = euclidean_gap(h, B.last_x, B.last_aty, B.last_y, B.last_ax, wp, wd, d_last,
+                              &g_last)))
+        return rc;
+      const double ncg = get_gap(candidate_gap) / candidate_distance;
+      const double nlg = get_gap(g_last) / d_last;
+      const double ratio = ncg / nlg;
+      if (ratio < rp->necessary_reduction_for_restart) {
+        if (ratio < rp->sufficient_reduction_for_restart) do_restart = 1;
+        else if (ratio > h->gap_reduction_ratio_last_trial) do_restart = 1;
+      }
+      h->gap_reduction_ratio_last_trial = ratio;
+    } else if ((rp->restart_scheme == FOLP_ADAPTIVE_LOCALIZED ||
+                rp->restart_scheme == FOLP_ADAPTIVE_DISTANCE) && !h->has_last_gap) {
+      do_restart = 1;
+    } else if (rp->restart_scheme == FOLP_ADAPTIVE_LOCALIZED) {  // sp.jl:597-620
+      const double new_potential = get_gap(candidate_gap) / static_cast<double>(restart_length);
+      const double old_potential = h->last_gap / static_cast<double>(h->last_restart_length);
+      if (new_potential / old_potential < rp->necessary_reduction_for_restart) do_restart = 1;
+    } else if (rp->restart_scheme == FOLP_ADAPTIVE_DISTANCE) {  // sp.jl:623-648
+      const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);
+      const double new_potential = candidate_distance / static_cast<double>(restart_length);
+      const double old_potential = d_last / static_cast<double>(h->last_restart_length);
+      if (new_potential / old_potential < rp->necessary_reduction_for_restart) do_restart = 1;
+    } else if (rp->restart_scheme == FOLP_FIXED_FREQUENCY &&
+               rp->restart_frequency_if_fixed <= restart_length) {
+      do_restart = 1;
+    }
+  }
+  if (!do_restart) {
+    *choice_out = FOLP_RESTART_CHOICE_NO_RESTART;
+    return FOLP_OK;
+  }
+  launch_apply_restart(B, reset_to_average, have_ax_cur, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 1;
+  s->count_x = s->count_y = 0;  // reset_solution_weighted_average, sp.jl:238-250
+  s->sum_w_x = s->sum_w_y = 0.0;
+  // update_last_restart_info, sp.jl:893-927
+  h->pd_last = avg_px / sqrt(s->primal_weight);
+  h->dd_last = avg_dy * sqrt(s->primal_weight);
+  h->last_restart_length = restart_length;
+  h->has_last_gap = have_candidate;
+  h->last_gap = have_candidate ? get_gap(candidate_gap) : 0.0;
+  *choice_out = reset_to_average ? FOLP_RESTART_CHOICE_RESTART_TO_AVERAGE
+                                 : FOLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
+  return FOLP_OK;
+}
+
+// The evaluation block, pdhg.jl:892-1023. hs holds the current device state.
+static int evaluate(folp_handle* h, folp_eval* out) {
+  DevState* s = h->hs;
+  const folp_params* prm = &h->prm;
+  Bufs& B = h->B;
+  const int64_t iteration = h->iteration;
+  int rc;
+  s->kkt_passes += 2.0;  // :899
+  const int use_current = (s->numerical_error || s->count_x == 0 || s->count_y == 0) ? 1 : 0;
+  if (s->pending_avg) {
+    launch_flush_avg(B, h->stream);
+    h->launches += 2;
+    s->pending_avg = 0;
+  }
+  launch_make_avg(B, use_current, h->stream);
+  launch_spmv_plain(h->A, B.avg_x, B.ax_avg, B.grid_spmv, h->stream);
+  launch_spmv_plain(h->At, B.avg_y, B.aty_avg, B.grid_spmv, h->stream);
+  launch_stats_n(B, B.red, h->stream);
+  launch_stats_m(B, B.red + kMaxScalars, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 5;
+  TRY(cudaMemcpyAsync(h->h_red, B.red, sizeof(double) * 2 * kMaxScalars, cudaMemcpyDeviceToHost,
+                      h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  const double* sn = h->h_red;
+  const double* sm = h->h_red + kMaxScalars;
+
+  folp_eval e;
+  memset(&e, 0, sizeof(e));
+  e.iteration_number = static_cast<int32_t>(iteration - 1);
+  e.candidate_type = FOLP_POINT_TYPE_AVERAGE_ITERATE;
+  e.cumulative_kkt_matrix_passes = s->kkt_passes;
+  e.cumulative_time_sec = now_sec() - h->start_time;
+  const double eps_ratio = prm->eps_optimal_absolute / prm->eps_optimal_relative;
+  const double c0 = h->objective_constant;
+  // compute_convergence_information, isu.jl:228-280
+  e.primal_objective = c0 + sn[SN_cx] + 0.0;
+  e.l_inf_primal_residual = jl_max(jl_max(sm[SM_pres_max], sn[SN_lviol_max]), sn[SN_uviol_max]);
+  e.l2_primal_residual = sqrt(sm[SM_pres2] + sn[SN_lviol2] + sn[SN_uviol2]);
+  e.relative_l_inf_primal_residual = e.l_inf_primal_residual / (eps_ratio + h->cache[1]);
+  e.relative_l2_primal_residual = e.l2_primal_residual / (eps_ratio + h->cache[3]);
+  e.l_inf_primal_variable = sn[SN_x_max];
+  e.l2_primal_variable = sqrt(sn[SN_x2]);
+  e.dual_objective = (sm[SM_by] + c0 - 0.0) + sn[SN_rcobj];
+  e.l_inf_dual_residual = jl_max(sm[SM_yneg_max], sn[SN_dres_max]);
+  e.l2_dual_residual = sqrt(sm[SM_yneg2] + sn[SN_dres2]);
+  e.relative_l_inf_dual_residual = e.l_inf_dual_residual / (eps_ratio + h->cache[0]);
+  e.relative_l2_dual_residual = e.l2_dual_residual / (eps_ratio + h->cache[2]);
+  e.l_inf_dual_variable = sm[SM_y_max];
+  e.l2_dual_variable = sqrt(sm[SM_y2]);
+  e.corrected_dual_objective = (e.l_inf_dual_residual == 0.0) ? e.dual_objective : -INFINITY;
+  {
+    const double gap = fabs(e.primal_objective - e.dual_objective);
+    const double abs_obj = fabs(e.primal_objective) + fabs(e.dual_objective);
+    e.relative_optimality_gap = gap / (eps_ratio + abs_obj);
+  }
+  // compute_infeasibility_information, isu.jl:287-349
+  {
+    const double xs = sn[SN_x_max];
+    const double inv = xs != 0.0 ? xs : 1.0;
+    e.max_primal_ray_infeasibility =
+        jl_max(jl_max(sm[SM_ray_act_max], sn[SN_ray_l_max]), sn[SN_ray_u_max]) / inv;
+    e.primal_ray_linear_objective = sn[SN_cx] / inv;
+    e.primal_ray_quadratic_norm = 0.0;
+    const double dobj = sm[SM_by] + sn[SN_ray_rcobj];
+    const double sf = jl_max(sm[SM_y_max], sn[SN_ray_rc_max]);
+    if (sf != 0.0) {
+      e.max_dual_ray_infeasibility = jl_max(sm[SM_yneg_max], sn[SN_ray_dres_max]) / sf;
+      e.dual_ray_objective = dobj / sf;
+    }
+  }
+  e.step_size = s->step_size;
+  e.primal_weight = s->primal_weight;
+  e.time_spent_doing_basic_algorithm = h->basic_time;  // :929
+  // define_norms, pdhg.jl:265-276
+  const double wp = 1 / s->step_size * s->primal_weight;
+  const double wd = 1 / s->step_size / s->primal_weight;
+  BoundResult at_avg{0, 0, 0};
+  {  // update_objective_bound_estimates, sp.jl:1015-1047
+    const double rp_ = jl_max(1e-8, sqrt(wp * sn[SN_xs2]));
+    const double rd_ = jl_max(1e-8, sqrt(wd * sm[SM_ys2]));
+    const double L = ((0.0 + sn[SN_cs_x]) - sn[SN_x_aty]) + sm[SM_bs_y] + c0;
+    TrProblem Pp{B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp / (rp_ * rp_), wd / (rd_ * rd_), 1.0,
+                 1, 0, 0};
+    TrProblem Pd = Pp;
+    Pd.use_primal = 0; Pd.use_dual = 1;
+    TrState tp, td;
+    if ((rc = tr_solve(h, Pp, &tp))) return rc;
+    if ((rc = tr_solve(h, Pd, &td))) return rc;
+    e.lagrangian_value = L;
+    e.estimated_lower_bound = L + tp.v_primal;
+    e.estimated_upper_bound = L - td.v_dual;
+    at_avg.lagrangian_value = L;
+  }
+  int reason = check_termination(prm, h->cache, &e);  // :947
+  if (s->numerical_error && reason == 0) reason = FOLP_TERMINATION_REASON_NUMERICAL_ERROR;
+  e.termination_reason = reason;
+  e.numerical_error = s->numerical_error;
+  e.total_number_iterations = s->total_iterations;
+  if (reason != 0) {  // :972-993
+    h->terminated = 1;
+    e.restart_used = FOLP_RESTART_CHOICE_UNSPECIFIED;
+    if ((rc = push_state(h))) return rc;
+    h->last_eval = e;
+    *out = e;
+    return FOLP_OK;
+  }
+  int choice = FOLP_RESTART_CHOICE_NO_RESTART;
+  if ((rc = run_restart_scheme(h, iteration - 1, wp, wd, at_avg, &choice))) return rc;  // :995
+  e.restart_used = choice;
+  if (choice != FOLP_RESTART_CHOICE_NO_RESTART) {  // :1009-1017, sp.jl:862-891
+    const double eps = 2.220446049250313e-16;
+    if (h->pd_last > eps && h->dd_last > eps) {
+      const double est = h->dd_last / h->pd_last;
+      const double th = prm->primal_weight_update_smoothing;
+      s->primal_weight = exp(th * log(est) + (1 - th) * log(s->primal_weight));
+    }
+    s->ratio_step_sizes = 1.0;
+  }
+  if ((rc = push_state(h))) return rc;
+  h->need_step = 1;
+  h->last_eval = e;
+  *out = e;
+  return FOLP_OK;
+}
+
+// iterations completed at the next evaluation, pdhg.jl:892-895
+static int64_t next_evaluation(const folp_handle* h, int64_t k) {
+  const int64_t freq = h->prm.termination_evaluation_frequency;
+  int64_t t = (k / freq + 1) * freq;
+  if (k + 1 <= 9) t = std::min(t, k + 1);
+  const int64_t limit = h->prm.iteration_limit;
+  if (limit > k) t = std::min(t, limit);
+  return t;
+}
+
+extern "C" int folp_run(folp_handle* h, folp_eval* out) {
+  if (!h || !out) return FOLP_INVALID_ARGUMENT;
+  if (h->terminated) {
+    *out = h->last_eval;
+    return FOLP_OK;
+  }
+  cudaSetDevice(h->device);
+  int rc;
+  if (h->need_step) {  // :1044, as many take_step calls as fit before the next evaluation
+    const int64_t k = h->hs->iterations;
+    if ((rc = run_steps(h, next_evaluation(h, k)))) return rc;
+    h->need_step = 0;
+  }
+  h->iteration = h->hs->iterations + 1;  // :887
+  return evaluate(h, out);
+}
+
+extern "C" int folp_get_solution(folp_handle* h, int which, int unscaled, double* x_out,
+                                 double* y_out) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  DevState* s = h->hs;
+  Bufs& B = h->B;
+  const double *px, *py;
+  if (which == 0) {  // pdhg.jl:902-910
+    const int use_current = (s->numerical_error || s->count_x == 0 || s->count_y == 0) ? 1 : 0;
+    if (s->pending_avg) {
+      launch_flush_avg(B, h->stream);
+      h->launches += 2;
+      s->pending_avg = 0;
+    }
+    launch_make_avg(B, use_current, h->stream);
+    h->launches += 1;
+    px = B.avg_x; py = B.avg_y;
+  } else {
+    px = B.x[s->cur]; py = B.y[s->cur];
+  }
+  // sp.jl:65-67; tr_t is free scratch outside a trust-region solve
+  launch_scale_div(px, unscaled ? B.D : nullptr, B.tr_t, B.n, B.grid_vec, h->stream);
+  launch_scale_div(py, unscaled ? B.E : nullptr, B.tr_t + B.n, B.m, B.grid_vec, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 2;
+  if (x_out && B.n)
+    TRY(cudaMemcpyAsync(x_out, B.tr_t, sizeof(double) * B.n, cudaMemcpyDeviceToHost, h->stream));
+  if (y_out && B.m)
+    TRY(cudaMemcpyAsync(y_out, B.tr_t + B.n, sizeof(double) * B.m, cudaMemcpyDeviceToHost,
+                        h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  return FOLP_OK;
+}
+
+extern "C" int folp_solve(folp_handle* h, folp_eval* evals, int64_t max_evals, int64_t* num_evals,
+                          int32_t* termination_reason, int32_t* iteration_count, double* x_out,
+                          double* y_out) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  int64_t cnt = 0;
+  folp_eval e;
+  for (;;) {
+    int rc = folp_run(h, &e);
+    if (rc) return rc;
+    if (evals && (h->prm.record_iteration_stats || e.termination_reason != 0)) {  // :958-960
+      if (cnt < max_evals) evals[cnt++] = e;
+      else if (max_evals > 0) evals[max_evals - 1] = e;
+    }
+    if (e.termination_reason != 0) break;
+  }
+  if (num_evals) *num_evals = cnt;
+  if (termination_reason) *termination_reason = e.termination_reason;
+  if (iteration_count) *iteration_count = e.iteration_number;
+  return folp_get_solution(h, 0, 1, x_out, y_out);
+}
+
+// ---------------------------------------------------------------------------
+// test hooks
+// ---------------------------------------------------------------------------
+extern "C" int folp_debug_attempts(folp_handle* h, int64_t attempts) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  DevState* s = h->hs;
+  int rc;
+  if (s->policy == FOLP_STEP_ADAPTIVE) {
+    s->target_iterations = INT64_MAX / 4;
+    s->active = s->numerical_error ? 0 : 1;
+    if ((rc = push_state(h))) return rc;
+    TRY(cudaEventRecord(h->ev0, h->stream));
+    while (attempts > 0) {
+      const int chunk = static_cast<int>(std::min<int64_t>(attempts, 256));
+      if ((rc = enqueue_attempts(h, chunk))) return rc;
+      attempts -= chunk;
+    }
+    TRY(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = pull_state(h))) return rc;
+    float ms = 0.f;
+    TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->basic_time += 1e-3 * ms;
+    return FOLP_OK;
+  }
+  return run_steps(h, s->iterations + attempts);
+}
+
+extern "C" int folp_debug_state(folp_handle* h, double* x, double* y, double* dual_product,
+                                double* sum_x, double* sum_y, folp_debug_scalars* out) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  DevState* s = h->hs;
+  Bufs& B = h->B;
+  if (s->pending_avg) {
+    launch_flush_avg(B, h->stream);
+    h->launches += 2;
+    s->pending_avg = 0;
+  }
+  const size_t nb = sizeof(double) * B.n, mb = sizeof(double) * B.m;
+  if (x && nb) TRY(cudaMemcpyAsync(x, B.x[s->cur], nb, cudaMemcpyDeviceToHost, h->stream));
+  if (y && mb) TRY(cudaMemcpyAsync(y, B.y[s->cur], mb, cudaMemcpyDeviceToHost, h->stream));
+  if (dual_product && nb)
+    TRY(cudaMemcpyAsync(dual_product, B.aty[s->cur], nb, cudaMemcpyDeviceToHost, h->stream));
+  if (sum_x && nb) TRY(cudaMemcpyAsync(sum_x, B.sum_x, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (sum_y && mb) TRY(cudaMemcpyAsync(sum_y, B.sum_y, mb, cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  if (out) {
+    memset(out, 0, sizeof(*out));
+    out->step_size = s->policy == FOLP_STEP_ADAPTIVE ? s->trial_step : s->step_size;
+    out->primal_weight = s->primal_weight;
+    out->cumulative_kkt_passes = s->kkt_passes;
+    out->sum_primal_solution_weights = s->sum_w_x;
+    out->sum_dual_solution_weights = s->sum_w_y;
+    out->total_number_iterations = s->total_iterations;
+    out->iterations_completed = s->count_x;
+    out->sum_primal_solutions_count = s->count_x;
+    out->sum_dual_solutions_count = s->count_y;
+    out->numerical_error = s->numerical_error;
+    out->last_interaction = s->last_interaction;
+    out->last_movement = s->last_movement;
+  }
+  return FOLP_OK;
+}
+
+extern "C" int folp_debug_set_state(folp_handle* h, const double* x, const double* y,
+                                    double step_size, double primal_weight) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  DevState* s = h->hs;
+  Bufs& B = h->B;
+  if (x && B.n)
+    TRY(cudaMemcpyAsync(B.x[s->cur], x, sizeof(double) * B.n, cudaMemcpyHostToDevice, h->stream));
+  if (y && B.m) {
+    TRY(cudaMemcpyAsync(B.y[s->cur], y, sizeof(double) * B.m, cudaMemcpyHostToDevice, h->stream));
+    launch_spmv_plain(h->At, B.y[s->cur], B.aty[s->cur], B.grid_spmv, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 1;
+  }
+  if (step_size > 0) s->step_size = s->trial_step = s->avg_weight = step_size;
+  if (primal_weight > 0) s->primal_weight = primal_weight;
+  int rc = push_state(h);
+  if (rc) return rc;
+  TRY(cudaStreamSynchronize(h->stream));
+  return FOLP_OK;
+}
+
+extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, double* out) {
+  if (!h || !in || !out) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  Bufs& B = h->B;
+  const int len_in = transpose ? B.m : B.n, len_out = transpose ? B.n : B.m;
+  double* d_in = B.tr_t;            // scratch, n+m
+  double* d_out = B.tr_d;
+  if (len_in)
+    TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * len_in, cudaMemcpyHostToDevice, h->stream));
+  launch_spmv_plain(transpose ? h->At : h->A, d_in, d_out, B.grid_spmv, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 1;
+  if (len_out)
+    TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * len_out, cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  return FOLP_OK;
+}
+
+extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
+                                           int64_t* attempts_run) {
+  if (!h || !ms_out) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  DevState* s = h->hs;
+  int rc;
+  s->target_iterations = INT64_MAX / 4;
+  s->active = s->numerical_error ? 0 : 1;
+  if ((rc = push_state(h))) return rc;
+  std::vector<cudaEvent_t> ev(static_cast<size_t>(4 * attempts));
+  for (auto& e : ev) TRY(cudaEventCreate(&e));
+  for (int64_t a = 0; a < attempts; ++a)
+    launch_step_attempt_timed(h->B, h->A, h->At, ev.data() + 4 * a, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 3 * attempts;
+  if ((rc = pull_state(h))) return rc;
+  ms_out[0] = ms_out[1] = ms_out[2] = 0.0;
+  for (int64_t a = 0; a < attempts; ++a)
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      TRY(cudaEventElapsedTime(&ms, ev[4 * a + k], ev[4 * a + k + 1]));
+      ms_out[k] += ms;
+    }
+  for (auto& e : ev) cudaEventDestroy(e);
+  // every attempt does work unless a numerical error stopped the batch early
+  if (attempts_run) *attempts_run = s->numerical_error ? -1 : attempts;
+  return FOLP_OK;
+}
+
+extern "C" void* folp_debug_stream(folp_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+extern "C" int folp_counters(folp_handle* h, int64_t* kernel_launches,
+                             double* basic_algorithm_seconds, int64_t* iterations) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  if (kernel_launches) *kernel_launches = h->launches;
+  if (basic_algorithm_seconds) *basic_algorithm_seconds = h->basic_time;
+  if (iterations) *iterations = h->hs->iterations;
+  return FOLP_OK;
+}

@@ -1,0 +1,211 @@
+// folp_internal.cuh -- shared declarations of libfolp_b200.so (sm_100a only).
+//
+// The library replaces the loop of FirstOrderLp.optimize(::PdhgParameters, qp)
+// (reference: src/primal_dual_hybrid_gradient.jl:862-1048). Everything is fp64;
+// the whole library is compiled with -fmad=false so that element-wise arithmetic
+// rounds exactly like the (non-contracting) Julia reference; only the order of
+// long reductions (norms, dots) differs, see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/folp_b200.h"
+
+namespace folp {
+
+// ---------------------------------------------------------------------------
+// Device-resident solver scalars: PdhgSolverState (pdhg.jl:205-258) minus the
+// vectors, plus the bookkeeping that lets a whole batch of take_step attempts be
+// enqueued without a host round trip.
+// ---------------------------------------------------------------------------
+struct DevState {
+  double step_size;        // solver_state.step_size (value at entry of take_step)
+  double trial_step;       // the local `step_size` of take_step (pdhg.jl:660)
+  double primal_weight;
+  double kkt_passes;       // cumulative_kkt_passes
+  double avg_weight;       // weight of the next accepted iterate = step at entry (:512)
+  double sum_w_x, sum_w_y; // SolutionWeightedAverage weights (sp.jl:215-222)
+  double pending_w;        // weight of the accepted iterate not yet added to sum_x/sum_y
+  double last_interaction, last_movement;
+  double ratio_step_sizes; // Malitsky-Pock
+  double mp_theta;         // extrapolation coefficient of the current attempt
+  double mp_old_step;      // step_size at entry of the MP take_step
+  long long count_x, count_y;
+  long long total_iterations;   // total_number_iterations (counts rejected attempts)
+  long long iterations;         // completed take_step calls
+  long long target_iterations;  // attempts are no-ops once iterations == target
+  int cur;                 // parity of the live x/y/aty buffers
+  int numerical_error;
+  int pending_avg;         // 1: x[cur], y[cur] still have to be added to the sums
+  int active;              // 1: the next attempt does work
+  int mp_need_primal;      // Malitsky-Pock: next attempt starts a new take_step
+  int mp_retries;          // dual retries used in the current MP take_step
+  int policy;              // folp_step_size_policy
+  int reserved;
+  double reduction_exponent, growth_exponent;
+  double downscaling_factor, breaking_factor, interpolation_coefficient;
+};
+
+// ---------------------------------------------------------------------------
+// Tiled CSR matrix. Rows are packed into row-aligned tiles of bounded cost; a
+// row longer than a tile is split into chunks whose partial sums are combined
+// in chunk order by the last chunk to finish (deterministic).
+// ---------------------------------------------------------------------------
+constexpr int kTileNnz = 2048;     // max nonzeros staged per tile
+constexpr int kTileRows = 512;     // max rows per tile
+constexpr int kSpmvThreads = 256;
+constexpr int kTilePad = 8;        // slack for 16-byte aligned bulk copies
+
+enum TileKind : int { kTileThreadPerRow = 0, kTileWarpPerRow = 1, kTileLongChunk = 2 };
+
+struct Tile {
+  int row_begin, row_end;  // rows [row_begin,row_end); long chunk: the single row
+  int nnz_begin, nnz_end;  // nonzeros [nnz_begin,nnz_end)
+  int kind;
+  int long_id;             // index of the long row (kTileLongChunk)
+  int chunk_first;         // index into long_partials of this row's first chunk
+  int chunk_count;         // chunks of this long row
+  int chunk_index;         // which chunk of the long row this tile is
+  int reserved;
+};
+
+struct SpmvMat {
+  int rows = 0, cols = 0;
+  int64_t nnz = 0;
+  int* rowptr = nullptr;     // rows+1 (device)
+  int* colidx = nullptr;     // nnz + pad
+  double* vals = nullptr;    // nnz + pad
+  Tile* tiles = nullptr;
+  int ntiles = 0;
+  int nlong = 0;
+  double* long_partials = nullptr;   // one per long chunk
+  unsigned* long_tickets = nullptr;  // one per long row
+};
+
+// per-kernel partial-reduction scratch
+constexpr int kMaxPartialBlocks = 4096;
+constexpr int kMaxScalars = 32;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+#define FOLP_CUDA_TRY(h, expr)                                                    \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);              \
+      return _e == cudaErrorMemoryAllocation ? FOLP_OUT_OF_MEMORY : FOLP_CUDA_ERROR; \
+    }                                                                             \
+  } while (0)
+
+}  // namespace folp
+
+#ifdef __CUDACC__
+namespace folp {
+
+// ---------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                          uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// deterministic block reductions (fixed shape: shuffle tree, then warp 0)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// result valid in every thread; sh must hold 32 doubles
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = (lane < nwarps) ? sh[lane] : (IS_MAX ? -INFINITY : 0.0);
+  r = IS_MAX ? warp_max(r) : warp_sum(r);
+  return r;
+}
+
+// "last block done" ticket. Every block calls it after writing its partials.
+// Returns true in exactly one block (all threads), with the counter reset.
+__device__ __forceinline__ bool last_block_arrive(unsigned* counter) {
+  __shared__ int s_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(counter, 1u);
+    s_is_last = (t == gridDim.x - 1);
+    if (s_is_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_is_last) __threadfence();
+  return s_is_last != 0;
+}
+
+// Sum (or max) `count` partials with the whole block in a fixed order.
+template <bool IS_MAX>
+__device__ __forceinline__ double reduce_partials(const double* p, int count, double* sh) {
+  double v = IS_MAX ? -INFINITY : 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    double q = __ldcg(p + i);
+    v = IS_MAX ? fmax(v, q) : v + q;
+  }
+  return block_reduce<IS_MAX>(v, sh);
+}
+
+}  // namespace folp
+#endif  // __CUDACC__

@@ -1,0 +1,820 @@
+// folp_kernels.cu -- device code of libfolp_b200.so (sm_100a, fp64, -fmad=false).
+//
+// Per take_step attempt (pdhg.jl:653-731) three kernels run back to back on one
+// stream, all gated by DevState::active so that a batch can be enqueued blind:
+//   k_primal           S1-S3 + extrapolation + deferred primal average + |dx|^2
+//   k_spmv<EpiDual>    S4-S6: A*xbar, dual step, sign projection, deferred dual
+//                      average, |dy|^2
+//   k_spmv<EpiTrans>   A'*y+ (pdhg.jl:492), interaction dot (S7) and, in the last
+//                      CTA to finish, the scalar accept/reject + step-size rule (S8)
+// The evaluation block (pdhg.jl:892-1023) uses the kernels in the second half.
+#include <math_constants.h>
+
+#include "folp_kernels.cuh"
+#include "folp_spmv.cuh"
+
+namespace folp {
+
+constexpr int kVecThreads = 256;
+
+__device__ __forceinline__ double* part_ptr(const Bufs& B, int slot, int scalar) {
+  return B.part + (static_cast<size_t>(slot) * kMaxScalars + scalar) * kMaxPartialBlocks;
+}
+
+// Constant-index selection keeps the kernel parameter struct out of local memory.
+template <class T>
+__device__ __forceinline__ T* sel(T* const (&a)[2], int k) {
+  return k ? a[1] : a[0];
+}
+
+// Trial step and extrapolation coefficient of the attempt about to run.
+__device__ __forceinline__ void attempt_params(const DevState& s, double& trial, double& theta) {
+  if (s.policy == FOLP_STEP_MALITSKY_POCK) {
+    if (s.mp_need_primal) {  // pdhg.jl:580-584
+      trial = s.step_size +
+              s.interpolation_coefficient * (sqrt(1 + s.ratio_step_sizes) - 1) * s.step_size;
+    } else {
+      trial = s.trial_step;
+    }
+    theta = trial / s.step_size;  // pdhg.jl:592
+  } else {
+    trial = s.trial_step;
+    theta = 1.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: compute_next_primal_solution (pdhg.jl:442-470) + xbar (pdhg.jl:486)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
+  __shared__ double sh[32];
+  const DevState& s = *B.st;
+  if (!s.active) return;
+  double trial, theta;
+  attempt_params(s, trial, theta);
+  const bool mp = s.policy == FOLP_STEP_MALITSKY_POCK;
+  const bool do_primal = !mp || s.mp_need_primal;
+  const double f = (mp ? s.step_size : trial) / s.primal_weight;
+  const int cur = s.cur;
+  const double* __restrict__ xc = sel(B.x, cur);
+  double* __restrict__ xn = sel(B.x, cur ^ 1);
+  const double* __restrict__ at = sel(B.aty, cur);
+  const bool pend = s.pending_avg & 1, pend_old = (s.pending_avg & 2) != 0;
+  const double w = s.pending_w, w_old = s.mp_old_step;
+  double acc = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
+    const double x = xc[j];
+    if (pend || pend_old) {  // deferred add_to_primal_solution_weighted_average (sp.jl:252-263)
+      double sx = B.sum_x[j];
+      if (pend_old) sx += xn[j] * w_old;  // xn still holds the previous iterate (pdhg.jl:621-627)
+      if (pend) sx += x * w;
+      B.sum_x[j] = sx;
+    }
+    double xp;
+    if (do_primal) {
+      const double g = B.c[j] - at[j];  // sp.jl:1093-1100 with Q = 0
+      xp = x - f * g;
+      xp = fmin(B.u[j], fmax(B.l[j], xp));  // sp.jl:82-93
+      xn[j] = xp;
+    } else {
+      xp = xn[j];
+    }
+    const double d = xp - x;
+    B.xbar[j] = xp + theta * d;
+    acc += d * d;
+  }
+  const double t = block_reduce<false>(acc, sh);
+  if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 0)[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------
+// scalar rule at the end of an attempt
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double dy2, double inter, double dp2) {
+  DevState s = *st;
+  double trial, theta;
+  attempt_params(s, trial, theta);
+  s.pending_avg = 0;  // K1/K2 of this attempt have applied it
+  bool accepted = false;
+  if (s.policy == FOLP_STEP_ADAPTIVE) {  // pdhg.jl:653-731
+    s.total_iterations += 1;
+    const double ndx = sqrt(dx2), ndy = sqrt(dy2);
+    const double movement =
+        0.5 * s.primal_weight * (ndx * ndx) + (0.5 / s.primal_weight) * (ndy * ndy);
+    const double interaction = fabs(inter);
+    s.last_interaction = interaction;
+    s.last_movement = movement;
+    s.kkt_passes += 1;
+    if (movement == 0.0) {  // :691-695
+      s.numerical_error = 1;
+      s.step_size = trial;  // :730
+      s.iterations += 1;    // the failed take_step call still advances `iteration` (:887)
+    } else {
+      const double limit = interaction > 0 ? movement / interaction : CUDART_INF;
+      accepted = trial <= limit;
+      const double k1 = static_cast<double>(s.total_iterations + 1);
+      const double first = (1 - pow(k1, -s.reduction_exponent)) * limit;
+      const double second = (1 + pow(k1, -s.growth_exponent)) * trial;
+      const double next = fmin(first, second);
+      if (accepted) {
+        s.pending_w = s.avg_weight;  // :512, weight = step size at entry
+        s.step_size = next;
+        s.avg_weight = next;
+      }
+      s.trial_step = next;
+    }
+  } else if (s.policy == FOLP_STEP_CONSTANT) {  // pdhg.jl:737-767
+    s.kkt_passes += 1;
+    accepted = true;
+    s.pending_w = s.step_size;
+  } else {  // Malitsky-Pock, pdhg.jl:555-647
+    if (s.mp_need_primal) {
+      s.kkt_passes += 0.5;
+      s.mp_retries = 0;
+    }
+    s.mp_retries += 1;
+    s.total_iterations += 1;
+    s.kkt_passes += 0.5;
+    const double ratio = theta;
+    if (trial * sqrt(dp2) <= s.breaking_factor * sqrt(dy2)) {  // :615
+      if (s.count_x == 0) {  // :621-627: the previous iterate enters the primal average
+        s.mp_old_step = trial * ratio;
+        s.pending_avg |= 2;
+        s.count_x += 1;
+        s.sum_w_x += s.mp_old_step;
+      }
+      accepted = true;
+      s.pending_w = s.step_size;
+      s.step_size = trial;
+      s.ratio_step_sizes = ratio;
+      s.mp_need_primal = 1;
+    } else {
+      s.trial_step = trial * s.downscaling_factor;
+      s.mp_need_primal = 0;
+      if (s.mp_retries >= 60) {  // :640-643
+        s.numerical_error = 1;
+        s.iterations += 1;
+      }
+    }
+  }
+  if (accepted) {  // update_solution_in_solver_state, pdhg.jl:500-519
+    s.cur ^= 1;
+    s.count_x += 1;
+    s.count_y += 1;
+    s.sum_w_x += s.pending_w;
+    s.sum_w_y += s.pending_w;
+    s.pending_avg |= 1;
+    s.iterations += 1;
+  }
+  s.active = (s.iterations < s.target_iterations && !s.numerical_error) ? 1 : 0;
+  *st = s;
+}
+
+// ---------------------------------------------------------------------------
+// K2 epilogue: dual step on row i given (A*xbar)_i
+// ---------------------------------------------------------------------------
+struct EpiDual {
+  Bufs B;
+  const double* yc;
+  double* yn;
+  double f, w, acc;
+  bool pend;
+  __device__ bool begin() {
+    const DevState& s = *B.st;
+    if (!s.active) return false;
+    double trial, theta;
+    attempt_params(s, trial, theta);
+    f = s.primal_weight * trial;  // pdhg.jl:488
+    yc = sel(B.y, s.cur);
+    yn = sel(B.y, s.cur ^ 1);
+    pend = s.pending_avg & 1;
+    w = s.pending_w;
+    acc = 0.0;
+    return true;
+  }
+  __device__ const double* input() const { return B.xbar; }
+  __device__ void row(int i, double ax) {
+    const double yv = yc[i];
+    if (pend) B.sum_y[i] += yv * w;  // deferred add_to_dual_solution_weighted_average
+    const double g = B.b[i] - ax;    // compute_dual_gradient, sp.jl:1102-1107
+    double yp = yv + f * g;
+    if (i >= B.neq) yp = fmax(yp, 0.0);  // project_dual!, sp.jl:110-117
+    yn[i] = yp;
+    const double d = yp - yv;
+    acc += d * d;
+  }
+  __device__ void finish(double* sh) {
+    const double t = block_reduce<false>(acc, sh);
+    if (threadIdx.x == 0) part_ptr(B, kSlotDual, 0)[blockIdx.x] = t;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K3 epilogue: (A'*y+)_j, interaction dot, and the scalar rule in the last CTA
+// ---------------------------------------------------------------------------
+struct EpiTrans {
+  Bufs B;
+  int g_primal, g_dual;  // grids of K1 and K2 (number of partials they wrote)
+  const double *xc, *xn, *atc;
+  double* atn;
+  double inter, dp2;
+  __device__ bool begin() {
+    const DevState& s = *B.st;
+    if (!s.active) return false;
+    xc = sel(B.x, s.cur);
+    xn = sel(B.x, s.cur ^ 1);
+    atc = sel(B.aty, s.cur);
+    atn = sel(B.aty, s.cur ^ 1);
+    inter = 0.0;
+    dp2 = 0.0;
+    return true;
+  }
+  __device__ const double* input() const { return sel(B.y, B.st->cur ^ 1); }
+  __device__ void row(int j, double at) {
+    atn[j] = at;
+    const double dx = xn[j] - xc[j];
+    const double dat = at - atc[j];
+    inter += dx * dat;  // pdhg.jl:542-544
+    dp2 += dat * dat;   // pdhg.jl:615 (Malitsky-Pock)
+  }
+  __device__ void finish(double* sh) {
+    const double a = block_reduce<false>(inter, sh);
+    const double b = block_reduce<false>(dp2, sh);
+    if (threadIdx.x == 0) {
+      part_ptr(B, kSlotTrans, 0)[blockIdx.x] = a;
+      part_ptr(B, kSlotTrans, 1)[blockIdx.x] = b;
+    }
+    if (!last_block_arrive(B.counters + kSlotTrans)) return;
+    const double dx2 = reduce_partials<false>(part_ptr(B, kSlotPrimal, 0), g_primal, sh);
+    const double dy2 = reduce_partials<false>(part_ptr(B, kSlotDual, 0), g_dual, sh);
+    const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
+    const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
+    if (threadIdx.x == 0) finalize_attempt(B.st, dx2, dy2, it, dp);
+  }
+};
+
+int spmv_configure() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_spmv<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSpmvSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_spmv<EpiDual>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSpmvSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_spmv<EpiTrans>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSpmvSmemBytes);
+  return e;
+}
+
+static int spmv_grid(const SpmvMat& A, int grid_spmv) {
+  int g = A.ntiles < grid_spmv ? A.ntiles : grid_spmv;
+  return g < 1 ? 1 : g;
+}
+
+void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, int attempts,
+                          cudaStream_t s) {
+  const int g1 = B.grid_vec;
+  const int g2 = spmv_grid(A, B.grid_spmv), g3 = spmv_grid(At, B.grid_spmv);
+  EpiDual ed;
+  ed.B = B;
+  EpiTrans et;
+  et.B = B;
+  et.g_primal = g1;
+  et.g_dual = g2;
+  for (int a = 0; a < attempts; ++a) {
+    k_primal<<<g1, kVecThreads, 0, s>>>(B);
+    k_spmv<EpiDual><<<g2, kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
+    k_spmv<EpiTrans><<<g3, kSpmvThreads, kSpmvSmemBytes, s>>>(At, et);
+  }
+}
+
+void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaEvent_t* ev,
+                               cudaStream_t s) {
+  const int g1 = B.grid_vec;
+  const int g2 = spmv_grid(A, B.grid_spmv), g3 = spmv_grid(At, B.grid_spmv);
+  EpiDual ed;
+  ed.B = B;
+  EpiTrans et;
+  et.B = B;
+  et.g_primal = g1;
+  et.g_dual = g2;
+  cudaEventRecord(ev[0], s);
+  k_primal<<<g1, kVecThreads, 0, s>>>(B);
+  cudaEventRecord(ev[1], s);
+  k_spmv<EpiDual><<<g2, kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
+  cudaEventRecord(ev[2], s);
+  k_spmv<EpiTrans><<<g3, kSpmvThreads, kSpmvSmemBytes, s>>>(At, et);
+  cudaEventRecord(ev[3], s);
+}
+
+void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid, cudaStream_t s) {
+  EpiPlain ep;
+  ep.in = in;
+  ep.out = out;
+  k_spmv<EpiPlain><<<spmv_grid(A, grid), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ep);
+}
+
+// ---------------------------------------------------------------------------
+// evaluation block
+// ---------------------------------------------------------------------------
+
+// Applies the deferred average update (if any) so that sum_x / sum_y are current.
+__global__ void __launch_bounds__(kVecThreads) k_flush_avg(Bufs B) {
+  const DevState& s = *B.st;
+  const bool pend = s.pending_avg & 1, pend_old = (s.pending_avg & 2) != 0;
+  if (!pend && !pend_old) return;
+  const double w = s.pending_w, w_old = s.mp_old_step;
+  const double* __restrict__ xc = sel(B.x, s.cur);
+  const double* __restrict__ xo = sel(B.x, s.cur ^ 1);
+  const double* __restrict__ yc = sel(B.y, s.cur);
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
+    double sx = B.sum_x[j];
+    if (pend_old) sx += xo[j] * w_old;
+    if (pend) sx += xc[j] * w;
+    B.sum_x[j] = sx;
+  }
+  if (pend)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.m; i += stride)
+      B.sum_y[i] += yc[i] * w;
+}
+__global__ void k_clear_pending(DevState* st) { st->pending_avg = 0; }
+
+void launch_flush_avg(const Bufs& B, cudaStream_t s) {
+  k_flush_avg<<<B.grid_vec, kVecThreads, 0, s>>>(B);
+  k_clear_pending<<<1, 1, 0, s>>>(B.st);
+}
+
+// compute_average (sp.jl:296-301) or the current iterate (pdhg.jl:902-910)
+__global__ void __launch_bounds__(kVecThreads) k_make_avg(Bufs B, int use_current) {
+  const DevState& s = *B.st;
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (use_current) {
+    const double* __restrict__ xc = sel(B.x, s.cur);
+    const double* __restrict__ yc = sel(B.y, s.cur);
+    for (int j = t0; j < B.n; j += stride) B.avg_x[j] = xc[j];
+    for (int i = t0; i < B.m; i += stride) B.avg_y[i] = yc[i];
+  } else {
+    const double wx = s.sum_w_x, wy = s.sum_w_y;
+    for (int j = t0; j < B.n; j += stride) B.avg_x[j] = B.sum_x[j] / wx;
+    for (int i = t0; i < B.m; i += stride) B.avg_y[i] = B.sum_y[i] / wy;
+  }
+}
+void launch_make_avg(const Bufs& B, int use_current, cudaStream_t s) {
+  k_make_avg<<<B.grid_vec, kVecThreads, 0, s>>>(B, use_current);
+}
+
+// Block-reduces NSUM sums followed by NMAX maxima, and lets the last block
+// produce the final values in red_out[0 .. NSUM+NMAX).
+template <int NSUM, int NMAX>
+__device__ __forceinline__ void reduce_and_publish(const Bufs& B, double* sums, double* maxs,
+                                                   double* red_out, double* sh) {
+  double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
+#pragma unroll
+  for (int k = 0; k < NSUM; ++k) {
+    const double t = block_reduce<false>(sums[k], sh);
+    if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = t;
+  }
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    const double t = block_reduce<true>(maxs[k], sh);
+    if (threadIdx.x == 0)
+      part[static_cast<size_t>(NSUM + k) * kMaxPartialBlocks + blockIdx.x] = t;
+  }
+  if (!last_block_arrive(B.counters + kSlotEval)) return;
+  for (int k = 0; k < NSUM; ++k) {
+    const double t =
+        reduce_partials<false>(part + static_cast<size_t>(k) * kMaxPartialBlocks, gridDim.x, sh);
+    if (threadIdx.x == 0) red_out[k] = t;
+  }
+  for (int k = 0; k < NMAX; ++k) {
+    const double t = reduce_partials<true>(
+        part + static_cast<size_t>(NSUM + k) * kMaxPartialBlocks, gridDim.x, sh);
+    if (threadIdx.x == 0) red_out[NSUM + k] = t;
+  }
+}
+
+// compute_convergence_information / compute_infeasibility_information
+// (isu.jl:228-349) restricted to the variable-indexed terms, evaluated at
+// xhat = avg_x ./ D with A_O' yhat = D .* (A_P' avg_y); plus the pieces of the
+// Lagrangian of the scaled problem (sp.jl:1109-1120).
+__global__ void __launch_bounds__(kVecThreads) k_stats_n(Bufs B, double* red_out) {
+  __shared__ double sh[32];
+  constexpr int NMAX = SN_TOTAL - SN_NSUM;
+  double s[SN_NSUM], mx[NMAX];
+#pragma unroll
+  for (int k = 0; k < SN_NSUM; ++k) s[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) mx[k] = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
+    const double xa = B.avg_x[j], at = B.aty_avg[j], Dj = B.D[j];
+    const double xh = xa / Dj;  // sp.jl:65-67, isu.jl:436
+    const double q = at * Dj;
+    const double c = B.c_orig[j], l = B.l_orig[j], u = B.u_orig[j];
+    s[SN_cx] += c * xh;  // isu.jl:67-74
+    const double lv = fmax(l - xh, 0.0), uv = fmax(xh - u, 0.0);  // isu.jl:52-55
+    s[SN_lviol2] += lv * lv;
+    s[SN_uviol2] += uv * uv;
+    mx[SN_lviol_max - SN_NSUM] = fmax(mx[SN_lviol_max - SN_NSUM], lv);
+    mx[SN_uviol_max - SN_NSUM] = fmax(mx[SN_uviol_max - SN_NSUM], uv);
+    const double g = c - q;  // sp.jl:1081-1091
+    const double bound = g > 0.0 ? l : u;  // isu.jl:128-147
+    const double rc = isfinite(bound) ? g : 0.0;
+    const double dres = g - rc;  // isu.jl:171-178
+    s[SN_dres2] += dres * dres;
+    mx[SN_dres_max - SN_NSUM] = fmax(mx[SN_dres_max - SN_NSUM], fabs(dres));
+    if (rc != 0.0) s[SN_rcobj] += bound * rc;  // isu.jl:93-117
+    s[SN_x2] += xh * xh;
+    mx[SN_x_max - SN_NSUM] = fmax(mx[SN_x_max - SN_NSUM], fabs(xh));
+    // primal ray, bounds of the homogeneous problem (isu.jl:301-313); scaled by
+    // 1/|xhat|_inf on the host (positively homogeneous)
+    if (isfinite(l)) mx[SN_ray_l_max - SN_NSUM] = fmax(mx[SN_ray_l_max - SN_NSUM], -xh);
+    if (isfinite(u)) mx[SN_ray_u_max - SN_NSUM] = fmax(mx[SN_ray_u_max - SN_NSUM], xh);
+    // dual ray: objective vector and matrix zeroed (isu.jl:319-330)
+    const double g2 = -q;
+    const double bound2 = g2 > 0.0 ? l : u;
+    const double rc2 = isfinite(bound2) ? g2 : 0.0;
+    mx[SN_ray_dres_max - SN_NSUM] = fmax(mx[SN_ray_dres_max - SN_NSUM], fabs(g2 - rc2));
+    mx[SN_ray_rc_max - SN_NSUM] = fmax(mx[SN_ray_rc_max - SN_NSUM], fabs(rc2));
+    if (rc2 != 0.0) s[SN_ray_rcobj] += bound2 * rc2;
+    // scaled problem
+    s[SN_cs_x] += xa * B.c[j];
+    s[SN_x_aty] += xa * at;
+    s[SN_xs2] += xa * xa;
+  }
+  reduce_and_publish<SN_NSUM, NMAX>(B, s, mx, red_out, sh);
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_stats_m(Bufs B, double* red_out) {
+  __shared__ double sh[32];
+  constexpr int NMAX = SM_TOTAL - SM_NSUM;
+  double s[SM_NSUM], mx[NMAX];
+#pragma unroll
+  for (int k = 0; k < SM_NSUM; ++k) s[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) mx[k] = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.m; i += stride) {
+    const double ya = B.avg_y[i], ax = B.ax_avg[i], Ei = B.E[i];
+    const double yh = ya / Ei;
+    const double act = ax * Ei;  // A_O xhat = E .* (A_P avg_x)
+    const double b = B.b_orig[i];
+    double r = b - act;  // isu.jl:36-50
+    const bool ineq = i >= B.neq;
+    if (ineq) r = fmax(r, 0.0);
+    s[SM_pres2] += r * r;
+    mx[SM_pres_max - SM_NSUM] = fmax(mx[SM_pres_max - SM_NSUM], fabs(r));
+    s[SM_by] += b * yh;
+    s[SM_y2] += yh * yh;
+    mx[SM_y_max - SM_NSUM] = fmax(mx[SM_y_max - SM_NSUM], fabs(yh));
+    if (ineq) {
+      const double yn = fmax(-yh, 0.0);  // isu.jl:171-173
+      s[SM_yneg2] += yn * yn;
+      mx[SM_yneg_max - SM_NSUM] = fmax(mx[SM_yneg_max - SM_NSUM], yn);
+      mx[SM_ray_act_max - SM_NSUM] = fmax(mx[SM_ray_act_max - SM_NSUM], -act);
+    } else {
+      mx[SM_ray_act_max - SM_NSUM] = fmax(mx[SM_ray_act_max - SM_NSUM], fabs(act));
+    }
+    s[SM_bs_y] += ya * B.b[i];
+    s[SM_ys2] += ya * ya;
+  }
+  reduce_and_publish<SM_NSUM, NMAX>(B, s, mx, red_out, sh);
+}
+
+// squared distances of the average and of the current iterate to the last
+// restart point (sp.jl:444-488, :911-920)
+__global__ void __launch_bounds__(kVecThreads) k_dist(Bufs B, double* red_out) {
+  __shared__ double sh[32];
+  double s[SD_TOTAL] = {0.0, 0.0, 0.0, 0.0};
+  double mx[1] = {0.0};
+  const DevState& st = *B.st;
+  const double* __restrict__ xc = sel(B.x, st.cur);
+  const double* __restrict__ yc = sel(B.y, st.cur);
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = t0; j < B.n; j += stride) {
+    const double lx = B.last_x[j];
+    const double da = B.avg_x[j] - lx, dc = xc[j] - lx;
+    s[SD_avg_x] += da * da;
+    s[SD_cur_x] += dc * dc;
+  }
+  for (int i = t0; i < B.m; i += stride) {
+    const double ly = B.last_y[i];
+    const double da = B.avg_y[i] - ly, dc = yc[i] - ly;
+    s[SD_avg_y] += da * da;
+    s[SD_cur_y] += dc * dc;
+  }
+  reduce_and_publish<SD_TOTAL, 0>(B, s, mx, red_out, sh);
+}
+
+void launch_stats_n(const Bufs& B, double* red_out, cudaStream_t s) {
+  k_stats_n<<<B.grid_vec, kVecThreads, 0, s>>>(B, red_out);
+}
+void launch_stats_m(const Bufs& B, double* red_out, cudaStream_t s) {
+  k_stats_m<<<B.grid_vec, kVecThreads, 0, s>>>(B, red_out);
+}
+void launch_dist(const Bufs& B, double* red_out, cudaStream_t s) {
+  k_dist<<<B.grid_vec, kVecThreads, 0, s>>>(B, red_out);
+}
+
+// The vector half of a restart (sp.jl:804-825, :921-923, pdhg.jl:1018-1022).
+__global__ void __launch_bounds__(kVecThreads) k_apply_restart(Bufs B, int to_average,
+                                                               int have_ax_cur) {
+  const DevState& st = *B.st;
+  double* __restrict__ xc = sel(B.x, st.cur);
+  double* __restrict__ yc = sel(B.y, st.cur);
+  double* __restrict__ atc = sel(B.aty, st.cur);
+  const int stride = gridDim.x * blockDim.x;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = t0; j < B.n; j += stride) {
+    if (to_average) {
+      xc[j] = B.avg_x[j];
+      atc[j] = B.aty_avg[j];  // = A' * avg_y, what pdhg.jl:1021 recomputes
+    }
+    B.sum_x[j] = 0.0;
+    B.last_x[j] = xc[j];
+    B.last_aty[j] = atc[j];
+  }
+  for (int i = t0; i < B.m; i += stride) {
+    if (to_average) yc[i] = B.avg_y[i];
+    B.sum_y[i] = 0.0;
+    B.last_y[i] = yc[i];
+    if (to_average) B.last_ax[i] = B.ax_avg[i];
+    else if (have_ax_cur) B.last_ax[i] = B.ax_cur[i];
+  }
+}
+void launch_apply_restart(const Bufs& B, int to_average, int have_ax_cur, cudaStream_t s) {
+  k_apply_restart<<<B.grid_vec, kVecThreads, 0, s>>>(B, to_average, have_ax_cur);
+}
+
+// ---------------------------------------------------------------------------
+// bound-constrained trust region (tr.jl:68-224) by safeguarded Newton passes.
+//
+// With h_i = w_i d_i^2 and thresholds t_i, rho^2(tau) = L(tau) + tau^2 H(tau),
+// L(tau) = sum_{t_i <= tau} h_i t_i^2, H(tau) = sum_{t_i > tau} h_i, is the
+// squared weighted radius reached at threshold tau. The reference finds the
+// tau with rho^2 = r^2 by repeated medians; as a function of tau^2 it is
+// concave piecewise linear, so Newton from the left, tau <- sqrt((r^2-L)/H)
+// with the partition induced by the previous tau, increases monotonically and
+// stops exactly when the partition stops changing -- at the same tau up to
+// rounding. A bisection probe in bit-pattern space bounds the pass count.
+// ---------------------------------------------------------------------------
+enum TrInit {
+  TI_g2 = 0, TI_H0, TI_Hinf, TI_Ltot, TI_cnt0, TI_cx, TI_xaty, TI_yb, TI_norm2, TI_gdp, TI_gdd,
+  TI_NSUM, TI_max_t = TI_NSUM, TI_TOTAL
+};
+
+struct TrElem {
+  double x0, g, lb, ub, w;
+};
+__device__ __forceinline__ TrElem tr_elem(const Bufs& B, const TrProblem& P, int idx) {
+  TrElem e;
+  if (idx < B.n) {
+    e.x0 = P.px[idx];
+    e.g = B.c[idx] - P.atp[idx];  // sp.jl:1081-1091 (Q = 0)
+    e.lb = B.l[idx];
+    e.ub = B.u[idx];
+    e.w = P.wp;
+  } else {
+    const int i = idx - B.n;
+    e.x0 = P.py[i];
+    e.g = -(B.b[i] - P.axp[i]);  // tr.jl:291, :312
+    e.lb = i < B.neq ? -CUDART_INF : 0.0;  // tr.jl:288-290
+    e.ub = CUDART_INF;
+    e.w = P.wd;
+  }
+  return e;
+}
+__device__ __forceinline__ double jl_clamp(double x, double lo, double hi) {
+  return x > hi ? hi : (x < lo ? lo : x);
+}
+__device__ __forceinline__ double bit_mid(double a, double b) {
+  const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+  return __longlong_as_double(ia + (ib - ia) / 2);
+}
+
+__device__ void tr_next_candidates(TrState& t) {
+  double num = t.r2 - t.L_lo;
+  if (num < 0.0) num = 0.0;
+  double c0 = sqrt(num / t.H_lo);
+  if (c0 > t.hi) c0 = t.hi;
+  if (c0 < t.lo) c0 = t.lo;
+  t.cand[0] = c0;
+  t.cand[1] = bit_mid(c0, t.hi);
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_tr_init(Bufs B, TrProblem P, TrState* trs,
+                                                         double* red) {
+  __shared__ double sh[32];
+  double s[TI_NSUM], mx[1] = {0.0};
+#pragma unroll
+  for (int k = 0; k < TI_NSUM; ++k) s[k] = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  const int total = B.n + B.m;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const bool primal = idx < B.n;
+    const TrElem e = tr_elem(B, P, idx);
+    if (primal) {  // compute_lagrangian_value, sp.jl:1109-1120
+      s[TI_cx] += e.x0 * B.c[idx];
+      s[TI_xaty] += e.x0 * P.atp[idx];
+    } else {
+      s[TI_yb] += e.x0 * B.b[idx - B.n];
+    }
+    if (primal ? !P.use_primal : !P.use_dual) continue;
+    s[TI_g2] += e.g * e.g;
+    const bool skip = (e.x0 >= e.ub && e.g <= 0.0) || (e.x0 <= e.lb && e.g >= 0.0);  // tr.jl:96-103
+    const double d = skip ? 0.0 : -e.g / e.w;
+    B.tr_d[idx] = d;
+    if (P.approx) {  // tr.jl:194-224
+      s[TI_norm2] += e.w * d * d;
+      if (primal) s[TI_gdp] += e.g * d;
+      else s[TI_gdd] += e.g * d;
+      continue;
+    }
+    double t = 0.0;  // tr.jl:104-116
+    if (d > 0.0) t = (e.ub - e.x0) / d;
+    else if (d < 0.0) t = (e.lb - e.x0) / d;
+    B.tr_t[idx] = t;
+    const double h = e.w * d * d;
+    if (isinf(t)) {
+      s[TI_Hinf] += h;
+      s[TI_H0] += h;
+    } else {
+      if (t > 0.0) s[TI_H0] += h;
+      else s[TI_cnt0] += 1.0;
+      s[TI_Ltot] += h * t * t;
+      mx[0] = fmax(mx[0], t);
+    }
+  }
+  // publish through the generic path into `red`, then thread 0 of the last
+  // block (the only one that returns with values) sets up the search
+  double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
+#pragma unroll
+  for (int k = 0; k < TI_NSUM; ++k) {
+    const double v = block_reduce<false>(s[k], sh);
+    if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = v;
+  }
+  {
+    const double v = block_reduce<true>(mx[0], sh);
+    if (threadIdx.x == 0) part[static_cast<size_t>(TI_max_t) * kMaxPartialBlocks + blockIdx.x] = v;
+  }
+  if (!last_block_arrive(B.counters + kSlotEval)) return;
+  double r[TI_TOTAL];
+  for (int k = 0; k < TI_NSUM; ++k)
+    r[k] = reduce_partials<false>(part + static_cast<size_t>(k) * kMaxPartialBlocks, gridDim.x, sh);
+  r[TI_max_t] = reduce_partials<true>(part + static_cast<size_t>(TI_max_t) * kMaxPartialBlocks,
+                                      gridDim.x, sh);
+  if (threadIdx.x != 0) return;
+  for (int k = 0; k < TI_TOTAL; ++k) red[k] = r[k];
+  TrState t;
+  t.radius = P.radius;
+  t.r2 = P.radius * P.radius;
+  t.lo = 0.0; t.L_lo = 0.0; t.H_lo = r[TI_H0];
+  t.cnt_lo = static_cast<long long>(r[TI_cnt0]);
+  t.hi = r[TI_max_t];
+  t.max_t = r[TI_max_t];
+  t.cand[0] = t.cand[1] = 0.0;
+  t.tau = 0.0;
+  t.done = 0; t.zero_value = 0; t.approx = P.approx; t.passes = 0;
+  t.approx_scale = 1.0;
+  t.cx = r[TI_cx]; t.x_aty = r[TI_xaty]; t.y_b = r[TI_yb];
+  t.v_primal = 0.0; t.v_dual = 0.0;
+  if (P.approx) {
+    const double nrm = sqrt(r[TI_norm2]);
+    if (nrm > 0.0) t.approx_scale = P.radius / nrm;
+    t.v_primal = r[TI_gdp] * t.approx_scale;
+    t.v_dual = r[TI_gdd] * t.approx_scale;
+    t.done = 1; t.zero_value = 1;  // no final pass needed
+  } else if (P.radius == 0.0 || r[TI_g2] == 0.0 || r[TI_H0] == 0.0) {  // tr.jl:88-91
+    t.done = 1; t.zero_value = 1;
+  } else if (r[TI_Hinf] == 0.0 && r[TI_Ltot] < t.r2) {  // everything reaches its bound, tr.jl:175-177
+    t.tau = t.max_t; t.done = 1;
+  } else if (r[TI_Hinf] > 0.0 && r[TI_Ltot] <= t.r2 &&
+             sqrt((t.r2 - r[TI_Ltot]) / r[TI_Hinf]) >= t.max_t) {
+    t.tau = sqrt((t.r2 - r[TI_Ltot]) / r[TI_Hinf]); t.done = 1;
+  } else {
+    tr_next_candidates(t);
+  }
+  *trs = t;
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_tr_pass(Bufs B, TrProblem P, TrState* trs) {
+  __shared__ double sh[32];
+  if (trs->done) return;
+  const double c0 = trs->cand[0], c1 = trs->cand[1];
+  double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // L0,H0,cnt0,L1,H1,cnt1
+  double mx[1] = {0.0};
+  const int begin = P.use_primal ? 0 : B.n;
+  const int end = P.use_dual ? B.n + B.m : B.n;
+  const int stride = gridDim.x * blockDim.x;
+  for (int idx = begin + blockIdx.x * blockDim.x + threadIdx.x; idx < end; idx += stride) {
+    const double t = B.tr_t[idx], d = B.tr_d[idx];
+    const double h = (idx < B.n ? P.wp : P.wd) * d * d;
+    const double lt = h * t * t;
+    if (t <= c0) { s[0] += lt; s[2] += 1.0; } else { s[1] += h; }
+    if (t <= c1) { s[3] += lt; s[5] += 1.0; } else { s[4] += h; }
+  }
+  double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double v = block_reduce<false>(s[k], sh);
+    if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = v;
+  }
+  (void)mx;
+  if (!last_block_arrive(B.counters + kSlotEval)) return;
+  double r[6];
+  for (int k = 0; k < 6; ++k)
+    r[k] = reduce_partials<false>(part + static_cast<size_t>(k) * kMaxPartialBlocks, gridDim.x, sh);
+  if (threadIdx.x != 0) return;
+  TrState t = *trs;
+  t.passes += 1;
+  const long long cnt0 = static_cast<long long>(r[2]), cnt1 = static_cast<long long>(r[5]);
+  if (cnt0 == t.cnt_lo) {  // partition unchanged: cand[0] is the fixed point
+    t.tau = c0;
+    t.done = 1;
+  } else {
+    t.lo = c0; t.L_lo = r[0]; t.H_lo = r[1]; t.cnt_lo = cnt0;
+    if (c1 > c0 && c1 < t.hi) {
+      const double F1 = r[3] + c1 * c1 * r[4];
+      if (F1 < t.r2) { t.lo = c1; t.L_lo = r[3]; t.H_lo = r[4]; t.cnt_lo = cnt1; }
+      else t.hi = c1;
+    }
+    if (t.H_lo <= 0.0) {  // nothing left above lo
+      t.tau = t.max_t;
+      t.done = 1;
+    } else {
+      tr_next_candidates(t);
+    }
+  }
+  *trs = t;
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_tr_final(Bufs B, TrProblem P, TrState* trs) {
+  __shared__ double sh[32];
+  if (!trs->done || trs->zero_value) return;
+  const double tau = trs->tau;
+  double s[2] = {0.0, 0.0};
+  double mx[1] = {0.0};
+  const int begin = P.use_primal ? 0 : B.n;
+  const int end = P.use_dual ? B.n + B.m : B.n;
+  const int stride = gridDim.x * blockDim.x;
+  for (int idx = begin + blockIdx.x * blockDim.x + threadIdx.x; idx < end; idx += stride) {
+    const TrElem e = tr_elem(B, P, idx);
+    const double sol = jl_clamp(e.x0 + tau * B.tr_d[idx], e.lb, e.ub);  // tr.jl:182-188
+    const double v = e.g * (sol - e.x0);
+    if (idx < B.n) s[0] += v;
+    else s[1] += v;
+  }
+  double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double v = block_reduce<false>(s[k], sh);
+    if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = v;
+  }
+  (void)mx;
+  if (!last_block_arrive(B.counters + kSlotEval)) return;
+  const double vp = reduce_partials<false>(part, gridDim.x, sh);
+  const double vd = reduce_partials<false>(part + kMaxPartialBlocks, gridDim.x, sh);
+  if (threadIdx.x == 0) {
+    trs->v_primal = vp;
+    trs->v_dual = vd;
+  }
+}
+
+void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bool init,
+               cudaStream_t s) {
+  if (init) k_tr_init<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs, B.red);
+  for (int p = 0; p < passes; ++p) k_tr_pass<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
+  k_tr_final<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
+}
+
+// ---------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVecThreads) k_scale_div(const double* __restrict__ in,
+                                                           const double* __restrict__ scale,
+                                                           double* __restrict__ out, int len) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+    out[i] = scale ? in[i] / scale[i] : in[i];
+}
+void launch_scale_div(const double* in, const double* scale, double* out, int len, int grid,
+                      cudaStream_t s) {
+  k_scale_div<<<grid, kVecThreads, 0, s>>>(in, scale, out, len);
+}
+__global__ void __launch_bounds__(kVecThreads) k_fill(double* p, double v, int64_t len) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride)
+    p[i] = v;
+}
+void launch_fill(double* p, double v, int64_t len, cudaStream_t s) {
+  if (len <= 0) return;
+  int64_t g = (len + kVecThreads - 1) / kVecThreads;
+  if (g > 1184) g = 1184;
+  k_fill<<<static_cast<int>(g), kVecThreads, 0, s>>>(p, v, len);
+}
+
+}  // namespace folp

@@ -1,0 +1,92 @@
+// folp_kernels.cuh -- launch interface between folp_api.cu (host logic) and
+// folp_kernels.cu (device code).
+#pragma once
+#include "folp_internal.cuh"
+
+namespace folp {
+
+// Device pointers of one rank. Lengths: n_loc primal slice, m_loc dual rows.
+struct Bufs {
+  int n = 0, m = 0, neq = 0;  // local primal slice length, local rows, local equalities
+  DevState* st = nullptr;
+  double *x[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr}, *aty[2] = {nullptr, nullptr};
+  double* xbar = nullptr;                    // extrapolated primal, gathered by A*xbar
+  double *c = nullptr, *l = nullptr, *u = nullptr, *b = nullptr;  // scaled problem
+  double *sum_x = nullptr, *sum_y = nullptr;
+  // evaluation
+  double *avg_x = nullptr, *avg_y = nullptr, *ax_avg = nullptr, *aty_avg = nullptr;
+  double* ax_cur = nullptr;
+  double *last_x = nullptr, *last_y = nullptr, *last_ax = nullptr, *last_aty = nullptr;
+  double *D = nullptr, *E = nullptr;         // variable_rescaling, constraint_rescaling
+  double *c_orig = nullptr, *l_orig = nullptr, *u_orig = nullptr, *b_orig = nullptr;
+  double *tr_t = nullptr, *tr_d = nullptr;   // trust-region scratch, n+m each
+  // reductions
+  double* part = nullptr;     // kMaxScalars * kMaxPartialBlocks doubles per slot, 4 slots
+  double* red = nullptr;      // reduced scalars, kMaxScalars per slot
+  unsigned* counters = nullptr;
+  int grid_vec = 0, grid_spmv = 0;
+};
+
+constexpr int kSlotPrimal = 0, kSlotDual = 1, kSlotTrans = 2, kSlotEval = 3;
+constexpr int kNumSlots = 4;
+
+// n-pass statistics (isu.jl:228-349 on the original problem + Lagrangian pieces)
+enum StatN {
+  SN_cx = 0, SN_lviol2, SN_uviol2, SN_dres2, SN_rcobj, SN_x2, SN_ray_rcobj, SN_cs_x, SN_x_aty,
+  SN_xs2, SN_NSUM,
+  SN_lviol_max = SN_NSUM, SN_uviol_max, SN_dres_max, SN_x_max, SN_ray_l_max, SN_ray_u_max,
+  SN_ray_dres_max, SN_ray_rc_max, SN_TOTAL
+};
+enum StatM {
+  SM_pres2 = 0, SM_by, SM_y2, SM_yneg2, SM_bs_y, SM_ys2, SM_NSUM,
+  SM_pres_max = SM_NSUM, SM_y_max, SM_yneg_max, SM_ray_act_max, SM_TOTAL
+};
+enum StatDist { SD_avg_x = 0, SD_cur_x, SD_avg_y, SD_cur_y, SD_TOTAL };
+
+// Trust-region solve state (tr.jl:68-224), device resident.
+struct TrState {
+  double radius, r2;
+  double lo, L_lo, H_lo;
+  long long cnt_lo;
+  double hi;
+  double cand[2];
+  double tau;        // final threshold
+  double max_t;
+  int done;          // 1: tau is final
+  int zero_value;    // 1: solution == center (value 0)
+  int approx;
+  int passes;
+  double approx_scale;
+  // Lagrangian pieces and results
+  double cx, x_aty, y_b;
+  double v_primal, v_dual;  // objective_vector . (solution - center), per segment
+};
+
+struct TrProblem {
+  const double *px, *atp;   // primal center and A' * dual center
+  const double *py, *axp;   // dual center and A * primal center
+  double wp, wd, radius;
+  int use_primal, use_dual, approx;
+};
+
+void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, int attempts,
+                          cudaStream_t s);
+// one attempt with events ev[0..3] recorded before/between/after the three kernels
+void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaEvent_t* ev,
+                               cudaStream_t s);
+void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid, cudaStream_t s);
+void launch_flush_avg(const Bufs& B, cudaStream_t s);
+void launch_make_avg(const Bufs& B, int use_current, cudaStream_t s);
+// results in B.red + kSlotEval*kMaxScalars ... see folp_api.cu
+void launch_stats_n(const Bufs& B, double* red_out, cudaStream_t s);
+void launch_stats_m(const Bufs& B, double* red_out, cudaStream_t s);
+void launch_dist(const Bufs& B, double* red_out, cudaStream_t s);
+void launch_apply_restart(const Bufs& B, int to_average, int have_ax_cur, cudaStream_t s);
+void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bool init,
+               cudaStream_t s);
+void launch_scale_div(const double* in, const double* scale, double* out, int len, int grid,
+                      cudaStream_t s);
+void launch_fill(double* p, double v, int64_t len, cudaStream_t s);
+int spmv_configure();  // sets the dynamic shared memory attribute; returns cudaError_t
+
+}  // namespace folp

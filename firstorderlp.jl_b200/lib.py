@@ -1,0 +1,187 @@
+"""ctypes binding of libfolp_b200.so (the C ABI of include/folp_b200.h).
+
+This is what the Julia host would do with `ccall`; see INTEGRATION.md. There
+is no CPU fallback: if the shared library is missing or no sm_100 device is
+present, `Solver` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from ._abi import FolpDebugScalars, FolpDist, FolpEval, FolpParams, FolpProblem, Status
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfolp_b200.so")
+_pd = C.POINTER(C.c_double)
+_LIB: Optional[C.CDLL] = None
+
+EXPORTS = [
+    "folp_nccl_unique_id", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
+    "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
+    "folp_debug_profile_attempts", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
+]
+
+
+class FolpError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libfolp_b200: {Status(status).name}: {message}")
+        self.status = Status(status)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "folp_b200.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in srcs)
+    if force or stale:
+        cmd = ["make", "-C", csrc, "-j4"] + (["-B"] if force else [])
+        subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL,
+                              stderr=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Loads libfolp_b200.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "folp_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.folp_nccl_unique_id.argtypes = [C.c_void_p]
+        L.folp_create.argtypes = [C.POINTER(FolpProblem), C.POINTER(FolpParams), C.POINTER(FolpDist),
+                                  C.POINTER(C.c_void_p)]
+        L.folp_run.argtypes = [C.c_void_p, C.POINTER(FolpEval)]
+        L.folp_solve.argtypes = [C.c_void_p, C.POINTER(FolpEval), C.c_int64, C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32), _pd, _pd]
+        L.folp_get_solution.argtypes = [C.c_void_p, C.c_int, C.c_int, _pd, _pd]
+        L.folp_debug_attempts.argtypes = [C.c_void_p, C.c_int64]
+        L.folp_debug_state.argtypes = [C.c_void_p, _pd, _pd, _pd, _pd, _pd, C.POINTER(FolpDebugScalars)]
+        L.folp_debug_set_state.argtypes = [C.c_void_p, _pd, _pd, C.c_double, C.c_double]
+        L.folp_debug_spmv.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
+        L.folp_debug_profile_attempts.argtypes = [C.c_void_p, C.c_int64, _pd, C.POINTER(C.c_int64)]
+        L.folp_debug_stream.argtypes = [C.c_void_p]
+        L.folp_debug_stream.restype = C.c_void_p
+        L.folp_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), _pd, C.POINTER(C.c_int64)]
+        L.folp_destroy.argtypes = [C.c_void_p]
+        L.folp_destroy.restype = None
+        L.folp_last_error.argtypes = [C.c_void_p]
+        L.folp_last_error.restype = C.c_char_p
+        L.folp_build_info.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def build_info() -> str:
+    return lib().folp_build_info().decode()
+
+
+def _d(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_pd)
+
+
+class Solver:
+    """One folp_handle: the device-resident PDHG state of one optimize() call."""
+
+    def __init__(self, problem_holder, params: FolpParams, dist: Optional[FolpDist] = None):
+        self._holder = problem_holder
+        self.params = params
+        self.n = problem_holder.struct.num_variables
+        self.m = problem_holder.struct.num_constraints
+        self._h = C.c_void_p()
+        L = lib()
+        rc = L.folp_create(problem_holder.byref(), C.byref(params),
+                           C.byref(dist) if dist is not None else None, C.byref(self._h))
+        if rc != 0:
+            raise FolpError(rc, L.folp_last_error(None).decode())
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise FolpError(rc, lib().folp_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().folp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def run(self) -> FolpEval:
+        e = FolpEval()
+        self._check(lib().folp_run(self._h, C.byref(e)))
+        return e
+
+    def solve(self, max_evals: int = 1 << 16):
+        evals = (FolpEval * max_evals)()
+        n_ev = C.c_int64()
+        reason = C.c_int32()
+        iters = C.c_int32()
+        x = np.zeros(self.n)
+        y = np.zeros(self.m)
+        self._check(lib().folp_solve(self._h, evals, max_evals, C.byref(n_ev), C.byref(reason),
+                                     C.byref(iters), _p(x), _p(y)))
+        return x, y, reason.value, iters.value, [evals[i] for i in range(n_ev.value)]
+
+    def get_solution(self, which=0, unscaled=True):
+        x = np.zeros(self.n)
+        y = np.zeros(self.m)
+        self._check(lib().folp_get_solution(self._h, which, int(unscaled), _p(x), _p(y)))
+        return x, y
+
+    def debug_attempts(self, k: int):
+        self._check(lib().folp_debug_attempts(self._h, k))
+
+    def debug_state(self):
+        x = np.zeros(self.n); y = np.zeros(self.m); aty = np.zeros(self.n)
+        sx = np.zeros(self.n); sy = np.zeros(self.m)
+        s = FolpDebugScalars()
+        self._check(lib().folp_debug_state(self._h, _p(x), _p(y), _p(aty), _p(sx), _p(sy), C.byref(s)))
+        return {"x": x, "y": y, "dual_product": aty, "sum_x": sx, "sum_y": sy, **s.as_dict()}
+
+    def debug_set_state(self, x, y, step_size=-1.0, primal_weight=-1.0):
+        x = None if x is None else _d(x)
+        y = None if y is None else _d(y)
+        self._check(lib().folp_debug_set_state(self._h, _p(x), _p(y), step_size, primal_weight))
+
+    def spmv(self, v, transpose=False):
+        v = _d(v)
+        out = np.zeros(self.n if transpose else self.m)
+        self._check(lib().folp_debug_spmv(self._h, int(transpose), _p(v), _p(out)))
+        return out
+
+    def profile_attempts(self, attempts: int):
+        """Device ms spent in {primal, A*xbar+dual, A'*y+rule} over `attempts` attempts."""
+        ms = (C.c_double * 3)()
+        ran = C.c_int64()
+        self._check(lib().folp_debug_profile_attempts(self._h, attempts, ms, C.byref(ran)))
+        return [ms[0], ms[1], ms[2]], ran.value
+
+    def stream(self) -> int:
+        return int(lib().folp_debug_stream(self._h) or 0)
+
+    def counters(self):
+        k = C.c_int64(); t = C.c_double(); it = C.c_int64()
+        self._check(lib().folp_counters(self._h, C.byref(k), C.cast(C.byref(t), _pd), C.byref(it)))
+        return {"kernel_launches": k.value, "basic_algorithm_seconds": t.value, "iterations": it.value}

@@ -1,0 +1,93 @@
+"""optimize(params::PdhgParameters, qp) -- the entry point the B200 path keeps.
+
+Mirrors src/primal_dual_hybrid_gradient.jl:782-1049: the host half (:786-859:
+validate, cached norms, rescale_problem, initial step size, initial primal
+weight) runs here exactly as the reference's Julia host does; the loop
+(:862-1048) runs in libfolp_b200.so through the C ABI. No CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _abi, _marshal
+from .lib import Solver
+from .params import (
+    AdaptiveStepsizeParams,
+    MalitskyPockStepsizeParameters,
+    PdhgParameters,
+)
+from .preprocess import rescale_problem
+from .problem import (
+    QuadraticProgrammingProblem,
+    ScaledQpProblem,
+    cached_quadratic_program_info,
+    validate,
+)
+from .solve_log import SaddlePointOutput, iteration_stats_from_eval, termination_reason_to_string
+
+
+def power_method_failure_probability(dimension: int, epsilon: float, k: int) -> float:
+    """src/primal_dual_hybrid_gradient.jl:379-391"""
+    if k < 2 or epsilon <= 0.0:
+        return 1.0
+    return (min(0.824, 0.354 / math.sqrt(epsilon * (k - 1))) * math.sqrt(dimension)
+            * (1.0 - epsilon) ** (k - 1 / 2))
+
+
+def estimate_maximum_singular_value(matrix, probability_of_failure=0.001,
+                                    desired_relative_error=0.2, seed=1):
+    """src/primal_dual_hybrid_gradient.jl:414-440. The start vector of the
+    reference comes from Julia's MersenneTwister(seed) randn stream, which is
+    not reproducible outside Julia; NumPy's legacy MT19937 normal stream is used
+    (parity of this value is unpinned by the reference's tests)."""
+    n = matrix.shape[1]
+    epsilon = 1.0 - (1.0 - desired_relative_error) ** 2
+    x = np.random.RandomState(seed).randn(n)
+    At = matrix.T.tocsr()
+    k = 0
+    while power_method_failure_probability(n, epsilon, k) > probability_of_failure:
+        x = x / np.linalg.norm(x, 2)
+        x = At @ (matrix @ x)
+        k += 1
+    sigma = math.sqrt(float(x @ (At @ (matrix @ x))) / float(np.linalg.norm(x, 2) ** 2))
+    return sigma, k
+
+
+def host_setup(params: PdhgParameters, original_problem: QuadraticProgrammingProblem,
+               scaled: Optional[ScaledQpProblem] = None):
+    """pdhg.jl:786-859 -> (ProblemHolder, FolpParams, ScaledQpProblem)."""
+    validate(original_problem)
+    cache = cached_quadratic_program_info(original_problem)
+    if scaled is None:
+        scaled = rescale_problem(params.l_inf_ruiz_iterations, params.l2_norm_rescaling,
+                                 params.pock_chambolle_alpha, params.verbosity, original_problem)
+    problem = scaled.scaled_qp
+    if params.primal_importance <= 0 or not math.isfinite(params.primal_importance):
+        raise ValueError("primal_importance must be positive and finite")  # :798-801
+    pol = params.step_size_policy_params
+    if isinstance(pol, (AdaptiveStepsizeParams, MalitskyPockStepsizeParameters)):
+        kkt0 = 0.5
+        step0 = _marshal.initial_step_size_inf_norm(problem)  # :823, :826
+    else:
+        sigma, k = estimate_maximum_singular_value(problem.constraint_matrix, 0.001, 0.2)
+        step0 = (1 - 0.2) / sigma  # :836
+        kkt0 = float(k)
+    if params.scale_invariant_initial_primal_weight:
+        pw0 = _marshal.select_initial_primal_weight(problem, params.primal_importance)
+    else:
+        pw0 = params.primal_importance
+    holder = _marshal.make_problem(scaled, cache, with_original_matrix=False)
+    fparams = _marshal.make_params(params, step0, pw0, kkt0)
+    return holder, fparams, scaled
+
+
+def optimize(params: PdhgParameters, original_problem: QuadraticProgrammingProblem) -> SaddlePointOutput:
+    holder, fparams, _ = host_setup(params, original_problem)
+    with Solver(holder, fparams) as solver:
+        x, y, reason, iters, evals = solver.solve()
+    stats = [iteration_stats_from_eval(e) for e in evals]
+    reason = _abi.TerminationReason(reason)
+    return SaddlePointOutput(x, y, reason, termination_reason_to_string(reason), iters, stats)

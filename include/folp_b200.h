@@ -303,6 +303,18 @@ int folp_debug_spmv(folp_handle* h, int transpose, const double* in,
 int folp_counters(folp_handle* h, int64_t* kernel_launches,
                   double* basic_algorithm_seconds, int64_t* iterations);
 
+/* Measurement hook for bench.py: runs `attempts` real take_step attempts
+ * (un-graphed) with CUDA events on the library's stream around each of the
+ * three kernels, and returns the accumulated device milliseconds of
+ * {primal step, A*xbar + dual step, A'*y + interaction/step rule} plus the
+ * number of attempts that did work. The solver state advances. */
+int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
+                                int64_t* attempts_run);
+
+/* The CUDA stream (cudaStream_t) all kernels of this handle are launched on,
+ * so a caller can bracket calls with its own events. */
+void* folp_debug_stream(folp_handle* h);
+
 void folp_destroy(folp_handle* h);
 
 /* Last error message of this handle (or of the failed folp_create when h is

@@ -1,0 +1,333 @@
+"""GPU parity tests: libfolp_b200.so (through the C ABI) against the CPU oracle.
+
+Parity definition:
+  (i)   one take_step attempt from identical state: x+, y+, A'y+ relative <= 1e-13
+        (bit-identical where the row fits one tile), interaction/movement <= 1e-12;
+  (ii)  first 200 iterations with restarts disabled: identical accept/reject
+        sequence, iterates <= 1e-10 relative;
+  (iii) full solves: same termination reason, KKT quantities within 1e-9 relative.
+
+PDHG with the adaptive step-size rule amplifies rounding noise: the oracle run
+twice, the second time with its initial step size moved by ONE ulp, drifts apart
+by ~10x every 10-15 iterations of the transient phase (1e-16 -> 1e-10 after 200
+iterations on these instances). Long-reduction order (tree on the GPU, serial in
+the oracle, BLAS in Julia) is such a perturbation, so trajectory tolerances are
+max(stated tolerance, 20 x the measured 1-ulp sensitivity of the oracle itself).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import folp_b200
+from folp_b200 import RestartScheme, TerminationReason, _marshal
+from folp_b200.lib import Solver
+from folp_b200.synthetic import netlib_shaped_lp, pagerank_lp, random_sparse_lp
+from oracle import oracle
+from shared_problems import example_lp, generate_pdhg_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-300)
+    return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+
+
+def _pair(problem, params, scaled=None, perturbed=False):
+    """Oracle and GPU solvers built from the same bytes (+ the oracle again with
+    a one-ulp larger initial step size, the sensitivity probe)."""
+    holder, fparams, scaled = oracle.host_setup(params, problem, scaled)
+    g_holder, g_params, _ = folp_b200.host_setup(params, problem, scaled)
+    # identical scalar inputs on both sides
+    g_params.initial_step_size = fparams.initial_step_size
+    g_params.initial_primal_weight = fparams.initial_primal_weight
+    o, g = oracle.OracleSolver(holder, fparams), Solver(g_holder, g_params)
+    if not perturbed:
+        return o, g
+    h2, p2, _ = oracle.host_setup(params, problem, scaled)
+    p2.initial_step_size = np.nextafter(fparams.initial_step_size, np.inf)
+    return o, g, oracle.OracleSolver(h2, p2)
+
+
+def _ragged_lp(seed=3):
+    """Rows of length 0, 1, ~10, 100 (warp path) and 5000 (multi-tile path)."""
+    rng = np.random.default_rng(seed)
+    n = 6000
+    lens = np.concatenate([np.zeros(5, int), np.ones(40, int), rng.integers(2, 20, 600),
+                           np.full(7, 100), np.array([5000, 2049, 2048, 33, 32])])
+    rng.shuffle(lens)
+    rows, cols, vals = [], [], []
+    for i, k in enumerate(lens):
+        c = rng.choice(n, size=int(k), replace=False)
+        rows += [i] * int(k)
+        cols += list(c)
+        vals += list(rng.standard_normal(int(k)))
+    m = len(lens)
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(m, n))
+    neq = m // 3
+    from folp_b200.synthetic import _lp, _plant
+    x, y, b, c, l, u = _plant(A, neq, rng, upper_fraction=0.2)
+    return _lp(A, c, l, u, b, neq)
+
+
+# ---------------------------------------------------------------------------
+# SpMV kernels in isolation
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("make", [lambda: random_sparse_lp(3000, 2500, 8, seed=5),
+                                  lambda: netlib_shaped_lp(), _ragged_lp,
+                                  lambda: pagerank_lp(3000)])
+def test_spmv_matches_oracle(make):
+    problem = make()
+    params = generate_pdhg_params(iteration_limit=10)
+    o, g = _pair(problem, params)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(o.n)
+    y = rng.standard_normal(o.m)
+    ax_o, ax_g = o.spmv(x), g.spmv(x)
+    aty_o, aty_g = o.spmv(y, transpose=True), g.spmv(y, transpose=True)
+    A = problem.constraint_matrix.tocsr()
+    row_len = np.diff(A.indptr)
+    col_len = np.diff(problem.constraint_matrix.indptr)
+    # rows summed by a single thread follow the oracle's summation order exactly
+    short_r, short_c = row_len <= 32, col_len <= 32
+    if A.nnz and row_len.max() <= 32:
+        assert np.array_equal(ax_o, ax_g)
+    if A.nnz and col_len.max() <= 32:
+        assert np.array_equal(aty_o, aty_g)
+    assert _rel(ax_g, ax_o) <= 1e-13
+    assert _rel(aty_g, aty_o) <= 1e-13
+    assert short_r.sum() + short_c.sum() > 0
+    o.close(); g.close()
+
+
+def test_spmv_empty_matrix():
+    problem = folp_b200.linear_programming_problem(
+        np.zeros(3), np.full(3, np.inf), np.array([1.0, 2.0, 3.0]), 0.0,
+        sp.csc_matrix((2, 3)), np.zeros(2), 1)
+    params = generate_pdhg_params(iteration_limit=5)
+    g_holder, g_params, _ = folp_b200.host_setup(params, problem)
+    g_params.initial_step_size = 1.0
+    with Solver(g_holder, g_params) as g:
+        assert np.array_equal(g.spmv(np.ones(3)), np.zeros(2))
+        assert np.array_equal(g.spmv(np.ones(2), transpose=True), np.zeros(3))
+
+
+# ---------------------------------------------------------------------------
+# (i) single attempts from identical state
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("make", [lambda: random_sparse_lp(4000, 3000, 10, seed=11), _ragged_lp])
+def test_single_attempt_parity(make):
+    problem = make()
+    params = generate_pdhg_params(iteration_limit=100, l_inf_ruiz_iterations=4,
+                                  pock_chambolle_alpha=1.0)
+    o, g = _pair(problem, params)
+    rng = np.random.default_rng(1)
+    x0 = np.abs(rng.standard_normal(o.n))
+    y0 = rng.standard_normal(o.m)
+    y0[problem.num_equalities:] = np.abs(y0[problem.num_equalities:])
+    for s in (o, g):
+        s.debug_set_state(x0, y0, step_size=0.05, primal_weight=1.3)
+    for _ in range(3):
+        o.debug_attempts(1)
+        g.debug_attempts(1)
+        so, sg = o.debug_state(), g.debug_state()
+        assert _rel(sg["x"], so["x"]) <= 1e-13
+        assert _rel(sg["y"], so["y"]) <= 1e-13
+        assert _rel(sg["dual_product"], so["dual_product"]) <= 1e-13
+        assert abs(sg["last_movement"] - so["last_movement"]) <= 1e-12 * abs(so["last_movement"])
+        assert abs(sg["last_interaction"] - so["last_interaction"]) <= \
+            1e-12 * max(abs(so["last_interaction"]), abs(so["last_movement"]))
+        assert sg["total_number_iterations"] == so["total_number_iterations"]
+        assert abs(sg["step_size"] - so["step_size"]) <= 1e-12 * so["step_size"]
+    o.close(); g.close()
+
+
+# ---------------------------------------------------------------------------
+# (ii) 200 iterations, restarts disabled
+# ---------------------------------------------------------------------------
+def test_trajectory_parity_no_restarts():
+    problem = random_sparse_lp(1500, 1200, 6, seed=21)
+    params = generate_pdhg_params(iteration_limit=1000, l_inf_ruiz_iterations=5,
+                                  pock_chambolle_alpha=1.0)
+    o, g, o2 = _pair(problem, params, perturbed=True)
+    done = 0
+    for chunk in (1, 1, 3, 15, 40, 140):
+        for s_ in (o, g, o2):
+            s_.debug_attempts(chunk)
+        done += chunk
+        so, sg, s2 = o.debug_state(), g.debug_state(), o2.debug_state()
+        # identical accept/reject sequence <=> identical counters
+        assert sg["total_number_iterations"] == so["total_number_iterations"] == done
+        assert sg["sum_primal_solutions_count"] == so["sum_primal_solutions_count"]
+        for key in ("x", "y", "sum_x", "sum_y", "dual_product"):
+            assert _rel(sg[key], so[key]) <= max(1e-10, 20 * _rel(s2[key], so[key])), (key, done)
+        sens = abs(s2["step_size"] - so["step_size"]) / so["step_size"]
+        assert abs(sg["step_size"] - so["step_size"]) <= max(1e-10, 20 * sens) * so["step_size"]
+        assert abs(sg["cumulative_kkt_passes"] - so["cumulative_kkt_passes"]) == 0.0
+        if done <= 20:  # before the amplification sets in the plain 1e-13 bound holds
+            assert _rel(sg["x"], so["x"]) <= 1e-13 and _rel(sg["y"], so["y"]) <= 1e-13
+    assert so["sum_primal_solutions_count"] <= done
+    o.close(); g.close(); o2.close()
+
+
+# ---------------------------------------------------------------------------
+# evaluation records
+# ---------------------------------------------------------------------------
+_EVAL_FIELDS = [
+    "primal_objective", "dual_objective", "l_inf_primal_residual", "l2_primal_residual",
+    "l_inf_dual_residual", "l2_dual_residual", "relative_l_inf_primal_residual",
+    "relative_l2_primal_residual", "relative_l_inf_dual_residual", "relative_l2_dual_residual",
+    "relative_optimality_gap", "l_inf_primal_variable", "l2_primal_variable",
+    "l_inf_dual_variable", "l2_dual_variable", "max_primal_ray_infeasibility",
+    "primal_ray_linear_objective", "max_dual_ray_infeasibility", "dual_ray_objective",
+    "cumulative_kkt_matrix_passes", "step_size", "primal_weight", "lagrangian_value",
+    "estimated_lower_bound", "estimated_upper_bound",
+]
+
+
+def _assert_eval_close(eg, eo, tol, e_pert=None, restart_length=None):
+    """eg (GPU) against eo (oracle); e_pert = the oracle's record when its initial
+    step size is one ulp larger (the inherent sensitivity at this iteration)."""
+    assert eg.iteration_number == eo.iteration_number
+    if eg.restart_used != eo.restart_used:
+        # With a single iterate in the average, average == current up to one
+        # rounding, and should_reset_to_average (sp.jl:530-547, a `>=` between two
+        # equal quantities) is decided by that rounding: either restart is the
+        # reference's behaviour.
+        assert restart_length == 1 and {eg.restart_used, eo.restart_used} == {2, 3}
+    assert eg.termination_reason == eo.termination_reason
+    ref = max(abs(eo.primal_objective), abs(eo.dual_objective), 1.0)
+    for f in _EVAL_FIELDS:
+        a, b = getattr(eg, f), getattr(eo, f)
+        if np.isnan(b):
+            assert np.isnan(a), f
+            continue
+        if np.isinf(b):
+            assert a == b, f
+            continue
+        scale = max(abs(b), ref if "objective" in f or "bound" in f or "lagr" in f else 0.0, 1e-12)
+        bound = tol * scale
+        if e_pert is not None and np.isfinite(getattr(e_pert, f)):
+            bound = max(bound, 20 * abs(getattr(e_pert, f) - b))
+        assert abs(a - b) <= bound, (f, a, b, eo.iteration_number)
+
+
+def _run_lockstep(problem, params, tol=1e-9):
+    """Steps oracle, GPU and the perturbed oracle evaluation by evaluation."""
+    o, g, o2 = _pair(problem, params, perturbed=True)
+    last_restart_iter, n_restart, records = 0, 0, 0
+    while True:
+        eo, eg, e2 = o.run(), g.run(), o2.run()
+        _assert_eval_close(eg, eo, tol, e2, eo.iteration_number - last_restart_iter)
+        records += 1
+        if eo.restart_used >= 2:
+            n_restart += 1
+            last_restart_iter = eo.iteration_number
+        if eo.termination_reason != 0:
+            break
+    xo, yo = o.get_solution()
+    xg, yg = g.get_solution()
+    x2, y2 = o2.get_solution()
+    assert _rel(xg, xo) <= max(tol, 20 * _rel(x2, xo))
+    assert _rel(yg, yo) <= max(tol, 20 * _rel(y2, yo))
+    for s_ in (o, g, o2):
+        s_.close()
+    return eo, n_restart, records
+
+
+@pytest.mark.parametrize("scheme", [RestartScheme.NO_RESTARTS, RestartScheme.ADAPTIVE_NORMALIZED,
+                                    RestartScheme.FIXED_FREQUENCY, RestartScheme.ADAPTIVE_LOCALIZED,
+                                    RestartScheme.ADAPTIVE_DISTANCE])
+def test_eval_records_match_oracle(scheme):
+    """Every IterationStats record of the first 120 iterations, restart logic on."""
+    problem = random_sparse_lp(1200, 900, 6, seed=31, upper_fraction=0.1)
+    params = generate_pdhg_params(iteration_limit=120, l_inf_ruiz_iterations=10,
+                                  pock_chambolle_alpha=1.0, restart_scheme=scheme,
+                                  restart_frequency_if_fixed=25)
+    params.termination_evaluation_frequency = 8
+    eo, n_restart, records = _run_lockstep(problem, params)
+    assert eo.termination_reason == TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
+    assert n_restart >= 3 and records == 10 + 14
+
+
+# ---------------------------------------------------------------------------
+# (iii) full solves with the CLI default parameters
+# ---------------------------------------------------------------------------
+def _kkt_of(problem, x, y, eps=1e-6):
+    e = oracle.iteration_stats(problem, x, y, x, y, eps, eps)
+    return e
+
+
+@pytest.mark.parametrize("make,eps", [
+    (lambda: random_sparse_lp(2000, 1500, 8, seed=41), 1e-6),
+    (lambda: netlib_shaped_lp(seed=11), 1e-6),
+    (lambda: pagerank_lp(2000), 1e-8),
+])
+def test_full_solve_matches_oracle(make, eps):
+    problem = make()
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.eps_optimal_absolute = eps
+    params.termination_criteria.eps_optimal_relative = eps
+    params.termination_criteria.iteration_limit = 300000
+    out_o = oracle.optimize(params, problem)
+    out_g = folp_b200.optimize(params, problem)
+    # iteration counts of the oracle itself under 1..4 ulp changes of the initial
+    # step size: the inherent spread of "iterations to tolerance" on this instance
+    spread = [out_o.iteration_count]
+    for k in range(1, 5):
+        holder, fparams, _ = oracle.host_setup(params, problem)
+        for _ in range(k):
+            fparams.initial_step_size = np.nextafter(fparams.initial_step_size, np.inf)
+        s_ = oracle.OracleSolver(holder, fparams)
+        spread.append(s_.solve()[3])
+        s_.close()
+    assert out_g.termination_reason == out_o.termination_reason == \
+        TerminationReason.TERMINATION_REASON_OPTIMAL
+    # the GPU-reported KKT record equals the oracle's evaluation of the GPU's point
+    fin = out_g.iteration_stats[-1].convergence_information[0]
+    chk = _kkt_of(problem, out_g.primal_solution, out_g.dual_solution, eps)
+    ref = max(abs(chk.primal_objective), abs(chk.dual_objective), 1.0)
+    assert abs(fin.primal_objective - chk.primal_objective) <= 1e-12 * ref
+    assert abs(fin.dual_objective - chk.dual_objective) <= 1e-10 * ref
+    assert abs(fin.l2_primal_residual - chk.l2_primal_residual) <= 1e-10 * max(1.0, chk.l2_primal_residual)
+    assert abs(fin.l2_dual_residual - chk.l2_dual_residual) <= 1e-10 * max(1.0, chk.l2_dual_residual)
+    # both solves meet the same tolerance on the same (relative) KKT quantities
+    fo = out_o.iteration_stats[-1].convergence_information[0]
+    for f in ("relative_l2_primal_residual", "relative_l2_dual_residual", "relative_optimality_gap"):
+        assert getattr(fin, f) <= 2 * eps and getattr(fo, f) <= 2 * eps
+    # objective values agree to the solve tolerance
+    assert abs(fin.primal_objective - fo.primal_objective) <= 10 * eps * ref
+    # iteration count inside the oracle's own spread (a factor 1.5 either side)
+    assert min(spread) / 1.5 - 80 <= out_g.iteration_count <= 1.5 * max(spread) + 80, (
+        out_g.iteration_count, spread)
+
+
+def test_full_solve_trajectory_short_horizon():
+    """CLI default parameters (restarts on), every record of the first 160 iterations."""
+    problem = random_sparse_lp(800, 700, 5, seed=51)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.eps_optimal_absolute = 0.0
+    params.termination_criteria.eps_optimal_relative = 0.0
+    params.termination_criteria.iteration_limit = 160
+    eo, _, _ = _run_lockstep(problem, params)
+    assert eo.iteration_number == 160
+
+
+def test_deterministic_run_to_run():
+    problem = random_sparse_lp(3000, 2500, 10, seed=61)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.iteration_limit = 200
+    a = folp_b200.optimize(params, problem)
+    b = folp_b200.optimize(params, problem)
+    assert np.array_equal(a.primal_solution, b.primal_solution)
+    assert np.array_equal(a.dual_solution, b.dual_solution)
+    assert a.iteration_count == b.iteration_count == 200
+
+
+def test_example_lp_exact_record():
+    """example_lp at the reference's test parameters: every record matches."""
+    params = generate_pdhg_params(iteration_limit=300)
+    eo, _, _ = _run_lockstep(example_lp(), params)
+    assert eo.iteration_number == 300

@@ -1,179 +1,14 @@
 """Pins the CPU oracle against the reference's own end-to-end PDHG tests
 (test/test_primal_dual_hybrid_gradient.jl:76-424), same parameters and
-tolerances. `optimize` is the whole-path restatement `oracle.oracle.optimize`."""
-import numpy as np
+tolerances. The cases live in tests/pdhg_cases.py; `optimize` here is the
+whole-path restatement `oracle.oracle.optimize`."""
 import pytest
 
-from folp_b200 import RestartChoice, RestartScheme, RestartToCurrentMetric, TerminationReason
 from oracle import oracle
-from shared_problems import (
-    example_cc_lp, example_cc_star_lp, example_lp, example_lp_without_bounds, example_qp,
-    example_qp2, generate_pdhg_params,
-)
-
-X_LP = np.array([1.0, 0.0, 6.0, 2.0])
-Y_LP = np.array([0.5, 4.0, 0.0])
+from pdhg_cases import CASES
 
 
-def _close(a, b, atol):
-    assert np.max(np.abs(np.asarray(a) - np.asarray(b))) <= atol, (a, b)
-
-
-def test_low_precision():  # :77-87
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=300), example_lp())
-    _close(out.primal_solution, X_LP, 1e-4)
-    _close(out.dual_solution, Y_LP, 1e-4)
-    assert out.termination_reason == TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
-    assert out.iteration_count == 300
-
-
-def test_terminate_with_optimal_solution():  # :88-98
-    params = generate_pdhg_params(iteration_limit=1000)
-    params.termination_criteria.eps_optimal_absolute = 1e-8
-    out = oracle.optimize(params, example_lp())
-    assert out.termination_reason == TerminationReason.TERMINATION_REASON_OPTIMAL
-
-
-def test_fixed_frequency_restart():  # :116-129
-    params = generate_pdhg_params(iteration_limit=500, restart_scheme=RestartScheme.FIXED_FREQUENCY,
-                                  restart_frequency_if_fixed=30)
-    out = oracle.optimize(params, example_lp())
-    _close(out.primal_solution, X_LP, 1e-9)
-    _close(out.dual_solution, Y_LP, 1e-9)
-
-
-def _has_restart_to_average(out):
-    return any(s.restart_used == RestartChoice.RESTART_CHOICE_RESTART_TO_AVERAGE
-               for s in out.iteration_stats)
-
-
-def test_adaptive_restart_heuristic():  # :130-147
-    params = generate_pdhg_params(iteration_limit=600, restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED)
-    out = oracle.optimize(params, example_lp())
-    _close(out.primal_solution, X_LP, 1e-9)
-    _close(out.dual_solution, Y_LP, 1e-9)
-    assert _has_restart_to_average(out)
-
-
-def test_constant_step_no_smoothing():  # :149-172 (initial step: parity unpinned, see oracle.py)
-    params = generate_pdhg_params(iteration_limit=700, primal_weight_update_smoothing=0.0,
-                                  restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED,
-                                  step_size_policy="constant")
-    out = oracle.optimize(params, example_lp())
-    _close(out.primal_solution, X_LP, 1e-9)
-    _close(out.dual_solution, Y_LP, 1e-9)
-    assert _has_restart_to_average(out)
-    step = out.iteration_stats[0].step_size
-    assert all(s.step_size == step for s in out.iteration_stats)
-
-
-@pytest.mark.parametrize("metric", [RestartToCurrentMetric.NO_RESTART_TO_CURRENT,
-                                    RestartToCurrentMetric.GAP_OVER_DISTANCE])
-def test_restart_to_current_metrics(metric):  # :174-212
-    params = generate_pdhg_params(iteration_limit=600, restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED,
-                                  restart_to_current_metric=metric)
-    out = oracle.optimize(params, example_lp())
-    _close(out.primal_solution, X_LP, 1e-9)
-    _close(out.dual_solution, Y_LP, 1e-9)
-    assert _has_restart_to_average(out)
-
-
-@pytest.mark.parametrize("approx,limit", [(False, 200), (True, 300)])
-def test_adaptive_restart_zero_objective(approx, limit):  # :214-243
-    params = generate_pdhg_params(iteration_limit=limit, restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED,
-                                  use_approximate_localized_duality_gap=approx)
-    problem = example_lp()
-    problem.objective_vector = np.zeros(4)
-    params.termination_criteria.eps_optimal_absolute = 1e-8
-    out = oracle.optimize(params, problem)
-    assert out.termination_reason == TerminationReason.TERMINATION_REASON_OPTIMAL
-
-
-@pytest.mark.parametrize("smoothing", [0.0, 0.5])
-def test_malitsky_pock(smoothing):  # :245-274
-    params = generate_pdhg_params(iteration_limit=700, primal_weight_update_smoothing=smoothing,
-                                  restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED,
-                                  step_size_policy="malitsky-pock")
-    out = oracle.optimize(params, example_lp())
-    _close(out.primal_solution, X_LP, 1e-9)
-    _close(out.dual_solution, Y_LP, 1e-9)
-
-
-def test_quadratic_programming_1():  # :276-286
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=200), example_qp())
-    _close(out.primal_solution, [0.2, 0.8], 1e-4)
-    _close(out.dual_solution, [0.2], 1e-4)
-
-
-def test_quadratic_programming_2():  # :287-297
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=200), example_qp2())
-    _close(out.primal_solution, [0.25, 0.0], 1e-4)
-    _close(out.dual_solution, [0.0], 1e-4)
-
-
-@pytest.mark.parametrize("kw", [dict(l2_norm_rescaling=True), dict(l_inf_ruiz_iterations=10)])
-def test_preprocessing_qp2(kw):  # :298-322
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=200, **kw), example_qp2())
-    _close(out.primal_solution, [0.25, 0.0], 1e-4)
-    _close(out.dual_solution, [0.0], 1e-4)
-
-
-def test_pock_chambolle_rescaling():  # :323-335
-    out = oracle.optimize(generate_pdhg_params(pock_chambolle_alpha=1.0, iteration_limit=3000), example_lp())
-    _close(out.primal_solution, X_LP, 1e-4)
-    _close(out.dual_solution, Y_LP, 1e-4)
-
-
-def test_high_precision():  # :337-347
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=800), example_lp())
-    _close(out.primal_solution, X_LP, 1e-9)
-    _close(out.dual_solution, Y_LP, 1e-9)
-
-
-def test_infeasible_instance():  # :348-360
-    problem = example_lp()
-    problem.right_hand_side[2] = 8
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=800), problem)
-    assert out.termination_reason == TerminationReason.TERMINATION_REASON_PRIMAL_INFEASIBLE
-
-
-def test_lp_without_bounds():  # :361-371
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=400), example_lp_without_bounds())
-    _close(out.primal_solution, [2.0], 1e-9)
-    _close(out.dual_solution, [1.0], 1e-9)
-
-
-def _check_cc(out):
-    tol = 1e-14
-    _close(out.primal_solution, [1.0, 1.0, 0.0, 1.0, 0.0, 0.0], tol)
-    final = out.iteration_stats[-1]
-    assert abs(final.convergence_information[0].dual_objective - 1.0) <= tol
-    assert all(out.dual_solution >= 0.0)
-    assert out.dual_solution[0] + out.dual_solution[1] >= 1.0 - tol
-
-
-def test_correlation_clustering_triangle_plus():  # :372-390
-    _check_cc(oracle.optimize(generate_pdhg_params(iteration_limit=15), example_cc_lp()))
-
-
-def test_numerical_error():  # :391-412
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=150), example_cc_lp())
-    assert out.termination_reason == TerminationReason.TERMINATION_REASON_NUMERICAL_ERROR
-    _check_cc(out)
-
-
-def test_correlation_clustering_star():  # :413-423
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=100), example_cc_star_lp())
-    _close(out.primal_solution, [0.5, 0.5, 0.5, 0.0, 0.0, 0.0], 1e-6)
-    _close(out.dual_solution, [0.5, 0.5, 0.5], 1e-6)
-
-
-def test_artificial_restart_cadence():
-    """with NO_RESTARTS and threshold 0.5 the artificial
-    restarts fire at evaluated iterations 1,2,4,8,20,40,80,... (sp.jl:719-727)."""
-    out = oracle.optimize(generate_pdhg_params(iteration_limit=100), example_lp())
-    resets = [s.iteration_number for s in out.iteration_stats
-              if s.restart_used == RestartChoice.RESTART_CHOICE_WEIGHTED_AVERAGE_RESET]
-    assert resets == [1, 2, 4, 8, 20, 40, 80]
-    evaluated = [s.iteration_number for s in out.iteration_stats]
-    assert evaluated[:11] == list(range(10)) + [10] and evaluated[-1] == 100
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_reference_pdhg_case_on_oracle(case):
+    _, fn, kwargs, _ = case
+    fn(oracle.optimize, **kwargs)
