@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- PDHG iterations/sec on the synthetic random sparse LP of BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A "step" is ITERS_PER_STEP PDHG iterations (outer take_step calls, evaluation /
+restart blocks included, exactly the reference's iteration_count) of
+optimize(PdhgParameters defaults of scripts/solve_qp.jl, lp) on one resident
+problem. `value` = iterations/sec with the problem already in HBM, timed with
+CUDA events on the library's own stream; `e2e` = the same metric through the
+C-ABI call a host makes (folp_create from HOST arrays + folp_solve +
+folp_get_solution), wall clock, uploads and downloads inside the timed region.
+`--impl reference` times the CPU oracle (the single-threaded C restatement of
+the reference's loop; the Julia reference itself cannot run in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ITERS_PER_STEP = 400
+WORKLOADS = {
+    # name: (n, m, nnz_per_row)
+    "c2": (1_000_000, 1_000_000, 10),      # BASELINE.json configs[1]
+    "target": (10_000_000, 10_000_000, 10),  # north_star target size
+    "small": (100_000, 100_000, 10),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_problem(workload):
+    import folp_b200
+    from folp_b200.synthetic import random_sparse_lp
+
+    n, m, k = WORKLOADS[workload]
+    t0 = time.time()
+    lp = random_sparse_lp(n, m, k)
+    params = folp_b200.PdhgParameters(verbosity=0)  # scripts/solve_qp.jl defaults
+    # fixed amount of work per step: never stop on a tolerance
+    params.termination_criteria.eps_optimal_absolute = 0.0
+    params.termination_criteria.eps_optimal_relative = 0.0
+    params.termination_criteria.eps_primal_infeasible = 0.0
+    params.termination_criteria.eps_dual_infeasible = 0.0
+    holder, fparams, scaled = folp_b200.host_setup(params, lp)
+    log(f"[bench] problem {workload}: n={n} m={m} nnz={lp.constraint_matrix.nnz} "
+        f"generated+rescaled on host in {time.time() - t0:.1f}s")
+    return lp, params, holder, fparams, scaled
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.samples = []
+        self.device = device
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=5)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            if len(s) < 9:
+                continue
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n, m, nnz):
+    """bytes one accepted iteration must move (LP, averaging on)."""
+    k1 = 8 * 9 * n                                   # primal step
+    k2 = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * 5 * m  # A*xbar + dual step
+    k3 = 12 * nnz + 4 * (n + 1) + 8 * m + 8 * 4 * n  # A'*y + interaction
+    return k1, k2, k3
+
+
+def run_until(solver, iteration):
+    while True:
+        e = solver.run()
+        if e.iteration_number >= iteration or e.termination_reason != 0:
+            return e
+
+
+def bench_gpu(args):
+    import torch
+    import folp_b200
+    from folp_b200.lib import Solver, build_info
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}: launch with torchrun for N>1")
+    if world > 1:
+        raise SystemExit("bench.py: the multi-GPU row partition is not wired into bench.py yet")
+    torch.cuda.set_device(local_rank)
+    lp, params, holder, fparams, scaled = make_problem(args.workload)
+    n, m, nnz = lp.num_variables, lp.num_constraints, lp.constraint_matrix.nnz
+    total_steps = args.warmup + args.steps
+    fparams.iteration_limit = ITERS_PER_STEP * (total_steps + 1) + 10_000_000
+
+    t0 = time.time()
+    solver = Solver(holder, fparams)
+    t_create = time.time() - t0
+    log(f"[bench] folp_create {t_create:.2f}s; {build_info()}")
+    stream = torch.cuda.ExternalStream(solver.stream())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    done = 0
+    for _ in range(args.warmup):
+        done += ITERS_PER_STEP
+        run_until(solver, done)
+    c0 = solver.counters()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            done += ITERS_PER_STEP
+            e = run_until(solver, done)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    c1 = solver.counters()
+    iters = c1["iterations"] - c0["iterations"]
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    basic_s = c1["basic_algorithm_seconds"] - c0["basic_algorithm_seconds"]
+    value = iters / (ms * 1e-3)
+
+    # per-kernel device time of real attempts, continuing the same solve
+    prof_attempts = 100
+    solver.profile_attempts(10)
+    kms, ran = solver.profile_attempts(prof_attempts)
+    b1, b2, b3 = algorithmic_bytes(n, m, nnz)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
+    per = [k / prof_attempts for k in kms]
+    spmv_ms = per[1] + per[2]
+    achieved = (b2 + b3) / (spmv_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "k_spmv (A*xbar + dual step, A'*y + interaction; two launches per iteration)",
+        "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None,
+        "per_kernel": {
+            "k_primal": {"ms": per[0], "bytes": b1, "gbs": b1 / per[0] / 1e6},
+            "k_spmv<EpiDual>": {"ms": per[1], "bytes": b2, "gbs": b2 / per[1] / 1e6},
+            "k_spmv<EpiTrans>": {"ms": per[2], "bytes": b3, "gbs": b3 / per[2] / 1e6},
+        },
+        "iteration": {"bytes": b1 + b2 + b3, "gbs_at_value": (b1 + b2 + b3) * value / 1e9,
+                      "frac_at_value": (b1 + b2 + b3) * value / 1e9 / peak,
+                      "matrix_only_gbs_at_value": 24 * nnz * value / 1e9},
+    }
+    x_gpu, y_gpu = solver.get_solution()
+    solver.close()
+
+    # ---- e2e: the C-ABI call sequence with host buffers ----
+    e2e_iters = args.e2e_iters
+    fparams.iteration_limit = e2e_iters
+    from folp_b200 import _marshal
+    h2d = sum(a.nbytes for a in holder._keep)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s2 = Solver(holder, fparams)
+    x, y, reason, it2, evals = s2.solve()
+    s2.close()
+    t_e2e = time.perf_counter() - t0
+    d2h = x.nbytes + y.nbytes
+    e2e = {"value": it2 / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "iterations": it2, "seconds": t_e2e,
+           "what": "folp_create(host CSC arrays) + folp_solve + folp_get_solution, wall clock"}
+
+    # ---- cpu baseline: the oracle on a bounded sample of the same workload ----
+    cpu = cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
+
+    line = {
+        "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic random sparse LP n={n} m={m} nnz={nnz} fp64 ({args.workload})",
+                   "iterations_per_step": ITERS_PER_STEP, "parameters": "scripts/solve_qp.jl defaults "
+                   "(ruiz 10, pock-chambolle 1.0, adaptive step 0.3/0.6, adaptive_normalized restarts, "
+                   "evaluation every 40 iterations), tolerances 0 so every step does the same work",
+                   "l2_flush": "working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush"
+                               % ((24 * nnz + 8 * (20 * n + 12 * m)) / 1e6)},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks.summary(),
+        "detail": {"iterations_timed": int(iters), "take_step_seconds": basic_s,
+                   "pure_step_iterations_per_s": iters / basic_s if basic_s > 0 else None,
+                   "final_relative_l2_primal_residual": e.relative_l2_primal_residual,
+                   "final_l2_primal_residual": e.l2_primal_residual,
+                   "final_l2_dual_residual": e.l2_dual_residual,
+                   "folp_create_seconds": t_create, "build": build_info()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(params, lp, scaled, sample_iters):
+    """The oracle (kind "port": the Julia reference cannot run here), one thread,
+    timed from iteration 40 (after the ten per-iteration evaluations of the start)."""
+    from oracle import oracle
+
+    holder, fparams, _ = oracle.host_setup(params, lp, scaled)
+    fparams.iteration_limit = 1_000_000
+    o = oracle.OracleSolver(holder, fparams)
+    run_until(o, 40)
+    t0 = time.perf_counter()
+    e = run_until(o, 40 + sample_iters)
+    dt = time.perf_counter() - t0
+    o.close()
+    return {"value": sample_iters / dt, "unit": "iterations/s", "cores": 1, "kind": "port",
+            "sample": f"iterations 40..{40 + sample_iters} of the same problem and parameters "
+                      f"({sample_iters // 40} evaluation/restart blocks included), {dt:.1f}s",
+            "host_cores_available": os.cpu_count()}
+
+
+def bench_reference(args):
+    """--impl reference: the CPU oracle on the box's host cores (the reference's
+    loop is serial: one thread). Each step = 40 iterations (one evaluation period)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lp, params, holder, fparams, scaled = make_problem(args.workload)
+    from oracle import oracle
+
+    n, m, nnz = lp.num_variables, lp.num_constraints, lp.constraint_matrix.nnz
+    o_holder, o_params, _ = oracle.host_setup(params, lp, scaled)
+    o_params.iteration_limit = 1_000_000
+    o = oracle.OracleSolver(o_holder, o_params)
+    per = 40
+    done = 40
+    run_until(o, done)  # the first ten iterations are evaluated one by one (pdhg.jl:894)
+    for _ in range(args.warmup):
+        done += per
+        run_until(o, done)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        done += per
+        run_until(o, done)
+    dt = time.perf_counter() - t0
+    o.close()
+    value = per * args.steps / dt
+    cpu = {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port",
+           "sample": f"{args.steps} steps x {per} iterations of the same problem and parameters, {dt:.1f}s",
+           "host_cores_available": os.cpu_count()}
+    line = {"impl": "reference", "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic random sparse LP n={n} m={m} nnz={nnz} fp64 ({args.workload})",
+                       "iterations_per_step": per},
+            "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="folp_b200", choices=["folp_b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-iters", type=int, default=2000)
+    ap.add_argument("--cpu-iters", type=int, default=80)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        log("[bench] warning: fewer than 3 warm-up steps")
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

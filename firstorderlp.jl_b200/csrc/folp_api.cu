@@ -68,7 +68,10 @@ struct folp_handle {
 template <class T>
 static int dev_alloc(folp_handle* h, T** p, size_t count) {
   void* q = nullptr;
-  TRY(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  // 16 elements of slack: the staged bulk copies of k_spmv round their extents up
+  // to 16-byte multiples and may read (never use) a few elements past the end
+  TRY(cudaMalloc(&q, (count + 16) * sizeof(T)));
+  TRY(cudaMemsetAsync(static_cast<char*>(q) + count * sizeof(T), 0, 16 * sizeof(T), h->stream));
   h->allocs.push_back(q);
   *p = static_cast<T*>(q);
   return FOLP_OK;
@@ -291,7 +294,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   // ---- vectors ----
   Bufs& B = h->B;
   B.n = static_cast<int>(n); B.m = static_cast<int>(m); B.neq = static_cast<int>(h->neq);
-  B.grid_spmv = h->sm_count * 4;
+  B.grid_spmv = h->sm_count;
   B.grid_vec = h->sm_count * 8;
   int rc;
   if ((rc = dev_alloc(h, &B.st, 1))) return rc;
@@ -401,7 +404,7 @@ extern "C" const char* folp_last_error(const folp_handle* h) {
 }
 
 extern "C" const char* folp_build_info(void) {
-  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;tile_nnz=2048;tile_rows=512";
+  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;tile_nnz=2048;tile_rows=256;spmv=warp-specialized(1+16+8 warps,6 stages)";
 }
 
 extern "C" int folp_nccl_unique_id(void* out128) {

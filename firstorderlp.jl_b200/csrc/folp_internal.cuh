@@ -55,8 +55,8 @@ struct DevState {
 // in chunk order by the last chunk to finish (deterministic).
 // ---------------------------------------------------------------------------
 constexpr int kTileNnz = 2048;     // max nonzeros staged per tile
-constexpr int kTileRows = 512;     // max rows per tile
-constexpr int kSpmvThreads = 256;
+constexpr int kTileRows = 256;     // max rows per tile (one per reduce thread)
+constexpr int kSpmvThreads = 800;   // 1 producer + 16 gather + 8 reduce warps
 constexpr int kTilePad = 8;        // slack for 16-byte aligned bulk copies
 
 enum TileKind : int { kTileThreadPerRow = 0, kTileWarpPerRow = 1, kTileLongChunk = 2 };

@@ -175,6 +175,7 @@ __device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double d
 // K2 epilogue: dual step on row i given (A*xbar)_i
 // ---------------------------------------------------------------------------
 struct EpiDual {
+  static constexpr int kNumIn = 3;  // y, b, sum_y
   Bufs B;
   const double* yc;
   double* yn;
@@ -194,10 +195,10 @@ struct EpiDual {
     return true;
   }
   __device__ const double* input() const { return B.xbar; }
-  __device__ void row(int i, double ax) {
-    const double yv = yc[i];
-    if (pend) B.sum_y[i] += yv * w;  // deferred add_to_dual_solution_weighted_average
-    const double g = B.b[i] - ax;    // compute_dual_gradient, sp.jl:1102-1107
+  __device__ const double* in_ptr(int v) const { return v == 0 ? yc : (v == 1 ? B.b : B.sum_y); }
+  __device__ void row(int i, double ax, double yv, double bi, double sy) {
+    if (pend) B.sum_y[i] = sy + yv * w;  // deferred add_to_dual_solution_weighted_average
+    const double g = bi - ax;        // compute_dual_gradient, sp.jl:1102-1107
     double yp = yv + f * g;
     if (i >= B.neq) yp = fmax(yp, 0.0);  // project_dual!, sp.jl:110-117
     yn[i] = yp;
@@ -214,6 +215,7 @@ struct EpiDual {
 // K3 epilogue: (A'*y+)_j, interaction dot, and the scalar rule in the last CTA
 // ---------------------------------------------------------------------------
 struct EpiTrans {
+  static constexpr int kNumIn = 3;  // x, x+, A'y
   Bufs B;
   int g_primal, g_dual;  // grids of K1 and K2 (number of partials they wrote)
   const double *xc, *xn, *atc;
@@ -231,10 +233,11 @@ struct EpiTrans {
     return true;
   }
   __device__ const double* input() const { return sel(B.y, B.st->cur ^ 1); }
-  __device__ void row(int j, double at) {
+  __device__ const double* in_ptr(int v) const { return v == 0 ? xc : (v == 1 ? xn : atc); }
+  __device__ void row(int j, double at, double xcj, double xnj, double atcj) {
     atn[j] = at;
-    const double dx = xn[j] - xc[j];
-    const double dat = at - atc[j];
+    const double dx = xnj - xcj;
+    const double dat = at - atcj;
     inter += dx * dat;  // pdhg.jl:542-544
     dp2 += dat * dat;   // pdhg.jl:615 (Malitsky-Pock)
   }
