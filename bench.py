@@ -195,23 +195,24 @@ def bench_gpu(args):
     solver.close()
 
     # ---- e2e: the C-ABI call sequence with host buffers ----
-    e2e_iters = args.e2e_iters
-    fparams.iteration_limit = e2e_iters
-    from folp_b200 import _marshal
-    h2d = sum(a.nbytes for a in holder._keep)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    s2 = Solver(holder, fparams)
-    x, y, reason, it2, evals = s2.solve()
-    s2.close()
-    t_e2e = time.perf_counter() - t0
-    d2h = x.nbytes + y.nbytes
-    e2e = {"value": it2 / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "iterations": it2, "seconds": t_e2e,
-           "what": "folp_create(host CSC arrays) + folp_solve + folp_get_solution, wall clock"}
+    e2e = None
+    if not args.skip_e2e:
+        e2e_iters = args.e2e_iters
+        fparams.iteration_limit = e2e_iters
+        h2d = sum(a.nbytes for a in holder._keep)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s2 = Solver(holder, fparams)
+        x, y, reason, it2, evals = s2.solve()
+        s2.close()
+        t_e2e = time.perf_counter() - t0
+        d2h = x.nbytes + y.nbytes
+        e2e = {"value": it2 / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "iterations": it2, "seconds": t_e2e,
+               "what": "folp_create(host CSC arrays) + folp_solve + folp_get_solution, wall clock"}
 
     # ---- cpu baseline: the oracle on a bounded sample of the same workload ----
-    cpu = cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
+    cpu = None if args.skip_cpu else cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
 
     line = {
         "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": 1,
@@ -305,6 +306,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-iters", type=int, default=2000)
     ap.add_argument("--cpu-iters", type=int, default=80)
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu)")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only (ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         log("[bench] warning: fewer than 3 warm-up steps")
