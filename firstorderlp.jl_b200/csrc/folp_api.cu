@@ -404,7 +404,12 @@ extern "C" const char* folp_last_error(const folp_handle* h) {
 }
 
 extern "C" const char* folp_build_info(void) {
-  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;tile_nnz=2048;tile_rows=256;spmv=warp-specialized(1+16+8 warps,6 stages)";
+#define FOLP_STR2(x) #x
+#define FOLP_STR(x) FOLP_STR2(x)
+  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;tile_nnz=" FOLP_STR(FOLP_TILE_NNZ)
+         ";tile_rows=" FOLP_STR(FOLP_TILE_ROWS) ";spmv=warp-specialized(1+" FOLP_STR(
+             FOLP_GATHER_WARPS) "+" FOLP_STR(FOLP_REDUCE_WARPS) " warps," FOLP_STR(FOLP_STAGES)
+         " stages, gathers pipelined one tile ahead)";
 }
 
 extern "C" int folp_nccl_unique_id(void* out128) {
@@ -998,6 +1003,27 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
   for (auto& e : ev) cudaEventDestroy(e);
   // every attempt does work unless a numerical error stopped the batch early
   if (attempts_run) *attempts_run = s->numerical_error ? -1 : attempts;
+  return FOLP_OK;
+}
+
+extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, double* ms_out) {
+  if (!h || !ms_out || reps < 1) return FOLP_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  Bufs& B = h->B;
+  // input: the live iterate (x or y); output: trust-region scratch
+  const double* in = transpose ? B.y[h->hs->cur] : B.x[h->hs->cur];
+  for (int w = 0; w < 3; ++w)
+    launch_spmv_plain(transpose ? h->At : h->A, in, B.tr_d, B.grid_spmv, h->stream);
+  TRY(cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; ++r)
+    launch_spmv_plain(transpose ? h->At : h->A, in, B.tr_d, B.grid_spmv, h->stream);
+  TRY(cudaEventRecord(h->ev1, h->stream));
+  CHECK_LAUNCH();
+  TRY(cudaEventSynchronize(h->ev1));
+  h->launches += reps + 3;
+  float ms = 0.f;
+  TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_out = ms / reps;
   return FOLP_OK;
 }
 

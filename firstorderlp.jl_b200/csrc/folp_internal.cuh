@@ -54,9 +54,26 @@ struct DevState {
 // row longer than a tile is split into chunks whose partial sums are combined
 // in chunk order by the last chunk to finish (deterministic).
 // ---------------------------------------------------------------------------
-constexpr int kTileNnz = 2048;     // max nonzeros staged per tile
-constexpr int kTileRows = 256;     // max rows per tile (one per reduce thread)
-constexpr int kSpmvThreads = 800;   // 1 producer + 16 gather + 8 reduce warps
+#ifndef FOLP_TILE_NNZ
+#define FOLP_TILE_NNZ 2048
+#endif
+#ifndef FOLP_TILE_ROWS
+#define FOLP_TILE_ROWS 256
+#endif
+#ifndef FOLP_GATHER_WARPS
+#define FOLP_GATHER_WARPS 16
+#endif
+#ifndef FOLP_REDUCE_WARPS
+#define FOLP_REDUCE_WARPS 8
+#endif
+#ifndef FOLP_STAGES
+#define FOLP_STAGES 6
+#endif
+constexpr int kTileNnz = FOLP_TILE_NNZ;    // max nonzeros staged per tile
+constexpr int kTileRows = FOLP_TILE_ROWS;  // max rows per tile (one per reduce thread)
+constexpr int kGatherWarps = FOLP_GATHER_WARPS;
+constexpr int kReduceWarps = FOLP_REDUCE_WARPS;
+constexpr int kSpmvThreads = 32 * (1 + kGatherWarps + kReduceWarps);  // + 1 producer warp
 constexpr int kTilePad = 8;        // slack for 16-byte aligned bulk copies
 
 enum TileKind : int { kTileThreadPerRow = 0, kTileWarpPerRow = 1, kTileLongChunk = 2 };

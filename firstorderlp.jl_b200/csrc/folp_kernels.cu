@@ -46,6 +46,32 @@ __device__ __forceinline__ void attempt_params(const DevState& s, double& trial,
 // ---------------------------------------------------------------------------
 // K1: compute_next_primal_solution (pdhg.jl:442-470) + xbar (pdhg.jl:486)
 // ---------------------------------------------------------------------------
+// One element of K1. Returns dx; writes x+ / xbar / sum_x through the references.
+struct PrimalCtx {
+  double f, theta, w, w_old;
+  bool do_primal, pend, pend_old;
+};
+__device__ __forceinline__ double primal_elem(const PrimalCtx& k, double x, double& xn, double c,
+                                              double at, double l, double u, double& sx,
+                                              double& xbar) {
+  if (k.pend || k.pend_old) {  // deferred add_to_primal_solution_weighted_average (sp.jl:252-263)
+    if (k.pend_old) sx += xn * k.w_old;  // xn still holds the previous iterate (pdhg.jl:621-627)
+    if (k.pend) sx += x * k.w;
+  }
+  double xp;
+  if (k.do_primal) {
+    const double g = c - at;  // sp.jl:1093-1100 with Q = 0
+    xp = x - k.f * g;
+    xp = fmin(u, fmax(l, xp));  // sp.jl:82-93
+    xn = xp;
+  } else {
+    xp = xn;
+  }
+  const double d = xp - x;
+  xbar = xp + k.theta * d;
+  return d;
+}
+
 __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   __shared__ double sh[32];
   const DevState& s = *B.st;
@@ -53,35 +79,49 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   double trial, theta;
   attempt_params(s, trial, theta);
   const bool mp = s.policy == FOLP_STEP_MALITSKY_POCK;
-  const bool do_primal = !mp || s.mp_need_primal;
-  const double f = (mp ? s.step_size : trial) / s.primal_weight;
+  PrimalCtx k;
+  k.do_primal = !mp || s.mp_need_primal;
+  k.f = (mp ? s.step_size : trial) / s.primal_weight;
+  k.theta = theta;
+  k.pend = s.pending_avg & 1;
+  k.pend_old = (s.pending_avg & 2) != 0;
+  k.w = s.pending_w;
+  k.w_old = s.mp_old_step;
   const int cur = s.cur;
   const double* __restrict__ xc = sel(B.x, cur);
   double* __restrict__ xn = sel(B.x, cur ^ 1);
   const double* __restrict__ at = sel(B.aty, cur);
-  const bool pend = s.pending_avg & 1, pend_old = (s.pending_avg & 2) != 0;
-  const double w = s.pending_w, w_old = s.mp_old_step;
+  const bool avg = k.pend || k.pend_old;
+  const bool rd_xn = k.pend_old || !k.do_primal;
   double acc = 0.0;
   const int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
-    const double x = xc[j];
-    if (pend || pend_old) {  // deferred add_to_primal_solution_weighted_average (sp.jl:252-263)
-      double sx = B.sum_x[j];
-      if (pend_old) sx += xn[j] * w_old;  // xn still holds the previous iterate (pdhg.jl:621-627)
-      if (pend) sx += x * w;
-      B.sum_x[j] = sx;
-    }
-    double xp;
-    if (do_primal) {
-      const double g = B.c[j] - at[j];  // sp.jl:1093-1100 with Q = 0
-      xp = x - f * g;
-      xp = fmin(B.u[j], fmax(B.l[j], xp));  // sp.jl:82-93
-      xn[j] = xp;
-    } else {
-      xp = xn[j];
-    }
-    const double d = xp - x;
-    B.xbar[j] = xp + theta * d;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  // two elements per thread and trip: every stream moves as 16-byte accesses
+  const int n2 = B.n >> 1;
+  for (int j = t0; j < n2; j += stride) {
+    const double2 x = reinterpret_cast<const double2*>(xc)[j];
+    const double2 c = reinterpret_cast<const double2*>(B.c)[j];
+    const double2 a = reinterpret_cast<const double2*>(at)[j];
+    const double2 l = reinterpret_cast<const double2*>(B.l)[j];
+    const double2 u = reinterpret_cast<const double2*>(B.u)[j];
+    double2 sx = avg ? reinterpret_cast<const double2*>(B.sum_x)[j] : make_double2(0.0, 0.0);
+    double2 xp = rd_xn ? reinterpret_cast<const double2*>(xn)[j] : make_double2(0.0, 0.0);
+    double2 xb;
+    const double d0 = primal_elem(k, x.x, xp.x, c.x, a.x, l.x, u.x, sx.x, xb.x);
+    const double d1 = primal_elem(k, x.y, xp.y, c.y, a.y, l.y, u.y, sx.y, xb.y);
+    if (avg) reinterpret_cast<double2*>(B.sum_x)[j] = sx;
+    if (k.do_primal) reinterpret_cast<double2*>(xn)[j] = xp;
+    reinterpret_cast<double2*>(B.xbar)[j] = xb;
+    acc += d0 * d0;
+    acc += d1 * d1;
+  }
+  if ((B.n & 1) && t0 == 0) {
+    const int j = B.n - 1;
+    double sx = avg ? B.sum_x[j] : 0.0, xp = rd_xn ? xn[j] : 0.0, xb;
+    const double d = primal_elem(k, xc[j], xp, B.c[j], at[j], B.l[j], B.u[j], sx, xb);
+    if (avg) B.sum_x[j] = sx;
+    if (k.do_primal) xn[j] = xp;
+    B.xbar[j] = xb;
     acc += d * d;
   }
   const double t = block_reduce<false>(acc, sh);

@@ -32,14 +32,12 @@ constexpr int kOffIn = kOffRowp + (kTileRows + 8) * 4;           // up to 3 epil
 constexpr int kInStride = (kTileRows + 4) * 8;
 constexpr int kOffDesc = kOffIn + 3 * kInStride;                 // the Tile descriptor
 constexpr int kSpmvStageBytes = kOffDesc + 64;
-constexpr int kSpmvStages = 6;
+constexpr int kSpmvStages = FOLP_STAGES;
 constexpr int kSpmvSmemBytes = kSpmvStages * kSpmvStageBytes;
 static_assert(kSpmvStageBytes % 16 == 0 && kOffCols % 16 == 0 && kOffRowp % 16 == 0 &&
                   kOffIn % 16 == 0 && kInStride % 16 == 0 && kOffDesc % 16 == 0,
               "bulk copies need 16-byte aligned destinations");
 static_assert(kSpmvSmemBytes <= 227 * 1024 - 1024, "stage ring must fit one SM");
-constexpr int kGatherWarps = 16;
-constexpr int kReduceWarps = 8;
 constexpr int kGatherThreads = kGatherWarps * 32;
 constexpr int kReduceThreads = kReduceWarps * 32;
 static_assert(kSpmvThreads == 32 + kGatherThreads + kReduceThreads, "role split");
@@ -142,31 +140,49 @@ __global__ void __launch_bounds__(kSpmvThreads, 1) k_spmv(SpmvMat A, Epi epi) {
     }
   } else if (warp <= kGatherWarps) {
     // ---------------- gather ----------------
+    // Software-pipelined across tiles: the gathers of tile i+1 are issued before the
+    // products of tile i are formed, so every warp keeps kPer..2*kPer L2 gathers in
+    // flight and the LSU never drains at a tile boundary.
     const int gt = tid - 32;
-    for (int i = 0; i < my_tiles; ++i) {
+    constexpr int kPer = kTileNnz / kGatherThreads;
+    double xv[kPer];
+    int kb = 0, ke = 0;
+    auto fetch = [&](int i) {
       const int st = i % kSpmvStages;
       unsigned char* sb = smem_raw + st * kSpmvStageBytes;
       mbar_wait(&s_full[st], (i / kSpmvStages) & 1);
       const Tile* td = reinterpret_cast<const Tile*>(sb + kOffDesc);
       const int nb = td->nnz_begin, ne = td->nnz_end;
       const int base = nb & ~3;
-      const int kb = nb - base, ke = ne - base;
-      double* __restrict__ sv = reinterpret_cast<double*>(sb + kOffVals);
+      kb = nb - base;
+      ke = ne - base;
       const int* __restrict__ sc = reinterpret_cast<const int*>(sb + kOffCols);
-      constexpr int kPer = kTileNnz / kGatherThreads;
       int c[kPer];
-      double xv[kPer];
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
         const int k = kb + gt + u * kGatherThreads;
         c[u] = k < ke ? sc[k] : -1;
       }
 #pragma unroll
+#ifdef FOLP_ABLATE_GATHER  // development: timing without the L2 gathers (wrong results)
+      for (int u = 0; u < kPer; ++u) xv[u] = c[u] >= 0 ? 1.0 + c[u] : 0.0;
+#else
       for (int u = 0; u < kPer; ++u) xv[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
+#endif
+    };
+    if (my_tiles > 0) fetch(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      const int st = i % kSpmvStages;
+      double* __restrict__ sv = reinterpret_cast<double*>(smem_raw + st * kSpmvStageBytes + kOffVals);
+      double xc[kPer];
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) xc[u] = xv[u];
+      const int kbc = kb, kec = ke;
+      if (i + 1 < my_tiles) fetch(i + 1);
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
-        const int k = kb + gt + u * kGatherThreads;
-        if (k < ke) sv[k] = sv[k] * xv[u];
+        const int k = kbc + gt + u * kGatherThreads;
+        if (k < kec) sv[k] = sv[k] * xc[u];
       }
       // products were written through the generic proxy; the stage is refilled by
       // the async proxy once the reduce warps release it
@@ -182,6 +198,11 @@ __global__ void __launch_bounds__(kSpmvThreads, 1) k_spmv(SpmvMat A, Epi epi) {
       const int st = i % kSpmvStages;
       unsigned char* sb = smem_raw + st * kSpmvStageBytes;
       mbar_wait(&s_prod[st], (i / kSpmvStages) & 1);
+#ifdef FOLP_ABLATE_REDUCE  // development: timing without row sums / epilogue (wrong results)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      continue;
+#endif
       const Tile t = *reinterpret_cast<const Tile*>(sb + kOffDesc);
       const int base = t.nnz_begin & ~3;
       const double* __restrict__ sv = reinterpret_cast<const double*>(sb + kOffVals);
@@ -195,8 +216,18 @@ __global__ void __launch_bounds__(kSpmvThreads, 1) k_spmv(SpmvMat A, Epi epi) {
         const int r = t.row_begin + rt;
         if (r < t.row_end) {
           const int k0 = rp[r - rb4] - base, k1 = rp[r - rb4 + 1] - base;
+          // ascending column order; the shared-memory loads are issued four at a time
+          // so that only the additions are serialised
           double s = 0.0;
-          for (int k = k0; k < k1; ++k) s += sv[k];  // ascending column order
+          int k = k0;
+          for (; k + 4 <= k1; k += 4) {
+            const double a0 = sv[k], a1 = sv[k + 1], a2 = sv[k + 2], a3 = sv[k + 3];
+            s += a0;
+            s += a1;
+            s += a2;
+            s += a3;
+          }
+          for (; k < k1; ++k) s += sv[k];
           const int li = r - rb2;
           epi.row(r, s, Epi::kNumIn > 0 ? in0[li] : 0.0, Epi::kNumIn > 1 ? in1[li] : 0.0,
                   Epi::kNumIn > 2 ? in2[li] : 0.0);

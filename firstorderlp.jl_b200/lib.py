@@ -16,14 +16,15 @@ import numpy as np
 from ._abi import FolpDebugScalars, FolpDist, FolpEval, FolpParams, FolpProblem, Status
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfolp_b200.so")
+# FOLP_B200_LIB selects another build of the same library (kernel variants under development)
+LIB_PATH = os.environ.get("FOLP_B200_LIB") or os.path.join(_HERE, "libfolp_b200.so")
 _pd = C.POINTER(C.c_double)
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
     "folp_nccl_unique_id", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
-    "folp_debug_profile_attempts", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
+    "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
 
 
@@ -68,6 +69,7 @@ def lib() -> C.CDLL:
         L.folp_debug_set_state.argtypes = [C.c_void_p, _pd, _pd, C.c_double, C.c_double]
         L.folp_debug_spmv.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
         L.folp_debug_profile_attempts.argtypes = [C.c_void_p, C.c_int64, _pd, C.POINTER(C.c_int64)]
+        L.folp_debug_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, _pd]
         L.folp_debug_stream.argtypes = [C.c_void_p]
         L.folp_debug_stream.restype = C.c_void_p
         L.folp_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), _pd, C.POINTER(C.c_int64)]
@@ -177,6 +179,12 @@ class Solver:
         ran = C.c_int64()
         self._check(lib().folp_debug_profile_attempts(self._h, attempts, ms, C.byref(ran)))
         return [ms[0], ms[1], ms[2]], ran.value
+
+    def time_spmv(self, transpose=False, reps=20) -> float:
+        """Average device milliseconds of the plain SpMV kernel."""
+        ms = C.c_double()
+        self._check(lib().folp_debug_time_spmv(self._h, int(transpose), int(reps), C.cast(C.byref(ms), _pd)))
+        return ms.value
 
     def stream(self) -> int:
         return int(lib().folp_debug_stream(self._h) or 0)

@@ -311,6 +311,10 @@ int folp_counters(folp_handle* h, int64_t* kernel_launches,
 int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
                                 int64_t* attempts_run);
 
+/* Measurement hook: average device milliseconds of `reps` launches of the plain
+ * SpMV kernel (A * x when transpose == 0, A' * y otherwise) on the live iterate. */
+int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, double* ms_out);
+
 /* The CUDA stream (cudaStream_t) all kernels of this handle are launched on,
  * so a caller can bracket calls with its own events. */
 void* folp_debug_stream(folp_handle* h);
