@@ -48,6 +48,7 @@ from .solve_log import (  # noqa: F401
     termination_reason_to_string,
 )
 
+from . import distributed  # noqa: F401
 from .pdhg import estimate_maximum_singular_value, host_setup, optimize  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -6,6 +6,7 @@
 // decisions sp.jl:688-846, primal weight sp.jl:862-891); every vector lives in
 // HBM and every O(n), O(m), O(nnz) operation is a kernel in folp_kernels.cu.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -14,6 +15,7 @@
 #include <new>
 
 #include "folp_kernels.cuh"
+#include "folp_nccl.h"
 
 using namespace folp;
 
@@ -57,10 +59,28 @@ struct folp_handle {
   int64_t tr_passes = 0, tr_solves = 0;
   std::map<int, cudaGraphExec_t> step_graphs;
   bool use_graphs = true;
+  // ---- row-partitioned mode (folp_dist.world_size > 1) ----
+  int rank = 0, world = 1;
+  const NcclApi* nccl = nullptr;
+  ncclComm_t comm = nullptr;
+  int64_t n_glob = 0, m_glob = 0;  // global sizes; n / m above are the local slice / rows
+  int64_t n_pad = 0, m_pad = 0;    // exchange strides: ceil(n/world) (even), max rows per rank
+  int64_t col0 = 0, row0 = 0;      // first global column / row owned by this rank
+  std::vector<int64_t> row_begin;  // world + 1
+  double* d_rows = nullptr;        // staging for row-indexed gathers, world * m_pad
+  double* h_sc = nullptr;          // pinned, world * kScBlock
 };
 
 #define TRY(expr) FOLP_CUDA_TRY(h, expr)
 #define CHECK_LAUNCH() TRY(cudaGetLastError())
+#define NCCL_TRY(expr)                                                             \
+  do {                                                                             \
+    ncclResult_t _r = (expr);                                                      \
+    if (_r != ncclSuccess) {                                                       \
+      h->err = std::string(#expr) + ": " + h->nccl->GetErrorString(_r);            \
+      return FOLP_NCCL_ERROR;                                                      \
+    }                                                                              \
+  } while (0)
 
 // ---------------------------------------------------------------------------
 // setup helpers
@@ -173,6 +193,8 @@ static void free_handle(folp_handle* h) {
   if (h->hs) cudaFreeHost(h->hs);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_trs) cudaFreeHost(h->h_trs);
+  if (h->h_sc) cudaFreeHost(h->h_sc);
+  if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -190,14 +212,49 @@ static int pull_state(folp_handle* h) {
 }
 
 // ---------------------------------------------------------------------------
+// 1-D row partition: contiguous row blocks balanced by
+// cost = nonzeros + 2 per row, and equal column slices of ceil(n / world) rounded
+// up to an even count (K1 moves 16-byte pairs). Pure host arithmetic; exported so
+// that CPU tests can check it without a device.
+// ---------------------------------------------------------------------------
+static void partition_rows(int64_t m, const std::vector<int64_t>& row_cost_prefix, int world,
+                           int64_t* row_begin) {
+  const int64_t total = row_cost_prefix[m];
+  row_begin[0] = 0;
+  for (int r = 1; r < world; ++r) {
+    const int64_t target = static_cast<int64_t>((static_cast<__int128>(total) * r) / world);
+    const int64_t i = std::lower_bound(row_cost_prefix.begin(), row_cost_prefix.end(), target) -
+                      row_cost_prefix.begin();
+    row_begin[r] = std::min<int64_t>(std::max<int64_t>(i, row_begin[r - 1]), m);
+  }
+  row_begin[world] = m;
+}
+
+extern "C" int folp_partition(int64_t m, int64_t n, int64_t nnz, const int64_t* rowval,
+                              int32_t index_base, int32_t world_size, int64_t* row_begin_out,
+                              int64_t* col_begin_out) {
+  if (m < 0 || n < 0 || nnz < 0 || world_size < 1 || !row_begin_out || !col_begin_out ||
+      (nnz > 0 && !rowval))
+    return FOLP_INVALID_ARGUMENT;
+  std::vector<int64_t> prefix(static_cast<size_t>(m) + 1, 0);
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t r = rowval[k] - index_base;
+    if (r < 0 || r >= m) return FOLP_INVALID_ARGUMENT;
+    prefix[r + 1] += 1;
+  }
+  for (int64_t i = 0; i < m; ++i) prefix[i + 1] += prefix[i] + 2;
+  partition_rows(m, prefix, world_size, row_begin_out);
+  int64_t n_pad = (n + world_size - 1) / world_size;
+  n_pad += n_pad & 1;
+  for (int r = 0; r <= world_size; ++r) col_begin_out[r] = std::min<int64_t>(n, r * n_pad);
+  return FOLP_OK;
+}
+
+// ---------------------------------------------------------------------------
 // folp_create
 // ---------------------------------------------------------------------------
 static int create_impl(folp_handle* h, const folp_problem* p, const folp_params* q,
                        const folp_dist* dist) {
-  if (dist && dist->world_size > 1) {
-    h->err = "multi-GPU row partition is not built into this library version";
-    return FOLP_UNSUPPORTED;
-  }
   const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
   if (n < 0 || m < 0 || nnz < 0 || p->num_equalities < 0 || p->num_equalities > m ||
       (p->index_base != 0 && p->index_base != 1)) {
@@ -230,7 +287,18 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     h->err = "initial_step_size and initial_primal_weight must be positive";
     return FOLP_INVALID_ARGUMENT;
   }
-  h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
+  if (dist && (dist->world_size < 1 || dist->rank < 0 || dist->rank >= dist->world_size)) {
+    h->err = "invalid folp_dist rank / world_size";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  h->use_graphs = getenv("FOLP_NO_GRAPHS") == nullptr;
+  h->world = dist ? dist->world_size : 1;
+  h->rank = dist ? dist->rank : 0;
+  if (h->world > 1 && !dist->nccl_unique_id) {
+    h->err = "folp_dist.nccl_unique_id is required when world_size > 1";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  h->n_glob = n; h->m_glob = m;
   h->prm = *q;
   h->cache[0] = p->l_inf_norm_primal_linear_objective;
   h->cache[1] = p->l_inf_norm_primal_right_hand_side;
@@ -255,9 +323,21 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->hs), sizeof(DevState)));
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_red), sizeof(double) * 4 * kMaxScalars));
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_trs), sizeof(TrState)));
+  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_sc), sizeof(double) * h->world * kScBlock));
+
+  if (h->world > 1) {
+    h->nccl = nccl_api(&h->err);
+    if (!h->nccl) return FOLP_NCCL_ERROR;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "folp_dist carries a 128-byte id");
+    memcpy(&id, dist->nccl_unique_id, sizeof(id));
+    NCCL_TRY(h->nccl->CommInitRank(&h->comm, h->world, id, h->rank));
+  }
 
   // ---- matrices: A' in CSR is the caller's CSC; A in CSR by counting sort ----
   const int base = p->index_base;
+  const int P = h->world;
+  h->row_begin.assign(static_cast<size_t>(P) + 1, 0);
   {
     std::vector<int> rp(static_cast<size_t>(n) + 1), ci(static_cast<size_t>(nnz));
     std::vector<double> v(static_cast<size_t>(nnz));
@@ -273,8 +353,6 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         h->err = "colptr is not monotone";
         return FOLP_INVALID_ARGUMENT;
       }
-    int rc = build_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp, ci, v);
-    if (rc) return rc;
     // transpose
     std::vector<int> rp2(static_cast<size_t>(m) + 1, 0), ci2(static_cast<size_t>(nnz));
     std::vector<double> v2(static_cast<size_t>(nnz));
@@ -287,58 +365,115 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         ci2[pos] = static_cast<int>(j);  // ascending j inside each row
         v2[pos] = v[k];
       }
-    rc = build_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, ci2, v2);
-    if (rc) return rc;
+    int rc;
+    if (P == 1) {
+      h->row_begin[1] = m;
+      h->n_pad = n; h->m_pad = m;
+      h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
+      if ((rc = build_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp, ci, v))) return rc;
+      if ((rc = build_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, ci2, v2))) return rc;
+    } else {
+      std::vector<int64_t> prefix(static_cast<size_t>(m) + 1, 0);
+      for (int64_t i = 0; i < m; ++i) prefix[i + 1] = prefix[i] + (rp2[i + 1] - rp2[i]) + 2;
+      partition_rows(m, prefix, P, h->row_begin.data());
+      h->n_pad = (n + P - 1) / P;
+      h->n_pad += h->n_pad & 1;
+      h->m_pad = 0;
+      for (int r = 0; r < P; ++r) h->m_pad = std::max(h->m_pad, h->row_begin[r + 1] - h->row_begin[r]);
+      h->col0 = std::min<int64_t>(n, h->rank * h->n_pad);
+      h->n = std::min<int64_t>(n, (h->rank + 1) * h->n_pad) - h->col0;
+      h->row0 = h->row_begin[h->rank];
+      const int64_t row1 = h->row_begin[h->rank + 1];
+      h->m = row1 - h->row0;
+      h->neq = std::max<int64_t>(0, std::min<int64_t>(p->num_equalities, row1) - h->row0);
+      // A_r: local rows, global columns
+      const int k0 = rp2[h->row0], k1 = rp2[row1];
+      h->nnz = k1 - k0;
+      std::vector<int> lrp(static_cast<size_t>(h->m) + 1);
+      for (int64_t i = 0; i <= h->m; ++i) lrp[i] = rp2[h->row0 + i] - k0;
+      std::vector<int> lci(ci2.begin() + k0, ci2.begin() + k1);
+      std::vector<double> lv(v2.begin() + k0, v2.begin() + k1);
+      if ((rc = build_matrix(h, &h->A, static_cast<int>(h->m), static_cast<int>(n), lrp, lci, lv))) return rc;
+      // A_r': all n rows, local columns (row indices ascend inside a CSC column, so the
+      // local entries of a column are one contiguous run)
+      std::vector<int> trp(static_cast<size_t>(n) + 1, 0), tci;
+      std::vector<double> tv;
+      tci.reserve(static_cast<size_t>(h->nnz));
+      tv.reserve(static_cast<size_t>(h->nnz));
+      for (int64_t j = 0; j < n; ++j) {
+        for (int k = rp[j]; k < rp[j + 1]; ++k)
+          if (ci[k] >= h->row0 && ci[k] < row1) {
+            tci.push_back(static_cast<int>(ci[k] - h->row0));
+            tv.push_back(v[k]);
+          }
+        trp[j + 1] = static_cast<int>(tci.size());
+      }
+      if ((rc = build_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(h->m), trp, tci, tv))) return rc;
+    }
   }
 
-  // ---- vectors ----
+  // ---- vectors: primal-indexed arrays hold the local slice, dual-indexed arrays the local rows ----
   Bufs& B = h->B;
-  B.n = static_cast<int>(n); B.m = static_cast<int>(m); B.neq = static_cast<int>(h->neq);
+  const int64_t nl = h->n, ml = h->m;            // local lengths
+  const int64_t na = std::max(h->n_pad, nl);     // allocation lengths (exchange strides)
+  const int64_t ma = std::max(h->m_pad, ml);
+  const int64_t c0 = h->col0, r0 = h->row0;
+  B.n = static_cast<int>(nl); B.m = static_cast<int>(ml); B.neq = static_cast<int>(h->neq);
+  B.world = P; B.rank = h->rank;
+  B.xbar_off = P > 1 ? static_cast<int>(c0) : 0;
   B.grid_spmv = h->sm_count;
   B.grid_vec = h->sm_count * 8;
+  auto at = [](const double* v, int64_t off) { return v ? v + off : nullptr; };
   int rc;
   if ((rc = dev_alloc(h, &B.st, 1))) return rc;
   for (int k = 0; k < 2; ++k) {
-    if ((rc = dev_zeros(h, &B.x[k], n))) return rc;
-    if ((rc = dev_zeros(h, &B.y[k], m))) return rc;
-    if ((rc = dev_zeros(h, &B.aty[k], n))) return rc;
+    if ((rc = dev_zeros(h, &B.x[k], na))) return rc;
+    if ((rc = dev_zeros(h, &B.y[k], ma))) return rc;
+    if ((rc = dev_zeros(h, &B.aty[k], na))) return rc;
   }
-  if ((rc = dev_zeros(h, &B.xbar, n))) return rc;
-  if ((rc = dev_upload(h, &B.c, p->objective_vector, n, 0.0))) return rc;
-  if ((rc = dev_upload(h, &B.l, p->variable_lower_bound, n, 0.0))) return rc;
-  if ((rc = dev_upload(h, &B.u, p->variable_upper_bound, n, 0.0))) return rc;
-  if ((rc = dev_upload(h, &B.b, p->right_hand_side, m, 0.0))) return rc;
-  if ((rc = dev_zeros(h, &B.sum_x, n))) return rc;
-  if ((rc = dev_zeros(h, &B.sum_y, m))) return rc;
-  if ((rc = dev_zeros(h, &B.avg_x, n))) return rc;
-  if ((rc = dev_zeros(h, &B.avg_y, m))) return rc;
-  if ((rc = dev_zeros(h, &B.ax_avg, m))) return rc;
-  if ((rc = dev_zeros(h, &B.aty_avg, n))) return rc;
-  if ((rc = dev_zeros(h, &B.ax_cur, m))) return rc;
-  if ((rc = dev_zeros(h, &B.last_x, n))) return rc;   // create_last_restart_info, sp.jl:199-213
-  if ((rc = dev_zeros(h, &B.last_y, m))) return rc;
-  if ((rc = dev_zeros(h, &B.last_ax, m))) return rc;
-  if ((rc = dev_zeros(h, &B.last_aty, n))) return rc;
-  if ((rc = dev_upload(h, &B.D, p->variable_rescaling, n, 1.0))) return rc;
-  if ((rc = dev_upload(h, &B.E, p->constraint_rescaling, m, 1.0))) return rc;
+  if ((rc = dev_zeros(h, &B.xbar, P > 1 ? P * h->n_pad : n))) return rc;
+  if (P > 1) {
+    if ((rc = dev_zeros(h, &B.p_full, P * h->n_pad))) return rc;
+    if ((rc = dev_zeros(h, &B.aty_rs, na))) return rc;
+    if ((rc = dev_zeros(h, &B.sc_send, kScBlock))) return rc;
+    if ((rc = dev_zeros(h, &B.sc_recv, static_cast<size_t>(P) * kScBlock))) return rc;
+    if ((rc = dev_zeros(h, &h->d_rows, P * ma))) return rc;
+  }
+  if ((rc = dev_upload(h, &B.c, at(p->objective_vector, c0), nl, 0.0))) return rc;
+  if ((rc = dev_upload(h, &B.l, at(p->variable_lower_bound, c0), nl, 0.0))) return rc;
+  if ((rc = dev_upload(h, &B.u, at(p->variable_upper_bound, c0), nl, 0.0))) return rc;
+  if ((rc = dev_upload(h, &B.b, at(p->right_hand_side, r0), ml, 0.0))) return rc;
+  if ((rc = dev_zeros(h, &B.sum_x, na))) return rc;
+  if ((rc = dev_zeros(h, &B.sum_y, ma))) return rc;
+  if ((rc = dev_zeros(h, &B.avg_x, na))) return rc;
+  if ((rc = dev_zeros(h, &B.avg_y, ma))) return rc;
+  if ((rc = dev_zeros(h, &B.ax_avg, ma))) return rc;
+  if ((rc = dev_zeros(h, &B.aty_avg, na))) return rc;
+  if ((rc = dev_zeros(h, &B.ax_cur, ma))) return rc;
+  if ((rc = dev_zeros(h, &B.last_x, na))) return rc;   // create_last_restart_info, sp.jl:199-213
+  if ((rc = dev_zeros(h, &B.last_y, ma))) return rc;
+  if ((rc = dev_zeros(h, &B.last_ax, ma))) return rc;
+  if ((rc = dev_zeros(h, &B.last_aty, na))) return rc;
+  if ((rc = dev_upload(h, &B.D, at(p->variable_rescaling, c0), nl, 1.0))) return rc;
+  if ((rc = dev_upload(h, &B.E, at(p->constraint_rescaling, r0), ml, 1.0))) return rc;
   if ((rc = dev_upload(h, &B.c_orig,
-                       p->orig_objective_vector ? p->orig_objective_vector : p->objective_vector, n,
-                       0.0)))
+                       at(p->orig_objective_vector ? p->orig_objective_vector : p->objective_vector, c0),
+                       nl, 0.0)))
     return rc;
   if ((rc = dev_upload(h, &B.l_orig,
-                       p->orig_variable_lower_bound ? p->orig_variable_lower_bound
-                                                    : p->variable_lower_bound, n, 0.0)))
+                       at(p->orig_variable_lower_bound ? p->orig_variable_lower_bound
+                                                       : p->variable_lower_bound, c0), nl, 0.0)))
     return rc;
   if ((rc = dev_upload(h, &B.u_orig,
-                       p->orig_variable_upper_bound ? p->orig_variable_upper_bound
-                                                    : p->variable_upper_bound, n, 0.0)))
+                       at(p->orig_variable_upper_bound ? p->orig_variable_upper_bound
+                                                       : p->variable_upper_bound, c0), nl, 0.0)))
     return rc;
   if ((rc = dev_upload(h, &B.b_orig,
-                       p->orig_right_hand_side ? p->orig_right_hand_side : p->right_hand_side, m,
-                       0.0)))
+                       at(p->orig_right_hand_side ? p->orig_right_hand_side : p->right_hand_side, r0),
+                       ml, 0.0)))
     return rc;
-  if ((rc = dev_zeros(h, &B.tr_t, n + m))) return rc;
-  if ((rc = dev_zeros(h, &B.tr_d, n + m))) return rc;
+  if ((rc = dev_zeros(h, &B.tr_t, std::max(nl + ml, P > 1 ? P * std::max(na, ma) : n + m)))) return rc;
+  if ((rc = dev_zeros(h, &B.tr_d, std::max(nl + ml, n + m)))) return rc;
   if ((rc = dev_zeros(h, &B.part, static_cast<size_t>(kNumSlots) * kMaxScalars * kMaxPartialBlocks)))
     return rc;
   if ((rc = dev_zeros(h, &B.red, static_cast<size_t>(4) * kMaxScalars))) return rc;
@@ -413,17 +548,149 @@ extern "C" const char* folp_build_info(void) {
 }
 
 extern "C" int folp_nccl_unique_id(void* out128) {
-  if (out128) memset(out128, 0, 128);
-  return FOLP_UNSUPPORTED;
+  if (!out128) return FOLP_INVALID_ARGUMENT;
+  memset(out128, 0, 128);
+  const NcclApi* api = nccl_api(&g_create_error);
+  if (!api) return FOLP_NCCL_ERROR;
+  ncclUniqueId id;
+  const ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) {
+    g_create_error = std::string("ncclGetUniqueId: ") + api->GetErrorString(r);
+    return FOLP_NCCL_ERROR;
+  }
+  memcpy(out128, &id, sizeof(id));
+  return FOLP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// exchanges of the row-partitioned mode (no-ops / plain copies when world == 1)
+// ---------------------------------------------------------------------------
+// slice (n_pad readable doubles per rank) -> full (world * n_pad), rank-major
+static int allgather_cols(folp_handle* h, const double* slice, double* full) {
+  NCCL_TRY(h->nccl->AllGather(slice, full, static_cast<size_t>(h->n_pad), ncclDouble, h->comm,
+                              h->stream));
+  return FOLP_OK;
+}
+// full partial vectors (world * n_pad) -> their sum on this rank's slice
+static int reduce_scatter_cols(folp_handle* h, const double* full, double* slice) {
+  NCCL_TRY(h->nccl->ReduceScatter(full, slice, static_cast<size_t>(h->n_pad), ncclDouble, ncclSum,
+                                  h->comm, h->stream));
+  return FOLP_OK;
+}
+// B.sc_send -> B.sc_recv (device resident, consumed by k_finalize_dist / k_tr_combine)
+static int exchange_scalars_dev(folp_handle* h) {
+  NCCL_TRY(h->nccl->AllGather(h->B.sc_send, h->B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
+  return FOLP_OK;
+}
+// h->h_red[off .. off+count) <- the global value of the reduced scalars B.red[off ...):
+// the first nsum entries are sums, the rest maxima. Ranks are combined in rank order on
+// the host, so every rank sees the same bits. Synchronises the stream.
+static int pull_red(folp_handle* h, int off, int count, int nsum) {
+  if (h->world == 1) {
+    TRY(cudaMemcpyAsync(h->h_red + off, h->B.red + off, sizeof(double) * count,
+                        cudaMemcpyDeviceToHost, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+    return FOLP_OK;
+  }
+  NCCL_TRY(h->nccl->AllGather(h->B.red + off, h->B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
+  TRY(cudaMemcpyAsync(h->h_sc, h->B.sc_recv, sizeof(double) * h->world * kScBlock,
+                      cudaMemcpyDeviceToHost, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < count; ++k) {
+    double v = h->h_sc[k];
+    for (int r = 1; r < h->world; ++r) {
+      const double w = h->h_sc[r * kScBlock + k];
+      v = k < nsum ? v + w : fmax(v, w);
+    }
+    h->h_red[off + k] = v;
+  }
+  return FOLP_OK;
+}
+// out = A_r * v where v is a primal-indexed vector held as slices (local rows out)
+static int spmv_A(folp_handle* h, const double* v_slice, double* out_rows) {
+  const double* in = v_slice;
+  if (h->world > 1) {
+    int rc = allgather_cols(h, v_slice, h->B.xbar);
+    if (rc) return rc;
+    in = h->B.xbar;
+  }
+  launch_spmv_plain(h->A, in, out_rows, h->B.grid_spmv, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 1;
+  return FOLP_OK;
+}
+// out = (A' * w) on the local slice where w is dual-indexed, held as local rows
+static int spmv_At(folp_handle* h, const double* w_rows, double* out_slice) {
+  if (h->world == 1) {
+    launch_spmv_plain(h->At, w_rows, out_slice, h->B.grid_spmv, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 1;
+    return FOLP_OK;
+  }
+  launch_spmv_plain(h->At, w_rows, h->B.p_full, h->B.grid_spmv, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 1;
+  return reduce_scatter_cols(h, h->B.p_full, out_slice);
+}
+// host_out (global length) <- a primal-indexed device vector held as slices
+static int fetch_cols(folp_handle* h, const double* slice, double* host_out) {
+  if (!host_out || h->n_glob == 0) return FOLP_OK;
+  const double* src = slice;
+  if (h->world > 1) {
+    int rc = allgather_cols(h, slice, h->B.xbar);
+    if (rc) return rc;
+    src = h->B.xbar;
+  }
+  TRY(cudaMemcpyAsync(host_out, src, sizeof(double) * h->n_glob, cudaMemcpyDeviceToHost, h->stream));
+  return FOLP_OK;
+}
+// host_out (global length) <- a dual-indexed device vector held as local rows
+static int fetch_rows(folp_handle* h, const double* rows, double* host_out) {
+  if (!host_out || h->m_glob == 0) return FOLP_OK;
+  if (h->world == 1) {
+    TRY(cudaMemcpyAsync(host_out, rows, sizeof(double) * h->m_glob, cudaMemcpyDeviceToHost, h->stream));
+    return FOLP_OK;
+  }
+  NCCL_TRY(h->nccl->AllGather(rows, h->d_rows, static_cast<size_t>(h->m_pad), ncclDouble, h->comm,
+                              h->stream));
+  for (int r = 0; r < h->world; ++r) {
+    const int64_t cnt = h->row_begin[r + 1] - h->row_begin[r];
+    if (cnt > 0)
+      TRY(cudaMemcpyAsync(host_out + h->row_begin[r], h->d_rows + r * h->m_pad, sizeof(double) * cnt,
+                          cudaMemcpyDeviceToHost, h->stream));
+  }
+  return FOLP_OK;
 }
 
 // ---------------------------------------------------------------------------
 // take_step batches
 // ---------------------------------------------------------------------------
+static int launch_attempts_any(folp_handle* h, int attempts) {
+  if (h->world == 1) {
+    launch_step_attempts(h->B, h->A, h->At, attempts, h->stream);
+    return FOLP_OK;
+  }
+  const Bufs& B = h->B;
+  for (int a = 0; a < attempts; ++a) {
+    int rc;
+    launch_dist_primal(B, h->stream);
+    NCCL_TRY(h->nccl->AllGather(B.xbar + static_cast<size_t>(h->rank) * h->n_pad, B.xbar,
+                                static_cast<size_t>(h->n_pad), ncclDouble, h->comm, h->stream));
+    launch_dist_dual(B, h->A, h->stream);
+    launch_dist_trans_partial(B, h->At, h->stream);
+    if ((rc = reduce_scatter_cols(h, B.p_full, B.aty_rs))) return rc;
+    launch_dist_interaction(B, h->A, h->stream);
+    if ((rc = exchange_scalars_dev(h))) return rc;
+    launch_dist_finalize(B, h->stream);
+  }
+  return FOLP_OK;
+}
+
 static int enqueue_attempts(folp_handle* h, int attempts) {
   if (attempts <= 0) return FOLP_OK;
+  int rc;
   if (!h->use_graphs || attempts < 2) {
-    launch_step_attempts(h->B, h->A, h->At, attempts, h->stream);
+    if ((rc = launch_attempts_any(h, attempts))) return rc;
     CHECK_LAUNCH();
   } else {
     auto it = h->step_graphs.find(attempts);
@@ -431,15 +698,17 @@ static int enqueue_attempts(folp_handle* h, int attempts) {
       cudaGraph_t g = nullptr;
       cudaGraphExec_t ge = nullptr;
       TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      launch_step_attempts(h->B, h->A, h->At, attempts, h->stream);
-      TRY(cudaStreamEndCapture(h->stream, &g));
+      rc = launch_attempts_any(h, attempts);
+      cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+      if (rc) return rc;
+      TRY(ce);
       TRY(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
       it = h->step_graphs.emplace(attempts, ge).first;
     }
     TRY(cudaGraphLaunch(it->second, h->stream));
   }
-  h->launches += 3 * static_cast<int64_t>(attempts);
+  h->launches += (h->world == 1 ? 3 : 5) * static_cast<int64_t>(attempts);
   return FOLP_OK;
 }
 
@@ -482,10 +751,34 @@ struct BoundResult {
 static double get_gap(const BoundResult& r) { return r.upper_bound_value - r.lower_bound_value; }
 
 // One trust-region solve on device; *out receives the final TrState.
-static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
-  launch_tr(h->B, P, h->d_trs, 10, true, h->stream);
+static int tr_round(folp_handle* h, const TrProblem& P, int passes, bool init) {
+  if (h->world == 1) {
+    launch_tr(h->B, P, h->d_trs, passes, init, h->stream);
+    CHECK_LAUNCH();
+    h->launches += passes + 1 + (init ? 1 : 0);
+    return FOLP_OK;
+  }
+  // row-partitioned: every kernel leaves local sums, the ranks exchange them, and a
+  // one-thread kernel applies the totals -- identical TrState on every rank
+  int rc;
+  auto stage = [&](int st) -> int {
+    launch_tr_stage(h->B, P, h->d_trs, st, h->stream);
+    if ((rc = exchange_scalars_dev(h))) return rc;
+    launch_tr_combine(h->B, P, h->d_trs, st, h->stream);
+    h->launches += 2;
+    return FOLP_OK;
+  };
+  if (init && (rc = stage(kTrInit))) return rc;
+  for (int p = 0; p < passes; ++p)
+    if ((rc = stage(kTrPass))) return rc;
+  if ((rc = stage(kTrFinal))) return rc;
   CHECK_LAUNCH();
-  h->launches += 12;
+  return FOLP_OK;
+}
+
+static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
+  int rc;
+  if ((rc = tr_round(h, P, h->world == 1 ? 10 : 6, true))) return rc;
   h->tr_solves += 1;
   for (int round = 0;; ++round) {
     TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState), cudaMemcpyDeviceToHost, h->stream));
@@ -495,9 +788,7 @@ static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
       h->err = "trust-region search did not converge";
       return FOLP_CUDA_ERROR;
     }
-    launch_tr(h->B, P, h->d_trs, 16, false, h->stream);
-    CHECK_LAUNCH();
-    h->launches += 17;
+    if ((rc = tr_round(h, P, h->world == 1 ? 16 : 6, false))) return rc;
   }
   *out = *h->h_trs;
   h->tr_passes += out->passes;
@@ -572,9 +863,7 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
   launch_dist(B, red, h->stream);
   CHECK_LAUNCH();
   h->launches += 1;
-  TRY(cudaMemcpyAsync(h->h_red + 2 * kMaxScalars, red, sizeof(double) * SD_TOTAL,
-                      cudaMemcpyDeviceToHost, h->stream));
-  TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = pull_red(h, 2 * kMaxScalars, SD_TOTAL, SD_TOTAL))) return rc;
   const double* dist = h->h_red + 2 * kMaxScalars;
   const double avg_px = sqrt(wp * dist[SD_avg_x]), avg_dy = sqrt(wd * dist[SD_avg_y]);
   const double cur_px = sqrt(wp * dist[SD_cur_x]), cur_dy = sqrt(wd * dist[SD_cur_y]);
@@ -592,9 +881,7 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
     BoundResult g_avg, g_cur;
     if ((rc = euclidean_gap(h, B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, d_avg, &g_avg)))
       return rc;
-    launch_spmv_plain(h->A, B.x[s->cur], B.ax_cur, B.grid_spmv, h->stream);
-    CHECK_LAUNCH();
-    h->launches += 1;
+    if ((rc = spmv_A(h, B.x[s->cur], B.ax_cur))) return rc;
     have_ax_cur = 1;
     if ((rc = euclidean_gap(h, B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, d_cur,
                             &g_cur)))
@@ -679,15 +966,28 @@ static int evaluate(folp_handle* h, folp_eval* out) {
     s->pending_avg = 0;
   }
   launch_make_avg(B, use_current, h->stream);
-  launch_spmv_plain(h->A, B.avg_x, B.ax_avg, B.grid_spmv, h->stream);
-  launch_spmv_plain(h->At, B.avg_y, B.aty_avg, B.grid_spmv, h->stream);
+  if ((rc = spmv_A(h, B.avg_x, B.ax_avg))) return rc;
+  if ((rc = spmv_At(h, B.avg_y, B.aty_avg))) return rc;
   launch_stats_n(B, B.red, h->stream);
   launch_stats_m(B, B.red + kMaxScalars, h->stream);
   CHECK_LAUNCH();
-  h->launches += 5;
-  TRY(cudaMemcpyAsync(h->h_red, B.red, sizeof(double) * 2 * kMaxScalars, cudaMemcpyDeviceToHost,
-                      h->stream));
-  TRY(cudaStreamSynchronize(h->stream));
+  h->launches += 3;
+  if (h->world == 1) {
+    TRY(cudaMemcpyAsync(h->h_red, B.red, sizeof(double) * 2 * kMaxScalars, cudaMemcpyDeviceToHost,
+                        h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+  } else {
+    static_assert(2 * kMaxScalars <= kScBlock, "both statistics blocks travel in one exchange");
+    if ((rc = pull_red(h, 0, SN_TOTAL, SN_NSUM))) return rc;  // gathers all 64 scalars once
+    for (int k = 0; k < SM_TOTAL; ++k) {
+      double v = h->h_sc[kMaxScalars + k];
+      for (int r = 1; r < h->world; ++r) {
+        const double w = h->h_sc[r * kScBlock + kMaxScalars + k];
+        v = k < SM_NSUM ? v + w : fmax(v, w);
+      }
+      h->h_red[kMaxScalars + k] = v;
+    }
+  }
   const double* sn = h->h_red;
   const double* sm = h->h_red + kMaxScalars;
 
@@ -837,16 +1137,16 @@ extern "C" int folp_get_solution(folp_handle* h, int which, int unscaled, double
   } else {
     px = B.x[s->cur]; py = B.y[s->cur];
   }
-  // sp.jl:65-67; tr_t is free scratch outside a trust-region solve
-  launch_scale_div(px, unscaled ? B.D : nullptr, B.tr_t, B.n, B.grid_vec, h->stream);
-  launch_scale_div(py, unscaled ? B.E : nullptr, B.tr_t + B.n, B.m, B.grid_vec, h->stream);
+  // sp.jl:65-67; tr_t / tr_d / aty_rs are free scratch outside a trust-region solve / attempt
+  double* sx = h->world > 1 ? B.aty_rs : B.tr_t;
+  double* sy = B.tr_d;
+  launch_scale_div(px, unscaled ? B.D : nullptr, sx, B.n, B.grid_vec, h->stream);
+  launch_scale_div(py, unscaled ? B.E : nullptr, sy, B.m, B.grid_vec, h->stream);
   CHECK_LAUNCH();
   h->launches += 2;
-  if (x_out && B.n)
-    TRY(cudaMemcpyAsync(x_out, B.tr_t, sizeof(double) * B.n, cudaMemcpyDeviceToHost, h->stream));
-  if (y_out && B.m)
-    TRY(cudaMemcpyAsync(y_out, B.tr_t + B.n, sizeof(double) * B.m, cudaMemcpyDeviceToHost,
-                        h->stream));
+  int rc;
+  if ((rc = fetch_cols(h, sx, x_out))) return rc;
+  if ((rc = fetch_rows(h, sy, y_out))) return rc;
   TRY(cudaStreamSynchronize(h->stream));
   return FOLP_OK;
 }
@@ -911,13 +1211,16 @@ extern "C" int folp_debug_state(folp_handle* h, double* x, double* y, double* du
     h->launches += 2;
     s->pending_avg = 0;
   }
-  const size_t nb = sizeof(double) * B.n, mb = sizeof(double) * B.m;
-  if (x && nb) TRY(cudaMemcpyAsync(x, B.x[s->cur], nb, cudaMemcpyDeviceToHost, h->stream));
-  if (y && mb) TRY(cudaMemcpyAsync(y, B.y[s->cur], mb, cudaMemcpyDeviceToHost, h->stream));
-  if (dual_product && nb)
-    TRY(cudaMemcpyAsync(dual_product, B.aty[s->cur], nb, cudaMemcpyDeviceToHost, h->stream));
-  if (sum_x && nb) TRY(cudaMemcpyAsync(sum_x, B.sum_x, nb, cudaMemcpyDeviceToHost, h->stream));
-  if (sum_y && mb) TRY(cudaMemcpyAsync(sum_y, B.sum_y, mb, cudaMemcpyDeviceToHost, h->stream));
+  int rc;
+  if ((rc = fetch_cols(h, B.x[s->cur], x))) return rc;
+  if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));  // B.xbar staging is reused below
+  if ((rc = fetch_rows(h, B.y[s->cur], y))) return rc;
+  if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = fetch_cols(h, B.aty[s->cur], dual_product))) return rc;
+  if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = fetch_cols(h, B.sum_x, sum_x))) return rc;
+  if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = fetch_rows(h, B.sum_y, sum_y))) return rc;
   TRY(cudaStreamSynchronize(h->stream));
   if (out) {
     memset(out, 0, sizeof(*out));
@@ -944,12 +1247,14 @@ extern "C" int folp_debug_set_state(folp_handle* h, const double* x, const doubl
   DevState* s = h->hs;
   Bufs& B = h->B;
   if (x && B.n)
-    TRY(cudaMemcpyAsync(B.x[s->cur], x, sizeof(double) * B.n, cudaMemcpyHostToDevice, h->stream));
-  if (y && B.m) {
-    TRY(cudaMemcpyAsync(B.y[s->cur], y, sizeof(double) * B.m, cudaMemcpyHostToDevice, h->stream));
-    launch_spmv_plain(h->At, B.y[s->cur], B.aty[s->cur], B.grid_spmv, h->stream);
-    CHECK_LAUNCH();
-    h->launches += 1;
+    TRY(cudaMemcpyAsync(B.x[s->cur], x + h->col0, sizeof(double) * B.n, cudaMemcpyHostToDevice,
+                        h->stream));
+  if (y) {
+    if (B.m)
+      TRY(cudaMemcpyAsync(B.y[s->cur], y + h->row0, sizeof(double) * B.m, cudaMemcpyHostToDevice,
+                          h->stream));
+    int rc2 = spmv_At(h, B.y[s->cur], B.aty[s->cur]);
+    if (rc2) return rc2;
   }
   if (step_size > 0) s->step_size = s->trial_step = s->avg_weight = step_size;
   if (primal_weight > 0) s->primal_weight = primal_weight;
@@ -963,16 +1268,23 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
   if (!h || !in || !out) return FOLP_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   Bufs& B = h->B;
-  const int len_in = transpose ? B.m : B.n, len_out = transpose ? B.n : B.m;
-  double* d_in = B.tr_t;            // scratch, n+m
-  double* d_out = B.tr_d;
-  if (len_in)
-    TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * len_in, cudaMemcpyHostToDevice, h->stream));
-  launch_spmv_plain(transpose ? h->At : h->A, d_in, d_out, B.grid_spmv, h->stream);
-  CHECK_LAUNCH();
-  h->launches += 1;
-  if (len_out)
-    TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * len_out, cudaMemcpyDeviceToHost, h->stream));
+  int rc;
+  if (!transpose) {  // in: global n -> out: global m
+    double* d_in = h->world > 1 ? B.xbar : B.tr_t;
+    if (h->n_glob)
+      TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * h->n_glob, cudaMemcpyHostToDevice, h->stream));
+    launch_spmv_plain(h->A, d_in, B.tr_d, B.grid_spmv, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 1;
+    if ((rc = fetch_rows(h, B.tr_d, out))) return rc;
+  } else {  // in: global m -> out: global n
+    if (B.m)
+      TRY(cudaMemcpyAsync(B.tr_t, in + h->row0, sizeof(double) * B.m, cudaMemcpyHostToDevice,
+                          h->stream));
+    double* d_out = h->world > 1 ? B.aty_rs : B.tr_d;
+    if ((rc = spmv_At(h, B.tr_t, d_out))) return rc;
+    if ((rc = fetch_cols(h, d_out, out))) return rc;
+  }
   TRY(cudaStreamSynchronize(h->stream));
   return FOLP_OK;
 }
@@ -980,6 +1292,10 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
 extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
                                            int64_t* attempts_run) {
   if (!h || !ms_out) return FOLP_INVALID_ARGUMENT;
+  if (h->world > 1) {
+    h->err = "folp_debug_profile_attempts times the fused single-GPU kernels only";
+    return FOLP_UNSUPPORTED;
+  }
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   int rc;
@@ -1011,7 +1327,7 @@ extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, dou
   cudaSetDevice(h->device);
   Bufs& B = h->B;
   // input: the live iterate (x or y); output: trust-region scratch
-  const double* in = transpose ? B.y[h->hs->cur] : B.x[h->hs->cur];
+  const double* in = transpose ? B.y[h->hs->cur] : (h->world > 1 ? B.xbar : B.x[h->hs->cur]);
   for (int w = 0; w < 3; ++w)
     launch_spmv_plain(transpose ? h->At : h->A, in, B.tr_d, B.grid_spmv, h->stream);
   TRY(cudaEventRecord(h->ev0, h->stream));
@@ -1035,5 +1351,16 @@ extern "C" int folp_counters(folp_handle* h, int64_t* kernel_launches,
   if (kernel_launches) *kernel_launches = h->launches;
   if (basic_algorithm_seconds) *basic_algorithm_seconds = h->basic_time;
   if (iterations) *iterations = h->hs->iterations;
+  return FOLP_OK;
+}
+
+extern "C" int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end,
+                               int64_t* col_begin, int64_t* col_end, int64_t* local_nonzeros) {
+  if (!h) return FOLP_INVALID_ARGUMENT;
+  if (row_begin) *row_begin = h->row0;
+  if (row_end) *row_end = h->row0 + h->m;
+  if (col_begin) *col_begin = h->col0;
+  if (col_end) *col_end = h->col0 + h->n;
+  if (local_nonzeros) *local_nonzeros = h->nnz;
   return FOLP_OK;
 }

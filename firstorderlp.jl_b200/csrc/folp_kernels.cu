@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     const double d1 = primal_elem(k, x.y, xp.y, c.y, a.y, l.y, u.y, sx.y, xb.y);
     if (avg) reinterpret_cast<double2*>(B.sum_x)[j] = sx;
     if (k.do_primal) reinterpret_cast<double2*>(xn)[j] = xp;
-    reinterpret_cast<double2*>(B.xbar)[j] = xb;
+    reinterpret_cast<double2*>(B.xbar + B.xbar_off)[j] = xb;
     acc += d0 * d0;
     acc += d1 * d1;
   }
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     const double d = primal_elem(k, xc[j], xp, B.c[j], at[j], B.l[j], B.u[j], sx, xb);
     if (avg) B.sum_x[j] = sx;
     if (k.do_primal) xn[j] = xp;
-    B.xbar[j] = xb;
+    B.xbar[B.xbar_off + j] = xb;
     acc += d * d;
   }
   const double t = block_reduce<false>(acc, sh);
@@ -297,6 +297,84 @@ struct EpiTrans {
   }
 };
 
+// ---------------------------------------------------------------------------
+// row-partitioned take_step (world > 1). Same arithmetic as the fused single-GPU
+// kernels, cut where the exchanges sit:
+//   k_primal (slice)  -> allgather xbar -> k_spmv<EpiDual> (local rows)
+//   -> k_spmv<EpiPlain> p = A_r' y_r+  -> reduce-scatter -> k_interaction (slice)
+//   -> allgather {|dx|^2, |dy|^2, dx.dA'y, |dA'y|^2} -> k_finalize_dist
+// Every rank sums the gathered scalars in rank order, so all ranks take the same
+// accept/reject decision and step size bit for bit.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVecThreads) k_interaction(Bufs B, int g_primal, int g_dual) {
+  __shared__ double sh[32];
+  const DevState& s = *B.st;
+  if (!s.active) return;
+  const double* __restrict__ xc = sel(B.x, s.cur);
+  const double* __restrict__ xn = sel(B.x, s.cur ^ 1);
+  const double* __restrict__ atc = sel(B.aty, s.cur);
+  double* __restrict__ atn = sel(B.aty, s.cur ^ 1);
+  double inter = 0.0, dp2 = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
+    const double at = B.aty_rs[j];
+    atn[j] = at;
+    const double dx = xn[j] - xc[j];
+    const double dat = at - atc[j];
+    inter += dx * dat;  // pdhg.jl:542-544
+    dp2 += dat * dat;   // pdhg.jl:615 (Malitsky-Pock)
+  }
+  const double a = block_reduce<false>(inter, sh);
+  const double b = block_reduce<false>(dp2, sh);
+  if (threadIdx.x == 0) {
+    part_ptr(B, kSlotTrans, 0)[blockIdx.x] = a;
+    part_ptr(B, kSlotTrans, 1)[blockIdx.x] = b;
+  }
+  if (!last_block_arrive(B.counters + kSlotTrans)) return;
+  const double dx2 = reduce_partials<false>(part_ptr(B, kSlotPrimal, 0), g_primal, sh);
+  const double dy2 = reduce_partials<false>(part_ptr(B, kSlotDual, 0), g_dual, sh);
+  const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
+  const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
+  if (threadIdx.x == 0) {
+    B.sc_send[0] = dx2;
+    B.sc_send[1] = dy2;
+    B.sc_send[2] = it;
+    B.sc_send[3] = dp;
+  }
+}
+
+__global__ void k_finalize_dist(Bufs B) {
+  if (threadIdx.x != 0 || !B.st->active) return;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < B.world; ++r)
+    for (int k = 0; k < 4; ++k) t[k] += B.sc_recv[r * kScBlock + k];
+  finalize_attempt(B.st, t[0], t[1], t[2], t[3]);
+}
+
+static int spmv_grid(const SpmvMat& A, int grid_spmv);
+
+void launch_dist_primal(const Bufs& B, cudaStream_t s) {
+  k_primal<<<B.grid_vec, kVecThreads, 0, s>>>(B);
+}
+void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
+  EpiDual ed;
+  ed.B = B;
+  k_spmv<EpiDual><<<spmv_grid(A, B.grid_spmv), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
+}
+void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s) {
+  EpiPlain ep;
+  ep.in = nullptr;
+  ep.out = B.p_full;
+  ep.gate = B.st;
+  ep.next0 = B.y[0];
+  ep.next1 = B.y[1];
+  k_spmv<EpiPlain><<<spmv_grid(At, B.grid_spmv), kSpmvThreads, kSpmvSmemBytes, s>>>(At, ep);
+}
+void launch_dist_interaction(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
+  k_interaction<<<B.grid_vec, kVecThreads, 0, s>>>(B, B.grid_vec, spmv_grid(A, B.grid_spmv));
+}
+void launch_dist_finalize(const Bufs& B, cudaStream_t s) { k_finalize_dist<<<1, 32, 0, s>>>(B); }
+
 int spmv_configure() {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_spmv<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -355,6 +433,7 @@ void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid
   EpiPlain ep;
   ep.in = in;
   ep.out = out;
+  ep.gate = nullptr;
   k_spmv<EpiPlain><<<spmv_grid(A, grid), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ep);
 }
 
@@ -649,6 +728,66 @@ __device__ void tr_next_candidates(TrState& t) {
   t.cand[1] = bit_mid(c0, t.hi);
 }
 
+// Starts the search from the global sums of k_tr_init (thread 0 only).
+__device__ void tr_setup(TrState* trs, const double* r, const TrProblem& P) {
+  TrState t;
+  t.radius = P.radius;
+  t.r2 = P.radius * P.radius;
+  t.lo = 0.0; t.L_lo = 0.0; t.H_lo = r[TI_H0];
+  t.cnt_lo = static_cast<long long>(r[TI_cnt0]);
+  t.hi = r[TI_max_t];
+  t.max_t = r[TI_max_t];
+  t.cand[0] = t.cand[1] = 0.0;
+  t.tau = 0.0;
+  t.done = 0; t.zero_value = 0; t.approx = P.approx; t.passes = 0;
+  t.approx_scale = 1.0;
+  t.cx = r[TI_cx]; t.x_aty = r[TI_xaty]; t.y_b = r[TI_yb];
+  t.v_primal = 0.0; t.v_dual = 0.0;
+  if (P.approx) {
+    const double nrm = sqrt(r[TI_norm2]);
+    if (nrm > 0.0) t.approx_scale = P.radius / nrm;
+    t.v_primal = r[TI_gdp] * t.approx_scale;
+    t.v_dual = r[TI_gdd] * t.approx_scale;
+    t.done = 1; t.zero_value = 1;  // no final pass needed
+  } else if (P.radius == 0.0 || r[TI_g2] == 0.0 || r[TI_H0] == 0.0) {  // tr.jl:88-91
+    t.done = 1; t.zero_value = 1;
+  } else if (r[TI_Hinf] == 0.0 && r[TI_Ltot] < t.r2) {  // everything reaches its bound, tr.jl:175-177
+    t.tau = t.max_t; t.done = 1;
+  } else if (r[TI_Hinf] > 0.0 && r[TI_Ltot] <= t.r2 &&
+             sqrt((t.r2 - r[TI_Ltot]) / r[TI_Hinf]) >= t.max_t) {
+    t.tau = sqrt((t.r2 - r[TI_Ltot]) / r[TI_Hinf]); t.done = 1;
+  } else {
+    tr_next_candidates(t);
+  }
+  *trs = t;
+}
+
+// One Newton / bisection step from the global sums {L0,H0,cnt0,L1,H1,cnt1} of k_tr_pass.
+__device__ void tr_update(TrState* trs, const double* r) {
+  TrState t = *trs;
+  const double c0 = t.cand[0], c1 = t.cand[1];
+  t.passes += 1;
+  const long long cnt0 = static_cast<long long>(r[2]), cnt1 = static_cast<long long>(r[5]);
+  if (cnt0 == t.cnt_lo) {  // partition unchanged: cand[0] is the fixed point
+    t.tau = c0;
+    t.done = 1;
+  } else {
+    t.lo = c0; t.L_lo = r[0]; t.H_lo = r[1]; t.cnt_lo = cnt0;
+    if (c1 > c0 && c1 < t.hi) {
+      const double F1 = r[3] + c1 * c1 * r[4];
+      if (F1 < t.r2) { t.lo = c1; t.L_lo = r[3]; t.H_lo = r[4]; t.cnt_lo = cnt1; }
+      else t.hi = c1;
+    }
+    if (t.H_lo <= 0.0) {  // nothing left above lo
+      t.tau = t.max_t;
+      t.done = 1;
+    } else {
+      tr_next_candidates(t);
+    }
+  }
+  *trs = t;
+}
+
 __global__ void __launch_bounds__(kVecThreads) k_tr_init(Bufs B, TrProblem P, TrState* trs,
                                                          double* red) {
   __shared__ double sh[32];
@@ -711,37 +850,12 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_init(Bufs B, TrProblem P, Tr
   r[TI_max_t] = reduce_partials<true>(part + static_cast<size_t>(TI_max_t) * kMaxPartialBlocks,
                                       gridDim.x, sh);
   if (threadIdx.x != 0) return;
-  for (int k = 0; k < TI_TOTAL; ++k) red[k] = r[k];
-  TrState t;
-  t.radius = P.radius;
-  t.r2 = P.radius * P.radius;
-  t.lo = 0.0; t.L_lo = 0.0; t.H_lo = r[TI_H0];
-  t.cnt_lo = static_cast<long long>(r[TI_cnt0]);
-  t.hi = r[TI_max_t];
-  t.max_t = r[TI_max_t];
-  t.cand[0] = t.cand[1] = 0.0;
-  t.tau = 0.0;
-  t.done = 0; t.zero_value = 0; t.approx = P.approx; t.passes = 0;
-  t.approx_scale = 1.0;
-  t.cx = r[TI_cx]; t.x_aty = r[TI_xaty]; t.y_b = r[TI_yb];
-  t.v_primal = 0.0; t.v_dual = 0.0;
-  if (P.approx) {
-    const double nrm = sqrt(r[TI_norm2]);
-    if (nrm > 0.0) t.approx_scale = P.radius / nrm;
-    t.v_primal = r[TI_gdp] * t.approx_scale;
-    t.v_dual = r[TI_gdd] * t.approx_scale;
-    t.done = 1; t.zero_value = 1;  // no final pass needed
-  } else if (P.radius == 0.0 || r[TI_g2] == 0.0 || r[TI_H0] == 0.0) {  // tr.jl:88-91
-    t.done = 1; t.zero_value = 1;
-  } else if (r[TI_Hinf] == 0.0 && r[TI_Ltot] < t.r2) {  // everything reaches its bound, tr.jl:175-177
-    t.tau = t.max_t; t.done = 1;
-  } else if (r[TI_Hinf] > 0.0 && r[TI_Ltot] <= t.r2 &&
-             sqrt((t.r2 - r[TI_Ltot]) / r[TI_Hinf]) >= t.max_t) {
-    t.tau = sqrt((t.r2 - r[TI_Ltot]) / r[TI_Hinf]); t.done = 1;
-  } else {
-    tr_next_candidates(t);
+  if (B.world > 1) {  // local sums only; tr_setup runs after the scalar exchange
+    for (int k = 0; k < TI_TOTAL; ++k) B.sc_send[k] = r[k];
+    return;
   }
-  *trs = t;
+  for (int k = 0; k < TI_TOTAL; ++k) red[k] = r[k];
+  tr_setup(trs, r, P);
 }
 
 __global__ void __launch_bounds__(kVecThreads) k_tr_pass(Bufs B, TrProblem P, TrState* trs) {
@@ -772,27 +886,11 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_pass(Bufs B, TrProblem P, Tr
   for (int k = 0; k < 6; ++k)
     r[k] = reduce_partials<false>(part + static_cast<size_t>(k) * kMaxPartialBlocks, gridDim.x, sh);
   if (threadIdx.x != 0) return;
-  TrState t = *trs;
-  t.passes += 1;
-  const long long cnt0 = static_cast<long long>(r[2]), cnt1 = static_cast<long long>(r[5]);
-  if (cnt0 == t.cnt_lo) {  // partition unchanged: cand[0] is the fixed point
-    t.tau = c0;
-    t.done = 1;
-  } else {
-    t.lo = c0; t.L_lo = r[0]; t.H_lo = r[1]; t.cnt_lo = cnt0;
-    if (c1 > c0 && c1 < t.hi) {
-      const double F1 = r[3] + c1 * c1 * r[4];
-      if (F1 < t.r2) { t.lo = c1; t.L_lo = r[3]; t.H_lo = r[4]; t.cnt_lo = cnt1; }
-      else t.hi = c1;
-    }
-    if (t.H_lo <= 0.0) {  // nothing left above lo
-      t.tau = t.max_t;
-      t.done = 1;
-    } else {
-      tr_next_candidates(t);
-    }
+  if (B.world > 1) {
+    for (int k = 0; k < 6; ++k) B.sc_send[k] = r[k];
+    return;
   }
-  *trs = t;
+  tr_update(trs, r);
 }
 
 __global__ void __launch_bounds__(kVecThreads) k_tr_final(Bufs B, TrProblem P, TrState* trs) {
@@ -822,8 +920,37 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_final(Bufs B, TrProblem P, T
   const double vp = reduce_partials<false>(part, gridDim.x, sh);
   const double vd = reduce_partials<false>(part + kMaxPartialBlocks, gridDim.x, sh);
   if (threadIdx.x == 0) {
-    trs->v_primal = vp;
-    trs->v_dual = vd;
+    if (B.world > 1) {
+      B.sc_send[0] = vp;
+      B.sc_send[1] = vd;
+    } else {
+      trs->v_primal = vp;
+      trs->v_dual = vd;
+    }
+  }
+}
+
+// row-partitioned mode: applies the rank-ordered totals of the exchanged local sums
+__global__ void k_tr_combine(Bufs B, TrProblem P, TrState* trs, int stage) {
+  if (threadIdx.x != 0) return;
+  double r[TI_TOTAL];
+  const int count = stage == kTrInit ? TI_TOTAL : (stage == kTrPass ? 6 : 2);
+  for (int k = 0; k < count; ++k) {
+    const bool is_max = stage == kTrInit && k == TI_max_t;
+    double v = is_max ? -CUDART_INF : 0.0;
+    for (int q = 0; q < B.world; ++q) {
+      const double w = B.sc_recv[q * kScBlock + k];
+      v = is_max ? fmax(v, w) : v + w;
+    }
+    r[k] = v;
+  }
+  if (stage == kTrInit) {
+    tr_setup(trs, r, P);
+  } else if (stage == kTrPass) {
+    if (!trs->done) tr_update(trs, r);
+  } else if (trs->done && !trs->zero_value) {
+    trs->v_primal = r[0];
+    trs->v_dual = r[1];
   }
 }
 
@@ -832,6 +959,15 @@ void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bo
   if (init) k_tr_init<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs, B.red);
   for (int p = 0; p < passes; ++p) k_tr_pass<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
   k_tr_final<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
+}
+
+void launch_tr_stage(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s) {
+  if (stage == kTrInit) k_tr_init<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs, B.red);
+  else if (stage == kTrPass) k_tr_pass<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
+  else k_tr_final<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
+}
+void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s) {
+  k_tr_combine<<<1, 32, 0, s>>>(B, P, d_trs, stage);
 }
 
 // ---------------------------------------------------------------------------
@@ -852,6 +988,18 @@ __global__ void __launch_bounds__(kVecThreads) k_fill(double* p, double v, int64
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride)
     p[i] = v;
+}
+__global__ void __launch_bounds__(kVecThreads) k_copy(const double* __restrict__ in,
+                                                       double* __restrict__ out, int64_t len) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride)
+    out[i] = in[i];
+}
+void launch_copy(const double* in, double* out, int64_t len, cudaStream_t s) {
+  if (len <= 0) return;
+  int64_t g = (len + kVecThreads - 1) / kVecThreads;
+  if (g > 1184) g = 1184;
+  k_copy<<<static_cast<int>(g), kVecThreads, 0, s>>>(in, out, len);
 }
 void launch_fill(double* p, double v, int64_t len, cudaStream_t s) {
   if (len <= 0) return;

@@ -25,7 +25,18 @@ struct Bufs {
   double* red = nullptr;      // reduced scalars, kMaxScalars per slot
   unsigned* counters = nullptr;
   int grid_vec = 0, grid_spmv = 0;
+  // ---- row-partitioned mode (world > 1); see DESIGN.md "Multi-GPU" ----
+  // n / m above are then the local primal slice length and the local row count;
+  // xbar is the FULL extrapolated primal (world * n_pad doubles) of which this rank
+  // writes [xbar_off, xbar_off + n).
+  int world = 1, rank = 0;
+  int xbar_off = 0;
+  double* p_full = nullptr;    // this rank's partial A_r' * y_r, world * n_pad doubles
+  double* aty_rs = nullptr;    // reduce-scatter result: (A' y+) on the local slice
+  double* sc_send = nullptr;   // kScBlock scalars this rank contributes to an exchange
+  double* sc_recv = nullptr;   // world * kScBlock scalars, rank-major
 };
+constexpr int kScBlock = 64;
 
 constexpr int kSlotPrimal = 0, kSlotDual = 1, kSlotTrans = 2, kSlotEval = 3;
 constexpr int kNumSlots = 4;
@@ -71,10 +82,18 @@ struct TrProblem {
 
 void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, int attempts,
                           cudaStream_t s);
+// The pieces of one attempt in row-partitioned mode; folp_api.cu interleaves them with the
+// NCCL exchanges (allgather xbar | reduce-scatter A'y | allgather of the 4 step-rule scalars).
+void launch_dist_primal(const Bufs& B, cudaStream_t s);
+void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s);
+void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s);
+void launch_dist_interaction(const Bufs& B, const SpmvMat& A, cudaStream_t s);
+void launch_dist_finalize(const Bufs& B, cudaStream_t s);
 // one attempt with events ev[0..3] recorded before/between/after the three kernels
 void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaEvent_t* ev,
                                cudaStream_t s);
 void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid, cudaStream_t s);
+void launch_copy(const double* in, double* out, int64_t len, cudaStream_t s);
 void launch_flush_avg(const Bufs& B, cudaStream_t s);
 void launch_make_avg(const Bufs& B, int use_current, cudaStream_t s);
 // results in B.red + kSlotEval*kMaxScalars ... see folp_api.cu
@@ -84,6 +103,12 @@ void launch_dist(const Bufs& B, double* red_out, cudaStream_t s);
 void launch_apply_restart(const Bufs& B, int to_average, int have_ax_cur, cudaStream_t s);
 void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bool init,
                cudaStream_t s);
+// row-partitioned mode: one kernel of the trust-region solve at a time; each leaves its
+// local sums in B.sc_send, and after the host's scalar exchange launch_tr_combine applies
+// the rank-ordered totals to the TrState.
+enum TrStage : int { kTrInit = 0, kTrPass = 1, kTrFinal = 2 };
+void launch_tr_stage(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s);
+void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s);
 void launch_scale_div(const double* in, const double* scale, double* out, int len, int grid,
                       cudaStream_t s);
 void launch_fill(double* p, double v, int64_t len, cudaStream_t s);

@@ -22,7 +22,7 @@ _pd = C.POINTER(C.c_double)
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
-    "folp_nccl_unique_id", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
+    "folp_nccl_unique_id", "folp_partition", "folp_shard_info", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
     "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
@@ -58,6 +58,9 @@ def lib() -> C.CDLL:
                 "folp_b200 has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         L.folp_nccl_unique_id.argtypes = [C.c_void_p]
+        _pi64 = C.POINTER(C.c_int64)
+        L.folp_partition.argtypes = [C.c_int64, C.c_int64, C.c_int64, _pi64, C.c_int32, C.c_int32, _pi64, _pi64]
+        L.folp_shard_info.argtypes = [C.c_void_p, _pi64, _pi64, _pi64, _pi64, _pi64]
         L.folp_create.argtypes = [C.POINTER(FolpProblem), C.POINTER(FolpParams), C.POINTER(FolpDist),
                                   C.POINTER(C.c_void_p)]
         L.folp_run.argtypes = [C.c_void_p, C.POINTER(FolpEval)]
@@ -94,6 +97,41 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_pd)
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId (rank 0 creates it, the host broadcasts it)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().folp_nccl_unique_id(buf)
+    if rc != 0:
+        raise FolpError(rc, lib().folp_last_error(None).decode())
+    return buf.raw
+
+
+def partition(constraint_matrix, world_size: int):
+    """The 1-D partition folp_create applies: (row_begin[world+1], col_begin[world+1])."""
+    import scipy.sparse as sp
+    A = sp.csc_matrix(constraint_matrix)
+    m, n = A.shape
+    rowval = np.ascontiguousarray(A.indices, dtype=np.int64)
+    rb = np.zeros(world_size + 1, dtype=np.int64)
+    cb = np.zeros(world_size + 1, dtype=np.int64)
+    _pi64 = C.POINTER(C.c_int64)
+    rc = lib().folp_partition(m, n, A.nnz, rowval.ctypes.data_as(_pi64), 0, world_size,
+                              rb.ctypes.data_as(_pi64), cb.ctypes.data_as(_pi64))
+    if rc != 0:
+        raise FolpError(rc, "folp_partition: invalid argument")
+    return rb, cb
+
+
+def make_dist(rank: int, world_size: int, device: int, unique_id: Optional[bytes]):
+    """folp_dist for one rank; keep the returned object alive until Solver() returns."""
+    d = FolpDist()
+    d.rank, d.world_size, d.device = rank, world_size, device
+    if unique_id is not None:
+        d._id = C.create_string_buffer(unique_id, 128)
+        d.nccl_unique_id = C.cast(d._id, C.c_void_p)
+    return d
+
+
 class Solver:
     """One folp_handle: the device-resident PDHG state of one optimize() call."""
 
@@ -104,6 +142,10 @@ class Solver:
         self.m = problem_holder.struct.num_constraints
         self._h = C.c_void_p()
         L = lib()
+        if dist is None:  # under torchrun after distributed.init(): join all ranks
+            from . import distributed
+            dist = distributed.new_dist()
+        self.dist = dist
         rc = L.folp_create(problem_holder.byref(), C.byref(params),
                            C.byref(dist) if dist is not None else None, C.byref(self._h))
         if rc != 0:
@@ -185,6 +227,12 @@ class Solver:
         ms = C.c_double()
         self._check(lib().folp_debug_time_spmv(self._h, int(transpose), int(reps), C.cast(C.byref(ms), _pd)))
         return ms.value
+
+    def shard_info(self):
+        v = [C.c_int64() for _ in range(5)]
+        self._check(lib().folp_shard_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("row_begin", "row_end", "col_begin", "col_end", "local_nonzeros"),
+                        (x.value for x in v)))
 
     def stream(self) -> int:
         return int(lib().folp_debug_stream(self._h) or 0)

@@ -231,10 +231,18 @@ typedef struct folp_eval {
 typedef struct folp_handle folp_handle;
 
 /* Multi-GPU: one process per GPU (torchrun). Each rank passes the FULL scaled
- * problem; the library keeps only its nnz-balanced row block. nccl_unique_id
- * is the 128-byte ncclUniqueId created on rank 0 by folp_nccl_unique_id() and
- * broadcast by the host's own plumbing (torch.distributed); NULL when
- * world_size == 1. */
+ * problem; the library keeps only its shard of the 1-D row partition: a
+ * contiguous block of constraint rows balanced by nonzeros (A_r in CSR and
+ * A_r' in CSR, y, b, dual averages) and an equal slice of the primal side
+ * (x, c, l, u, A'y, primal averages). Per take_step attempt the ranks exchange
+ * the extrapolated primal (allgather), the partial products A_r' y_r
+ * (reduce-scatter) and four step-rule scalars (allgather, summed in rank order
+ * so that every rank takes the same decision). Every rank must make the same
+ * sequence of calls; records and solutions returned are the global ones on
+ * every rank. nccl_unique_id is the 128-byte ncclUniqueId created on rank 0 by
+ * folp_nccl_unique_id() and broadcast by the host's own plumbing
+ * (torch.distributed); NULL when world_size == 1. NCCL is bound at run time
+ * (dlopen of libnccl.so.2), so a single-GPU host needs none. */
 typedef struct folp_dist {
   int32_t rank;
   int32_t world_size;
@@ -245,6 +253,17 @@ typedef struct folp_dist {
 
 /* Fills 128 bytes. */
 int folp_nccl_unique_id(void* out128);
+
+/* The partition folp_create applies, as pure host arithmetic (no device needed):
+ * row_begin_out[world_size + 1] and col_begin_out[world_size + 1] receive the
+ * first global row / column of every rank. rowval: the CSC row indices. */
+int folp_partition(int64_t num_constraints, int64_t num_variables, int64_t num_nonzeros,
+                   const int64_t* rowval, int32_t index_base, int32_t world_size,
+                   int64_t* row_begin_out, int64_t* col_begin_out);
+
+/* What this rank holds: rows [row_begin,row_end), primal slice [col_begin,col_end). */
+int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end, int64_t* col_begin,
+                    int64_t* col_end, int64_t* local_nonzeros);
 
 /* Replaces pdhg.jl:805-873: uploads, builds the device layouts (tiled CSR of A
  * and of A'), zero iterates, RestartInfo, averages. dist may be NULL
@@ -308,6 +327,7 @@ int folp_counters(folp_handle* h, int64_t* kernel_launches,
  * three kernels, and returns the accumulated device milliseconds of
  * {primal step, A*xbar + dual step, A'*y + interaction/step rule} plus the
  * number of attempts that did work. The solver state advances. */
+/* (single GPU only) */
 int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
                                 int64_t* attempts_run);
 

@@ -1,0 +1,92 @@
+"""Row-partitioned (multi-GPU) parity worker. Launch:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port P tests/dist_worker.py
+
+Every rank runs the same GPU-vs-oracle checks as tests/test_gpu_parity.py, with the GPU
+solver spread over all ranks (folp_b200.distributed makes every Solver join the ranks)."""
+import os
+import sys
+import traceback
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    import torch
+    import folp_b200
+    from folp_b200 import RestartScheme, distributed
+    from folp_b200.lib import Solver
+    from folp_b200.synthetic import random_sparse_lp
+
+    st = distributed.init("nccl")
+    assert st is not None, "launch with torchrun, world_size >= 2"
+    rank, world = st["rank"], st["world_size"]
+    import test_gpu_parity as T
+    from shared_problems import generate_pdhg_params
+
+    failures = []
+
+    def check(name, fn):
+        try:
+            fn()
+            if rank == 0:
+                print(f"[dist x{world}] {name}: ok", flush=True)
+        except Exception:  # every rank keeps the same call sequence as long as all fail alike
+            failures.append(name)
+            print(f"[dist x{world}] rank {rank} {name}: FAILED\n{traceback.format_exc()}", flush=True)
+            raise
+
+    # the shard layout is the exported partition
+    problem = random_sparse_lp(3000, 2500, 8, seed=5)
+    params = generate_pdhg_params(iteration_limit=10)
+    o, g = T._pair(problem, params)
+    info = g.shard_info()
+    rb, cb = folp_b200.lib.partition(problem.constraint_matrix, world)
+    assert (info["row_begin"], info["row_end"]) == (rb[rank], rb[rank + 1]), (info, rb)
+    assert (info["col_begin"], info["col_end"]) == (cb[rank], cb[rank + 1]), (info, cb)
+    o.close(); g.close()
+
+    for i, make in enumerate([lambda: random_sparse_lp(3000, 2500, 8, seed=5), T.netlib_shaped_lp,
+                              T._ragged_lp, lambda: T.pagerank_lp(3000)]):
+        check(f"spmv[{i}]", lambda make=make: T.test_spmv_matches_oracle(make))
+    check("single_attempt[random]", lambda: T.test_single_attempt_parity(
+        lambda: random_sparse_lp(4000, 3000, 10, seed=11)))
+    check("single_attempt[ragged]", lambda: T.test_single_attempt_parity(T._ragged_lp))
+    check("trajectory_no_restarts", T.test_trajectory_parity_no_restarts)
+    for scheme in (RestartScheme.NO_RESTARTS, RestartScheme.ADAPTIVE_NORMALIZED,
+                   RestartScheme.FIXED_FREQUENCY, RestartScheme.ADAPTIVE_LOCALIZED,
+                   RestartScheme.ADAPTIVE_DISTANCE):
+        check(f"eval_records[{scheme.name}]", lambda scheme=scheme: T.test_eval_records_match_oracle(scheme))
+    check("full_solve[random]", lambda: T.test_full_solve_matches_oracle(
+        lambda: random_sparse_lp(2000, 1500, 8, seed=41), 1e-6))
+    check("full_solve[pagerank]", lambda: T.test_full_solve_matches_oracle(lambda: T.pagerank_lp(2000), 1e-8))
+    check("short_horizon", T.test_full_solve_trajectory_short_horizon)
+    check("deterministic", T.test_deterministic_run_to_run)
+    check("example_lp", T.test_example_lp_exact_record)  # 3 rows on N ranks: empty shards
+
+    # every rank holds the same global records and solution
+    import torch.distributed as td
+    problem = random_sparse_lp(2500, 2000, 7, seed=71)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.iteration_limit = 120
+    out = folp_b200.optimize(params, problem)
+    digest = torch.tensor([float(np.sum(out.primal_solution)), float(np.sum(out.dual_solution)),
+                           out.iteration_stats[-1].convergence_information[0].primal_objective],
+                          dtype=torch.float64, device="cuda")
+    all_d = [torch.zeros_like(digest) for _ in range(world)]
+    td.all_gather(all_d, digest)
+    for d in all_d:
+        assert torch.equal(d, all_d[0]), all_d
+    if rank == 0:
+        print(f"[dist x{world}] all ranks agree; ALL OK", flush=True)
+    td.barrier()
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,7 +94,8 @@ def test_spmv_matches_oracle(make):
     short_r, short_c = row_len <= 32, col_len <= 32
     if A.nnz and row_len.max() <= 32:
         assert np.array_equal(ax_o, ax_g)
-    if A.nnz and col_len.max() <= 32:
+    # (row-partitioned: a column's sum is the NCCL sum of per-rank partial sums, not serial)
+    if A.nnz and col_len.max() <= 32 and folp_b200.distributed.state() is None:
         assert np.array_equal(aty_o, aty_g)
     assert _rel(ax_g, ax_o) <= 1e-13
     assert _rel(aty_g, aty_o) <= 1e-13
