@@ -35,6 +35,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the two k_spmv launches of an
+# iteration, from the committed `ncu --set full` capture (profiles/r01_ncu_full_c2_summary.csv)
+TRAFFIC_NCU = {"c2": 160.8e6 + 160.6e6}
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -118,28 +123,49 @@ def run_until(solver, iteration):
             return e
 
 
+def _max_over_ranks(x, world):
+    """max of a python float over all ranks (device all-reduce on the NCCL group)."""
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as td
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+    torch.cuda.synchronize()
+
+
 def bench_gpu(args):
     import torch
     import folp_b200
+    from folp_b200 import distributed
     from folp_b200.lib import Solver, build_info
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
-        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}: launch with torchrun for N>1")
-    if world > 1:
-        raise SystemExit("bench.py: the multi-GPU row partition is not wired into bench.py yet")
+        raise SystemExit(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}: for N>1 launch one rank per "
+                         "GPU with python -m torch.distributed.run --nproc-per-node N")
     torch.cuda.set_device(local_rank)
-    lp, params, holder, fparams, scaled = make_problem(args.workload)
+    distributed.init("nccl")  # no-op when world == 1
+    lp, params, holder, fparams, scaled = make_problem(args.workload)  # same seed on every rank
     n, m, nnz = lp.num_variables, lp.num_constraints, lp.constraint_matrix.nnz
     total_steps = args.warmup + args.steps
     fparams.iteration_limit = ITERS_PER_STEP * (total_steps + 1) + 10_000_000
 
     t0 = time.time()
-    solver = Solver(holder, fparams)
+    solver = Solver(holder, fparams)  # row-partitioned over all ranks when world > 1
     t_create = time.time() - t0
-    log(f"[bench] folp_create {t_create:.2f}s; {build_info()}")
+    log(f"[bench] rank {rank}/{world} folp_create {t_create:.2f}s shard {solver.shard_info()}; {build_info()}")
+    exchange = solver.shard_info()["exchange"]
     stream = torch.cuda.ExternalStream(solver.stream())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -148,25 +174,21 @@ def bench_gpu(args):
         done += ITERS_PER_STEP
         run_until(solver, done)
     c0 = solver.counters()
-    torch.cuda.synchronize()
+    _barrier(world)
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
             done += ITERS_PER_STEP
             e = run_until(solver, done)
         ev1.record(stream)
-        torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+        _barrier(world)
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world)
     c1 = solver.counters()
     iters = c1["iterations"] - c0["iterations"]
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     basic_s = c1["basic_algorithm_seconds"] - c0["basic_algorithm_seconds"]
     value = iters / (ms * 1e-3)
 
-    # per-kernel device time of real attempts, continuing the same solve
-    prof_attempts = 100
-    solver.profile_attempts(10)
-    kms, ran = solver.profile_attempts(prof_attempts)
     b1, b2, b3 = algorithmic_bytes(n, m, nnz)
     peaks = {}
     try:
@@ -175,23 +197,39 @@ def bench_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
-    per = [k / prof_attempts for k in kms]
-    spmv_ms = per[1] + per[2]
-    achieved = (b2 + b3) / (spmv_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": "k_spmv (A*xbar + dual step, A'*y + interaction; two launches per iteration)",
-        "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None,
-        "per_kernel": {
-            "k_primal": {"ms": per[0], "bytes": b1, "gbs": b1 / per[0] / 1e6},
-            "k_spmv<EpiDual>": {"ms": per[1], "bytes": b2, "gbs": b2 / per[1] / 1e6},
-            "k_spmv<EpiTrans>": {"ms": per[2], "bytes": b3, "gbs": b3 / per[2] / 1e6},
-        },
-        "iteration": {"bytes": b1 + b2 + b3, "gbs_at_value": (b1 + b2 + b3) * value / 1e9,
-                      "frac_at_value": (b1 + b2 + b3) * value / 1e9 / peak,
-                      "matrix_only_gbs_at_value": 24 * nnz * value / 1e9},
-    }
-    x_gpu, y_gpu = solver.get_solution()
+    iteration = {"bytes": b1 + b2 + b3, "gbs_at_value": (b1 + b2 + b3) * value / 1e9,
+                 "frac_at_value": (b1 + b2 + b3) * value / 1e9 / (peak * world),
+                 "matrix_only_gbs_at_value": 24 * nnz * value / 1e9}
+    if world == 1:
+        # per-kernel device time of real attempts, continuing the same solve
+        prof_attempts = 100
+        solver.profile_attempts(10)
+        kms, ran = solver.profile_attempts(prof_attempts)
+        per = [k / prof_attempts for k in kms]
+        spmv_ms = per[1] + per[2]
+        achieved = (b2 + b3) / (spmv_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": "k_spmv (A*xbar + dual step, A'*y + interaction; two launches per iteration)",
+            "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": TRAFFIC_NCU.get(args.workload),
+            "per_kernel": {
+                "k_primal": {"ms": per[0], "bytes": b1, "gbs": b1 / per[0] / 1e6},
+                "k_spmv<EpiDual>": {"ms": per[1], "bytes": b2, "gbs": b2 / per[1] / 1e6},
+                "k_spmv<EpiTrans>": {"ms": per[2], "bytes": b3, "gbs": b3 / per[2] / 1e6},
+            },
+            "iteration": iteration,
+            "note": "random 8-byte gathers of xbar / y+ (one L2 tag lookup per nonzero) bound k_spmv on this "
+                    "workload before HBM does: see DESIGN.md section 5 and tools/gather_bench.cu",
+        }
+    else:
+        # the per-rank kernels are the same; at N > 1 the whole-iteration figure is what can be stated
+        roofline = {
+            "bound": "hbm", "kernel": "whole iteration over all ranks (k_primal, k_spmv x2, k_interaction + NCCL "
+                                      "allgather / reduce-scatter / scalar exchange)",
+            "achieved": iteration["gbs_at_value"], "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": iteration["frac_at_value"], "traffic": None, "iteration": iteration,
+            "nvlink_bytes_per_iteration_per_gpu": 2 * 8 * n * (world - 1) // world,
+        }
     solver.close()
 
     # ---- e2e: the C-ABI call sequence with host buffers ----
@@ -200,22 +238,26 @@ def bench_gpu(args):
         e2e_iters = args.e2e_iters
         fparams.iteration_limit = e2e_iters
         h2d = sum(a.nbytes for a in holder._keep)
-        torch.cuda.synchronize()
+        _barrier(world)
         t0 = time.perf_counter()
         s2 = Solver(holder, fparams)
         x, y, reason, it2, evals = s2.solve()
         s2.close()
-        t_e2e = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        t_e2e = _max_over_ranks(time.perf_counter() - t0, world)
         d2h = x.nbytes + y.nbytes
         e2e = {"value": it2 / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "iterations": it2, "seconds": t_e2e,
-               "what": "folp_create(host CSC arrays) + folp_solve + folp_get_solution, wall clock"}
+               "what": "folp_create(host CSC arrays%s) + folp_solve + folp_get_solution, wall clock, max over ranks"
+                       % (", NCCL communicator" if world > 1 else "")}
 
-    # ---- cpu baseline: the oracle on a bounded sample of the same workload ----
-    cpu = None if args.skip_cpu else cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
+    # ---- cpu baseline: the oracle on a bounded sample of the same workload (rank 0, N = 1 only) ----
+    cpu = None
+    if not args.skip_cpu and world == 1:
+        cpu = cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
 
     line = {
-        "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": 1,
+        "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
@@ -223,6 +265,9 @@ def bench_gpu(args):
                    "iterations_per_step": ITERS_PER_STEP, "parameters": "scripts/solve_qp.jl defaults "
                    "(ruiz 10, pock-chambolle 1.0, adaptive step 0.3/0.6, adaptive_normalized restarts, "
                    "evaluation every 40 iterations), tolerances 0 so every step does the same work",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"1-D row partition over {world} GPUs (nnz-balanced row blocks + primal slices), per-attempt "
+                   f"exchange: {exchange}",
                    "l2_flush": "working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush"
                                % ((24 * nnz + 8 * (20 * n + 12 * m)) / 1e6)},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -234,7 +279,12 @@ def bench_gpu(args):
                    "final_l2_dual_residual": e.l2_dual_residual,
                    "folp_create_seconds": t_create, "build": build_info()},
     }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
 
 
 def cpu_baseline(params, lp, scaled, sample_iters):

@@ -68,7 +68,11 @@ struct folp_handle {
   int64_t col0 = 0, row0 = 0;      // first global column / row owned by this rank
   std::vector<int64_t> row_begin;  // world + 1
   double* d_rows = nullptr;        // staging for row-indexed gathers, world * m_pad
+  double* d_cols = nullptr;        // staging for column-indexed gathers, world * n_pad
   double* h_sc = nullptr;          // pinned, world * kScBlock
+  // peer-memory exchange region {xbar | p_full | sc_recv | flags} and the peers' mappings
+  void* region = nullptr;
+  void* peer_region[kMaxWorld] = {};
 };
 
 #define TRY(expr) FOLP_CUDA_TRY(h, expr)
@@ -194,7 +198,10 @@ static void free_handle(folp_handle* h) {
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_trs) cudaFreeHost(h->h_trs);
   if (h->h_sc) cudaFreeHost(h->h_sc);
+  for (int r = 0; r < kMaxWorld; ++r)
+    if (h->peer_region[r]) cudaIpcCloseMemHandle(h->peer_region[r]);
   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
+  if (h->region) cudaFree(h->region);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -247,6 +254,87 @@ extern "C" int folp_partition(int64_t m, int64_t n, int64_t nnz, const int64_t* 
   int64_t n_pad = (n + world_size - 1) / world_size;
   n_pad += n_pad & 1;
   for (int r = 0; r <= world_size; ++r) col_begin_out[r] = std::min<int64_t>(n, r * n_pad);
+  return FOLP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Peer-memory exchange: every rank opens every other rank's region through CUDA IPC
+// (NVLink / NVSwitch peer access), so that take_step needs no NCCL call: K1 pushes its
+// slice of xbar into all copies, k_interaction pulls the partial products, four scalars
+// and three flags per attempt travel as plain stores. Falls back to the NCCL exchanges
+// (FOLP_NO_P2P=1, more than kMaxWorld ranks, or IPC refused on any rank).
+// ---------------------------------------------------------------------------
+static int setup_peer_exchange(folp_handle* h) {
+  Bufs& B = h->B;
+  const int P = h->world;
+  static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(int) <= kScBlock * sizeof(double), "handle fits a block");
+  struct Msg {
+    cudaIpcMemHandle_t handle;
+    int ok;
+  } mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = (P <= kMaxWorld && getenv("FOLP_NO_P2P") == nullptr) ? 1 : 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.handle, h->region) != cudaSuccess) {
+    cudaGetLastError();
+    mine.ok = 0;
+  }
+  TRY(cudaMemcpyAsync(B.sc_send, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(h->nccl->AllGather(B.sc_send, B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
+  TRY(cudaMemcpyAsync(h->h_sc, B.sc_recv, sizeof(double) * P * kScBlock, cudaMemcpyDeviceToHost,
+                      h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  bool all_ok = true;
+  std::vector<Msg> msgs(static_cast<size_t>(P));
+  for (int r = 0; r < P; ++r) {
+    memcpy(&msgs[r], h->h_sc + static_cast<size_t>(r) * kScBlock, sizeof(Msg));
+    all_ok = all_ok && msgs[r].ok;
+  }
+  int opened = all_ok ? 1 : 0;
+  if (all_ok) {
+    for (int r = 0; r < P && opened; ++r) {
+      if (r == h->rank) continue;
+      if (cudaIpcOpenMemHandle(&h->peer_region[r], msgs[r].handle, cudaIpcMemLazyEnablePeerAccess) !=
+          cudaSuccess) {
+        cudaGetLastError();
+        h->peer_region[r] = nullptr;
+        opened = 0;
+      }
+    }
+  }
+  // second round: peer mode only if every rank opened every handle
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = opened;
+  TRY(cudaMemsetAsync(B.sc_recv, 0, sizeof(double) * P * kScBlock, h->stream));
+  TRY(cudaMemcpyAsync(B.sc_send, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(h->nccl->AllGather(B.sc_send, B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
+  TRY(cudaMemcpyAsync(h->h_sc, B.sc_recv, sizeof(double) * P * kScBlock, cudaMemcpyDeviceToHost,
+                      h->stream));
+  TRY(cudaMemsetAsync(B.sc_recv, 0, sizeof(double) * P * kScBlock, h->stream));
+  TRY(cudaMemsetAsync(B.sc_send, 0, sizeof(double) * kScBlock, h->stream));
+  TRY(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < P; ++r) {
+    Msg m2;
+    memcpy(&m2, h->h_sc + static_cast<size_t>(r) * kScBlock, sizeof(Msg));
+    opened = opened && m2.ok;
+  }
+  if (!opened) {
+    for (int r = 0; r < P; ++r)
+      if (h->peer_region[r]) {
+        cudaIpcCloseMemHandle(h->peer_region[r]);
+        h->peer_region[r] = nullptr;
+      }
+    B.p2p = 0;
+    return FOLP_OK;
+  }
+  const size_t full = static_cast<size_t>(P) * h->n_pad;
+  for (int r = 0; r < P; ++r) {
+    double* base = static_cast<double*>(r == h->rank ? h->region : h->peer_region[r]);
+    B.xbar_peer[r] = base;
+    B.pfull_peer[r] = base + full;
+    B.sc_peer[r] = base + 2 * full;
+    B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + 2 * full + static_cast<size_t>(P) * kScBlock);
+  }
+  B.p2p = 1;
   return FOLP_OK;
 }
 
@@ -431,13 +519,25 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     if ((rc = dev_zeros(h, &B.y[k], ma))) return rc;
     if ((rc = dev_zeros(h, &B.aty[k], na))) return rc;
   }
-  if ((rc = dev_zeros(h, &B.xbar, P > 1 ? P * h->n_pad : n))) return rc;
-  if (P > 1) {
-    if ((rc = dev_zeros(h, &B.p_full, P * h->n_pad))) return rc;
+  if (P == 1) {
+    if ((rc = dev_zeros(h, &B.xbar, n))) return rc;
+  } else {
+    // one allocation, so that one CUDA IPC handle exposes everything a peer touches
+    const size_t full = static_cast<size_t>(P) * h->n_pad;
+    const size_t region_doubles = 2 * full + static_cast<size_t>(P) * kScBlock +
+                                  kNumFlagKinds * kMaxWorld + 16;
+    TRY(cudaMalloc(&h->region, region_doubles * sizeof(double)));
+    TRY(cudaMemsetAsync(h->region, 0, region_doubles * sizeof(double), h->stream));
+    double* base = static_cast<double*>(h->region);
+    B.xbar = base;
+    B.p_full = base + full;
+    B.sc_recv = base + 2 * full;
+    B.flags = reinterpret_cast<unsigned long long*>(base + 2 * full + static_cast<size_t>(P) * kScBlock);
     if ((rc = dev_zeros(h, &B.aty_rs, na))) return rc;
     if ((rc = dev_zeros(h, &B.sc_send, kScBlock))) return rc;
-    if ((rc = dev_zeros(h, &B.sc_recv, static_cast<size_t>(P) * kScBlock))) return rc;
     if ((rc = dev_zeros(h, &h->d_rows, P * ma))) return rc;
+    if ((rc = dev_zeros(h, &h->d_cols, full))) return rc;
+    if ((rc = setup_peer_exchange(h))) return rc;
   }
   if ((rc = dev_upload(h, &B.c, at(p->objective_vector, c0), nl, 0.0))) return rc;
   if ((rc = dev_upload(h, &B.l, at(p->variable_lower_bound, c0), nl, 0.0))) return rc;
@@ -610,9 +710,9 @@ static int pull_red(folp_handle* h, int off, int count, int nsum) {
 static int spmv_A(folp_handle* h, const double* v_slice, double* out_rows) {
   const double* in = v_slice;
   if (h->world > 1) {
-    int rc = allgather_cols(h, v_slice, h->B.xbar);
+    int rc = allgather_cols(h, v_slice, h->d_cols);
     if (rc) return rc;
-    in = h->B.xbar;
+    in = h->d_cols;
   }
   launch_spmv_plain(h->A, in, out_rows, h->B.grid_spmv, h->stream);
   CHECK_LAUNCH();
@@ -637,9 +737,9 @@ static int fetch_cols(folp_handle* h, const double* slice, double* host_out) {
   if (!host_out || h->n_glob == 0) return FOLP_OK;
   const double* src = slice;
   if (h->world > 1) {
-    int rc = allgather_cols(h, slice, h->B.xbar);
+    int rc = allgather_cols(h, slice, h->d_cols);
     if (rc) return rc;
-    src = h->B.xbar;
+    src = h->d_cols;
   }
   TRY(cudaMemcpyAsync(host_out, src, sizeof(double) * h->n_glob, cudaMemcpyDeviceToHost, h->stream));
   return FOLP_OK;
@@ -673,14 +773,15 @@ static int launch_attempts_any(folp_handle* h, int attempts) {
   const Bufs& B = h->B;
   for (int a = 0; a < attempts; ++a) {
     int rc;
-    launch_dist_primal(B, h->stream);
-    NCCL_TRY(h->nccl->AllGather(B.xbar + static_cast<size_t>(h->rank) * h->n_pad, B.xbar,
-                                static_cast<size_t>(h->n_pad), ncclDouble, h->comm, h->stream));
+    launch_dist_primal(B, h->stream);  // peer mode: pushes its slice of xbar to every rank
+    if (!B.p2p)
+      NCCL_TRY(h->nccl->AllGather(B.xbar + static_cast<size_t>(h->rank) * h->n_pad, B.xbar,
+                                  static_cast<size_t>(h->n_pad), ncclDouble, h->comm, h->stream));
     launch_dist_dual(B, h->A, h->stream);
     launch_dist_trans_partial(B, h->At, h->stream);
-    if ((rc = reduce_scatter_cols(h, B.p_full, B.aty_rs))) return rc;
-    launch_dist_interaction(B, h->A, h->stream);
-    if ((rc = exchange_scalars_dev(h))) return rc;
+    if (!B.p2p && (rc = reduce_scatter_cols(h, B.p_full, B.aty_rs))) return rc;
+    launch_dist_interaction(B, h->A, h->stream);  // peer mode: pulls and sums the partial products
+    if (!B.p2p && (rc = exchange_scalars_dev(h))) return rc;
     launch_dist_finalize(B, h->stream);
   }
   return FOLP_OK;
@@ -727,6 +828,10 @@ static int run_steps(folp_handle* h, int64_t target) {
     attempts = std::min<int64_t>(attempts, 512);
     if ((rc = enqueue_attempts(h, static_cast<int>(attempts)))) return rc;
     if ((rc = pull_state(h))) return rc;
+    if (s->p2p_timeout) {
+      h->err = "peer exchange timed out: a rank of the row partition stopped responding";
+      return FOLP_CUDA_ERROR;
+    }
   }
   TRY(cudaEventRecord(h->ev1, h->stream));
   TRY(cudaEventSynchronize(h->ev1));
@@ -1213,7 +1318,7 @@ extern "C" int folp_debug_state(folp_handle* h, double* x, double* y, double* du
   }
   int rc;
   if ((rc = fetch_cols(h, B.x[s->cur], x))) return rc;
-  if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));  // B.xbar staging is reused below
+  if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));  // the gather staging is reused below
   if ((rc = fetch_rows(h, B.y[s->cur], y))) return rc;
   if (h->world > 1) TRY(cudaStreamSynchronize(h->stream));
   if ((rc = fetch_cols(h, B.aty[s->cur], dual_product))) return rc;
@@ -1270,7 +1375,7 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
   Bufs& B = h->B;
   int rc;
   if (!transpose) {  // in: global n -> out: global m
-    double* d_in = h->world > 1 ? B.xbar : B.tr_t;
+    double* d_in = h->world > 1 ? h->d_cols : B.tr_t;
     if (h->n_glob)
       TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * h->n_glob, cudaMemcpyHostToDevice, h->stream));
     launch_spmv_plain(h->A, d_in, B.tr_d, B.grid_spmv, h->stream);
@@ -1289,31 +1394,50 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
   return FOLP_OK;
 }
 
-extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
+extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[8],
                                            int64_t* attempts_run) {
   if (!h || !ms_out) return FOLP_INVALID_ARGUMENT;
-  if (h->world > 1) {
-    h->err = "folp_debug_profile_attempts times the fused single-GPU kernels only";
-    return FOLP_UNSUPPORTED;
-  }
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   int rc;
   s->target_iterations = INT64_MAX / 4;
   s->active = s->numerical_error ? 0 : 1;
   if ((rc = push_state(h))) return rc;
-  std::vector<cudaEvent_t> ev(static_cast<size_t>(4 * attempts));
+  const int nk = h->world == 1 ? 3 : 5;  // kernels (and, without peer memory, NCCL calls) per attempt
+  std::vector<cudaEvent_t> ev(static_cast<size_t>((nk + 1) * attempts));
   for (auto& e : ev) TRY(cudaEventCreate(&e));
-  for (int64_t a = 0; a < attempts; ++a)
-    launch_step_attempt_timed(h->B, h->A, h->At, ev.data() + 4 * a, h->stream);
+  for (int64_t a = 0; a < attempts; ++a) {
+    cudaEvent_t* e = ev.data() + (nk + 1) * a;
+    if (h->world == 1) {
+      launch_step_attempt_timed(h->B, h->A, h->At, e, h->stream);
+      continue;
+    }
+    const Bufs& B = h->B;
+    TRY(cudaEventRecord(e[0], h->stream));
+    launch_dist_primal(B, h->stream);
+    if (!B.p2p)
+      NCCL_TRY(h->nccl->AllGather(B.xbar + static_cast<size_t>(h->rank) * h->n_pad, B.xbar,
+                                  static_cast<size_t>(h->n_pad), ncclDouble, h->comm, h->stream));
+    TRY(cudaEventRecord(e[1], h->stream));
+    launch_dist_dual(B, h->A, h->stream);
+    TRY(cudaEventRecord(e[2], h->stream));
+    launch_dist_trans_partial(B, h->At, h->stream);
+    if (!B.p2p && (rc = reduce_scatter_cols(h, B.p_full, B.aty_rs))) return rc;
+    TRY(cudaEventRecord(e[3], h->stream));
+    launch_dist_interaction(B, h->A, h->stream);
+    if (!B.p2p && (rc = exchange_scalars_dev(h))) return rc;
+    TRY(cudaEventRecord(e[4], h->stream));
+    launch_dist_finalize(B, h->stream);
+    TRY(cudaEventRecord(e[5], h->stream));
+  }
   CHECK_LAUNCH();
-  h->launches += 3 * attempts;
+  h->launches += nk * attempts;
   if ((rc = pull_state(h))) return rc;
-  ms_out[0] = ms_out[1] = ms_out[2] = 0.0;
+  for (int k = 0; k < 8; ++k) ms_out[k] = 0.0;
   for (int64_t a = 0; a < attempts; ++a)
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < nk; ++k) {
       float ms = 0.f;
-      TRY(cudaEventElapsedTime(&ms, ev[4 * a + k], ev[4 * a + k + 1]));
+      TRY(cudaEventElapsedTime(&ms, ev[(nk + 1) * a + k], ev[(nk + 1) * a + k + 1]));
       ms_out[k] += ms;
     }
   for (auto& e : ev) cudaEventDestroy(e);
@@ -1327,7 +1451,7 @@ extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, dou
   cudaSetDevice(h->device);
   Bufs& B = h->B;
   // input: the live iterate (x or y); output: trust-region scratch
-  const double* in = transpose ? B.y[h->hs->cur] : (h->world > 1 ? B.xbar : B.x[h->hs->cur]);
+  const double* in = transpose ? B.y[h->hs->cur] : (h->world > 1 ? h->d_cols : B.x[h->hs->cur]);
   for (int w = 0; w < 3; ++w)
     launch_spmv_plain(transpose ? h->At : h->A, in, B.tr_d, B.grid_spmv, h->stream);
   TRY(cudaEventRecord(h->ev0, h->stream));
@@ -1352,6 +1476,11 @@ extern "C" int folp_counters(folp_handle* h, int64_t* kernel_launches,
   if (basic_algorithm_seconds) *basic_algorithm_seconds = h->basic_time;
   if (iterations) *iterations = h->hs->iterations;
   return FOLP_OK;
+}
+
+extern "C" int folp_exchange_mode(folp_handle* h) {
+  if (!h) return -1;
+  return h->world == 1 ? 0 : (h->B.p2p ? 2 : 1);
 }
 
 extern "C" int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end,

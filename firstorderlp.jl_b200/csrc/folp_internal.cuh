@@ -44,7 +44,8 @@ struct DevState {
   int mp_need_primal;      // Malitsky-Pock: next attempt starts a new take_step
   int mp_retries;          // dual retries used in the current MP take_step
   int policy;              // folp_step_size_policy
-  int reserved;
+  int p2p_timeout;         // row-partitioned peer exchange: a wait gave up (reported as an error)
+  long long epoch;         // active attempts finalized so far (orders the peer-exchange flags)
   double reduction_exponent, growth_exponent;
   double downscaling_factor, breaking_factor, interpolation_coefficient;
 };

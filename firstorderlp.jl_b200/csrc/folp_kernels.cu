@@ -21,6 +21,43 @@ __device__ __forceinline__ double* part_ptr(const Bufs& B, int slot, int scalar)
   return B.part + (static_cast<size_t>(slot) * kMaxScalars + scalar) * kMaxPartialBlocks;
 }
 
+// ---- peer-exchange flags (row-partitioned mode over CUDA IPC memory) --------------------
+// flag value of exchange `kind` in the attempt that starts at DevState::epoch
+__device__ __forceinline__ unsigned long long p2p_value(const DevState& s, int kind) {
+  return 3ull * static_cast<unsigned long long>(s.epoch) + kind + 1ull;
+}
+// One thread, after the data it publishes was fenced system-wide: raise this rank's flag of
+// `kind` on every rank.
+__device__ __forceinline__ void p2p_signal(const Bufs& B, int kind, unsigned long long v) {
+  for (int r = 0; r < B.world; ++r) {
+    unsigned long long* f = B.flag_peer[r] + kind * kMaxWorld + B.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+  }
+}
+// One thread: wait until every rank's flag of `kind` has reached v. Gives up after ~2 s so
+// that a lost peer surfaces as an error instead of a hung device.
+__device__ __forceinline__ void p2p_wait(const Bufs& B, int kind, unsigned long long v) {
+  for (int r = 0; r < B.world; ++r) {
+    const unsigned long long* f = B.flags + kind * kMaxWorld + r;
+    unsigned long long cur;
+    long long spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
+      if (cur >= v) break;
+      if (++spins > 20000000ll) {
+        B.st->p2p_timeout = 1;
+        return;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+// All threads of a CTA: block until the exchange has arrived.
+__device__ __forceinline__ void p2p_wait_cta(const Bufs& B, int kind) {
+  if (threadIdx.x == 0) p2p_wait(B, kind, p2p_value(*B.st, kind));
+  __syncthreads();
+}
+
 // Constant-index selection keeps the kernel parameter struct out of local memory.
 template <class T>
 __device__ __forceinline__ T* sel(T* const (&a)[2], int k) {
@@ -112,6 +149,10 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     if (avg) reinterpret_cast<double2*>(B.sum_x)[j] = sx;
     if (k.do_primal) reinterpret_cast<double2*>(xn)[j] = xp;
     reinterpret_cast<double2*>(B.xbar + B.xbar_off)[j] = xb;
+    if (B.p2p) {  // push the slice into every peer's copy of xbar (posted NVLink stores)
+      for (int r = 0; r < B.world; ++r)
+        if (r != B.rank) reinterpret_cast<double2*>(B.xbar_peer[r] + B.xbar_off)[j] = xb;
+    }
     acc += d0 * d0;
     acc += d1 * d1;
   }
@@ -122,10 +163,21 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     if (avg) B.sum_x[j] = sx;
     if (k.do_primal) xn[j] = xp;
     B.xbar[B.xbar_off + j] = xb;
+    if (B.p2p) {
+      for (int r = 0; r < B.world; ++r)
+        if (r != B.rank) B.xbar_peer[r][B.xbar_off + j] = xb;
+    }
     acc += d * d;
   }
   const double t = block_reduce<false>(acc, sh);
   if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 0)[blockIdx.x] = t;
+  if (B.p2p) {  // the last block to finish announces this rank's slice on every rank
+    __threadfence_system();
+    if (last_block_arrive(B.counters + 4) && threadIdx.x == 0) {
+      __threadfence_system();
+      p2p_signal(B, 0, p2p_value(s, 0));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -207,6 +259,8 @@ __device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double d
     s.pending_avg |= 1;
     s.iterations += 1;
   }
+  s.epoch += 1;
+  if (s.p2p_timeout) s.numerical_error = 1;  // stop the batch; the host reports the error
   s.active = (s.iterations < s.target_iterations && !s.numerical_error) ? 1 : 0;
   *st = s;
 }
@@ -232,6 +286,7 @@ struct EpiDual {
     pend = s.pending_avg & 1;
     w = s.pending_w;
     acc = 0.0;
+    if (B.p2p) p2p_wait_cta(B, 0);  // every rank's slice of xbar has landed
     return true;
   }
   __device__ const double* input() const { return B.xbar; }
@@ -316,8 +371,15 @@ __global__ void __launch_bounds__(kVecThreads) k_interaction(Bufs B, int g_prima
   double* __restrict__ atn = sel(B.aty, s.cur ^ 1);
   double inter = 0.0, dp2 = 0.0;
   const int stride = gridDim.x * blockDim.x;
+  if (B.p2p) p2p_wait_cta(B, 1);  // every rank's partial product is complete
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
-    const double at = B.aty_rs[j];
+    double at;
+    if (B.p2p) {  // pull this slice of every rank's partial product, summed in rank order
+      at = 0.0;
+      for (int r = 0; r < B.world; ++r) at += __ldcg(B.pfull_peer[r] + B.xbar_off + j);
+    } else {
+      at = B.aty_rs[j];  // NCCL reduce-scatter result
+    }
     atn[j] = at;
     const double dx = xn[j] - xc[j];
     const double dat = at - atc[j];
@@ -336,18 +398,27 @@ __global__ void __launch_bounds__(kVecThreads) k_interaction(Bufs B, int g_prima
   const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
   const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
   if (threadIdx.x == 0) {
-    B.sc_send[0] = dx2;
-    B.sc_send[1] = dy2;
-    B.sc_send[2] = it;
-    B.sc_send[3] = dp;
+    if (B.p2p) {  // push the four scalars into every rank's slot for this rank, then announce
+      const double t[4] = {dx2, dy2, it, dp};
+      for (int r = 0; r < B.world; ++r)
+        for (int k = 0; k < 4; ++k) B.sc_peer[r][B.rank * kScBlock + k] = t[k];
+      __threadfence_system();
+      p2p_signal(B, 2, p2p_value(s, 2));
+    } else {
+      B.sc_send[0] = dx2;
+      B.sc_send[1] = dy2;
+      B.sc_send[2] = it;
+      B.sc_send[3] = dp;
+    }
   }
 }
 
 __global__ void k_finalize_dist(Bufs B) {
   if (threadIdx.x != 0 || !B.st->active) return;
+  if (B.p2p) p2p_wait(B, 2, p2p_value(*B.st, 2));
   double t[4] = {0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < B.world; ++r)
-    for (int k = 0; k < 4; ++k) t[k] += B.sc_recv[r * kScBlock + k];
+    for (int k = 0; k < 4; ++k) t[k] += __ldcg(B.sc_recv + r * kScBlock + k);
   finalize_attempt(B.st, t[0], t[1], t[2], t[3]);
 }
 
@@ -361,19 +432,36 @@ void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
   ed.B = B;
   k_spmv<EpiDual><<<spmv_grid(A, B.grid_spmv), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
 }
-void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s) {
-  EpiPlain ep;
-  ep.in = nullptr;
-  ep.out = B.p_full;
-  ep.gate = B.st;
-  ep.next0 = B.y[0];
-  ep.next1 = B.y[1];
-  k_spmv<EpiPlain><<<spmv_grid(At, B.grid_spmv), kSpmvThreads, kSpmvSmemBytes, s>>>(At, ep);
-}
+void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s);
 void launch_dist_interaction(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
   k_interaction<<<B.grid_vec, kVecThreads, 0, s>>>(B, B.grid_vec, spmv_grid(A, B.grid_spmv));
 }
 void launch_dist_finalize(const Bufs& B, cudaStream_t s) { k_finalize_dist<<<1, 32, 0, s>>>(B); }
+
+// K3 of the row-partitioned mode: p = A_r' * y_r+ into this rank's p_full
+struct EpiTransPartial {
+  static constexpr int kNumIn = 0;
+  Bufs B;
+  __device__ bool begin() { return B.st->active != 0; }
+  __device__ const double* input() const { return sel(B.y, B.st->cur ^ 1); }
+  __device__ const double* in_ptr(int) const { return nullptr; }
+  __device__ void row(int r, double s, double, double, double) { B.p_full[r] = s; }
+  __device__ void finish(double*) {
+    if (!B.p2p) return;
+    __threadfence_system();
+    if (last_block_arrive(B.counters + 5) && threadIdx.x == 0) {
+      __threadfence_system();
+      p2p_signal(B, 1, p2p_value(*B.st, 1));
+    }
+  }
+};
+
+void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s) {
+  EpiTransPartial ep;
+  ep.B = B;
+  const int g = At.ntiles < B.grid_spmv ? (At.ntiles < 1 ? 1 : At.ntiles) : B.grid_spmv;
+  k_spmv<EpiTransPartial><<<g, kSpmvThreads, kSpmvSmemBytes, s>>>(At, ep);
+}
 
 int spmv_configure() {
   cudaError_t e;
@@ -384,6 +472,9 @@ int spmv_configure() {
                            kSpmvSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_spmv<EpiTrans>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSpmvSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_spmv<EpiTransPartial>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            kSpmvSmemBytes);
   return e;
 }
@@ -433,7 +524,6 @@ void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid
   EpiPlain ep;
   ep.in = in;
   ep.out = out;
-  ep.gate = nullptr;
   k_spmv<EpiPlain><<<spmv_grid(A, grid), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ep);
 }
 

@@ -5,6 +5,9 @@
 
 namespace folp {
 
+constexpr int kMaxWorld = 8;
+constexpr int kNumFlagKinds = 3;  // xbar pushed | partial A'y ready | step-rule scalars pushed
+
 // Device pointers of one rank. Lengths: n_loc primal slice, m_loc dual rows.
 struct Bufs {
   int n = 0, m = 0, neq = 0;  // local primal slice length, local rows, local equalities
@@ -35,6 +38,15 @@ struct Bufs {
   double* aty_rs = nullptr;    // reduce-scatter result: (A' y+) on the local slice
   double* sc_send = nullptr;   // kScBlock scalars this rank contributes to an exchange
   double* sc_recv = nullptr;   // world * kScBlock scalars, rank-major
+  // ---- peer-memory exchange (CUDA IPC over NVLink / NVSwitch), replaces NCCL inside take_step ----
+  // Every rank exposes one region {xbar, p_full, sc_recv, flags}; *_peer[r] is rank r's copy
+  // (this rank's own entries are the local pointers above).
+  int p2p = 0;
+  double* xbar_peer[kMaxWorld] = {};
+  double* pfull_peer[kMaxWorld] = {};
+  double* sc_peer[kMaxWorld] = {};
+  unsigned long long* flag_peer[kMaxWorld] = {};
+  unsigned long long* flags = nullptr;  // local flags [kNumFlagKinds][kMaxWorld]: kind k, source rank r
 };
 constexpr int kScBlock = 64;
 

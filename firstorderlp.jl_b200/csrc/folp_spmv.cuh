@@ -298,17 +298,7 @@ struct EpiPlain {
   static constexpr int kNumIn = 0;
   const double* in;
   double* out;
-  // row-partitioned take_step: a no-op unless the attempt is active, and the input is
-  // the NEW dual iterate, whose buffer parity is only known on the device
-  const DevState* gate = nullptr;
-  const double *next0 = nullptr, *next1 = nullptr;  // y[0], y[1]
-  __device__ bool begin() {
-    if (gate) {
-      if (!gate->active) return false;
-      in = (gate->cur ^ 1) ? next1 : next0;
-    }
-    return true;
-  }
+  __device__ bool begin() { return true; }
   __device__ const double* input() const { return in; }
   __device__ const double* in_ptr(int) const { return nullptr; }
   __device__ void row(int r, double s, double, double, double) { out[r] = s; }

@@ -22,7 +22,7 @@ _pd = C.POINTER(C.c_double)
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
-    "folp_nccl_unique_id", "folp_partition", "folp_shard_info", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
+    "folp_nccl_unique_id", "folp_partition", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
     "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         _pi64 = C.POINTER(C.c_int64)
         L.folp_partition.argtypes = [C.c_int64, C.c_int64, C.c_int64, _pi64, C.c_int32, C.c_int32, _pi64, _pi64]
         L.folp_shard_info.argtypes = [C.c_void_p, _pi64, _pi64, _pi64, _pi64, _pi64]
+        L.folp_exchange_mode.argtypes = [C.c_void_p]
         L.folp_create.argtypes = [C.POINTER(FolpProblem), C.POINTER(FolpParams), C.POINTER(FolpDist),
                                   C.POINTER(C.c_void_p)]
         L.folp_run.argtypes = [C.c_void_p, C.POINTER(FolpEval)]
@@ -217,10 +218,10 @@ class Solver:
 
     def profile_attempts(self, attempts: int):
         """Device ms spent in {primal, A*xbar+dual, A'*y+rule} over `attempts` attempts."""
-        ms = (C.c_double * 3)()
+        ms = (C.c_double * 8)()
         ran = C.c_int64()
         self._check(lib().folp_debug_profile_attempts(self._h, attempts, ms, C.byref(ran)))
-        return [ms[0], ms[1], ms[2]], ran.value
+        return list(ms), ran.value
 
     def time_spmv(self, transpose=False, reps=20) -> float:
         """Average device milliseconds of the plain SpMV kernel."""
@@ -231,8 +232,10 @@ class Solver:
     def shard_info(self):
         v = [C.c_int64() for _ in range(5)]
         self._check(lib().folp_shard_info(self._h, *[C.byref(x) for x in v]))
-        return dict(zip(("row_begin", "row_end", "col_begin", "col_end", "local_nonzeros"),
-                        (x.value for x in v)))
+        d = dict(zip(("row_begin", "row_end", "col_begin", "col_end", "local_nonzeros"),
+                     (x.value for x in v)))
+        d["exchange"] = ("none", "nccl", "peer")[lib().folp_exchange_mode(self._h)]
+        return d
 
     def stream(self) -> int:
         return int(lib().folp_debug_stream(self._h) or 0)

@@ -261,6 +261,11 @@ int folp_partition(int64_t num_constraints, int64_t num_variables, int64_t num_n
                    const int64_t* rowval, int32_t index_base, int32_t world_size,
                    int64_t* row_begin_out, int64_t* col_begin_out);
 
+/* How take_step exchanges data between ranks: 0 = single GPU (none), 1 = NCCL
+ * collectives, 2 = peer memory (CUDA IPC over NVLink: K1 pushes xbar, the
+ * interaction kernel pulls the partial products; no NCCL call per attempt). */
+int folp_exchange_mode(folp_handle* h);
+
 /* What this rank holds: rows [row_begin,row_end), primal slice [col_begin,col_end). */
 int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end, int64_t* col_begin,
                     int64_t* col_end, int64_t* local_nonzeros);
@@ -323,12 +328,13 @@ int folp_counters(folp_handle* h, int64_t* kernel_launches,
                   double* basic_algorithm_seconds, int64_t* iterations);
 
 /* Measurement hook for bench.py: runs `attempts` real take_step attempts
- * (un-graphed) with CUDA events on the library's stream around each of the
- * three kernels, and returns the accumulated device milliseconds of
- * {primal step, A*xbar + dual step, A'*y + interaction/step rule} plus the
- * number of attempts that did work. The solver state advances. */
-/* (single GPU only) */
-int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[3],
+ * (un-graphed) with CUDA events on the library's stream around each kernel, and
+ * returns the accumulated device milliseconds in ms_out[8]: single GPU
+ * {primal step, A*xbar + dual step, A'*y + interaction/step rule}; row-
+ * partitioned {primal slice (+ xbar exchange), A_r*xbar + dual step, partial
+ * A_r'*y (+ reduce-scatter), interaction (+ scalar exchange), step rule}; the
+ * rest 0. *attempts_run = attempts that did work. The solver state advances. */
+int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[8],
                                 int64_t* attempts_run);
 
 /* Measurement hook: average device milliseconds of `reps` launches of the plain

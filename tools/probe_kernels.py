@@ -25,7 +25,13 @@ def main():
     args = ap.parse_args()
     import bench
     import folp_b200
-    from folp_b200 import lib as L
+    from folp_b200 import distributed, lib as L
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        distributed.init("nccl")
+    rank = int(os.environ.get("RANK", "0"))
 
     lp, params, holder, fparams, scaled = bench.make_problem(args.workload)
     n, m, nnz = lp.num_variables, lp.num_constraints, lp.constraint_matrix.nnz
@@ -39,6 +45,13 @@ def main():
         s.profile_attempts(20)
         kms, ran = s.profile_attempts(args.attempts)
         per = [k / args.attempts for k in kms]
+        if distributed.state() is not None:
+            out = {"rank": rank, "exchange": s.shard_info()["exchange"],
+                   "us": {k: v * 1e3 for k, v in zip(("primal", "dual", "trans_partial", "interaction",
+                                                       "finalize"), per)}, "iter_us": sum(per) * 1e3}
+            s.close()
+            print(json.dumps(out), flush=True)
+            continue
         out = {"lib": os.path.basename(path), "info": L.build_info(), "k_primal_us": per[0] * 1e3,
                "k_dual_us": per[1] * 1e3, "k_trans_us": per[2] * 1e3,
                "gbs": [b1 / per[0] / 1e6, b2 / per[1] / 1e6, b3 / per[2] / 1e6],
