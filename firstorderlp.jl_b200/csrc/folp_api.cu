@@ -117,26 +117,30 @@ static int dev_upload(folp_handle* h, double** p, const double* src, size_t coun
   return FOLP_OK;
 }
 
-// Packs rows into tiles (see folp_internal.cuh) and uploads the CSR arrays.
+// Cuts the rows into warp-sized work items (see folp_internal.cuh), stores the nonzeros of
+// narrow groups position-major, and uploads the arrays.
 static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
-                        const std::vector<int>& rowptr, const std::vector<int>& colidx,
-                        const std::vector<double>& vals) {
+                        const std::vector<int>& rowptr, std::vector<int>& colidx,
+                        std::vector<double>& vals) {
   M->rows = rows;
   M->cols = cols;
   M->nnz = rowptr[rows];
   std::vector<Tile> tiles;
+  tiles.reserve(static_cast<size_t>(rows) / 32 + 16);
   int nlong = 0, nchunks_total = 0;
   int r = 0;
+  std::vector<int> tc;
+  std::vector<double> tv;
   while (r < rows) {
     const int len = rowptr[r + 1] - rowptr[r];
-    if (len > kTileNnz) {
-      const int nch = (len + kTileNnz - 1) / kTileNnz;
+    if (len > kChunkNnz) {  // long row: chunks
+      const int nch = (len + kChunkNnz - 1) / kChunkNnz;
       for (int c = 0; c < nch; ++c) {
         Tile t{};
-        t.row_begin = r; t.row_end = r + 1;
-        t.nnz_begin = rowptr[r] + c * kTileNnz;
-        t.nnz_end = std::min(rowptr[r + 1], t.nnz_begin + kTileNnz);
-        t.kind = kTileLongChunk;
+        t.row_begin = r;
+        t.nnz_begin = rowptr[r] + c * kChunkNnz;
+        t.nnz_end = std::min(rowptr[r + 1], t.nnz_begin + kChunkNnz);
+        t.rows_kind = (kTileLongChunk << 16) | 1;
         t.long_id = nlong; t.chunk_first = nchunks_total; t.chunk_count = nch; t.chunk_index = c;
         tiles.push_back(t);
       }
@@ -148,18 +152,31 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
     Tile t{};
     t.row_begin = r;
     t.nnz_begin = rowptr[r];
-    int nnz = 0, maxlen = 0;
-    while (r < rows && r - t.row_begin < kTileRows) {
-      const int l2 = rowptr[r + 1] - rowptr[r];
-      if (l2 > kTileNnz || nnz + l2 > kTileNnz) break;
-      nnz += l2;
-      maxlen = std::max(maxlen, l2);
+    if (len > kNarrowMax) {  // wide row: one warp
+      t.nnz_end = rowptr[r + 1];
+      t.rows_kind = (kTileWarpPerRow << 16) | 1;
+      tiles.push_back(t);
       r += 1;
+      continue;
     }
-    t.row_end = r;
-    t.nnz_end = t.nnz_begin + nnz;
-    t.kind = maxlen > 32 ? kTileWarpPerRow : kTileThreadPerRow;
+    const int g0 = r;
+    while (r < rows && r - g0 < 32 && rowptr[r + 1] - rowptr[r] <= kNarrowMax) r += 1;
+    const int g1 = r;
+    t.nnz_end = rowptr[g1];
+    t.rows_kind = (kTileThreadPerRow << 16) | (g1 - g0);
     tiles.push_back(t);
+    // position-major inside the group (each row keeps its own order)
+    const int kb = rowptr[g0], ke = rowptr[g1];
+    tc.assign(colidx.begin() + kb, colidx.begin() + ke);
+    tv.assign(vals.begin() + kb, vals.begin() + ke);
+    int out = kb;
+    for (int pos = 0; out < ke; ++pos)
+      for (int q = g0; q < g1; ++q)
+        if (rowptr[q + 1] - rowptr[q] > pos) {
+          colidx[out] = tc[rowptr[q] - kb + pos];
+          vals[out] = tv[rowptr[q] - kb + pos];
+          ++out;
+        }
   }
   M->ntiles = static_cast<int>(tiles.size());
   M->nlong = nlong;
@@ -509,7 +526,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   B.n = static_cast<int>(nl); B.m = static_cast<int>(ml); B.neq = static_cast<int>(h->neq);
   B.world = P; B.rank = h->rank;
   B.xbar_off = P > 1 ? static_cast<int>(c0) : 0;
-  B.grid_spmv = h->sm_count;
+  B.grid_spmv = h->sm_count * kSpmvCtasPerSm;
   B.grid_vec = h->sm_count * 8;
   auto at = [](const double* v, int64_t off) { return v ? v + off : nullptr; };
   int rc;
@@ -641,10 +658,9 @@ extern "C" const char* folp_last_error(const folp_handle* h) {
 extern "C" const char* folp_build_info(void) {
 #define FOLP_STR2(x) #x
 #define FOLP_STR(x) FOLP_STR2(x)
-  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;tile_nnz=" FOLP_STR(FOLP_TILE_NNZ)
-         ";tile_rows=" FOLP_STR(FOLP_TILE_ROWS) ";spmv=warp-specialized(1+" FOLP_STR(
-             FOLP_GATHER_WARPS) "+" FOLP_STR(FOLP_REDUCE_WARPS) " warps," FOLP_STR(FOLP_STAGES)
-         " stages, gathers pipelined one tile ahead)";
+  return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;spmv=one row per lane on position-major "
+         "32-row groups, coalesced direct loads, " FOLP_STR(FOLP_SPMV_CTAS_PER_SM) " CTAs of 256 per SM;"
+         "chunk_nnz=" FOLP_STR(FOLP_CHUNK_NNZ);
 }
 
 extern "C" int folp_nccl_unique_id(void* out128) {

@@ -51,44 +51,45 @@ struct DevState {
 };
 
 // ---------------------------------------------------------------------------
-// Tiled CSR matrix. Rows are packed into row-aligned tiles of bounded cost; a
-// row longer than a tile is split into chunks whose partial sums are combined
-// in chunk order by the last chunk to finish (deterministic).
+// CSR matrix cut into warp-sized work items ("tiles"):
+//   narrow group  up to 32 consecutive rows of <= kNarrowMax nonzeros each, one row per
+//                 lane. Their nonzeros are stored POSITION-MAJOR inside the group's own
+//                 range [rowptr[g0], rowptr[g0+rows)): first the 1st entry of every row
+//                 that has one, then the 2nd entries, ... Each row keeps its ascending
+//                 column order, and at every position the lanes of a warp read
+//                 CONSECUTIVE values / column indices (the slot of lane l at position p is
+//                 base + #entries of earlier positions + #lanes < l that reach p: a ballot
+//                 and two popcounts) -- fully coalesced loads with no staging.
+//   wide row      one row of 33 .. kChunkNnz nonzeros, plain CSR order, one warp.
+//   long chunk    kChunkNnz nonzeros of a longer row; the partial sums are combined in
+//                 chunk order by the last chunk to finish (deterministic).
 // ---------------------------------------------------------------------------
-#ifndef FOLP_TILE_NNZ
-#define FOLP_TILE_NNZ 2048
+#ifndef FOLP_CHUNK_NNZ
+#define FOLP_CHUNK_NNZ 4096
 #endif
-#ifndef FOLP_TILE_ROWS
-#define FOLP_TILE_ROWS 256
+#ifndef FOLP_SPMV_CTAS_PER_SM
+#define FOLP_SPMV_CTAS_PER_SM 4
 #endif
-#ifndef FOLP_GATHER_WARPS
-#define FOLP_GATHER_WARPS 16
-#endif
-#ifndef FOLP_REDUCE_WARPS
-#define FOLP_REDUCE_WARPS 8
-#endif
-#ifndef FOLP_STAGES
-#define FOLP_STAGES 6
-#endif
-constexpr int kTileNnz = FOLP_TILE_NNZ;    // max nonzeros staged per tile
-constexpr int kTileRows = FOLP_TILE_ROWS;  // max rows per tile (one per reduce thread)
-constexpr int kGatherWarps = FOLP_GATHER_WARPS;
-constexpr int kReduceWarps = FOLP_REDUCE_WARPS;
-constexpr int kSpmvThreads = 32 * (1 + kGatherWarps + kReduceWarps);  // + 1 producer warp
-constexpr int kTilePad = 8;        // slack for 16-byte aligned bulk copies
-
+constexpr int kChunkNnz = FOLP_CHUNK_NNZ;   // a longer row is split into chunks of this many nonzeros
+constexpr int kSpmvThreads = 256;           // 8 warps per CTA, one work item per warp at a time
+constexpr int kSpmvWarps = kSpmvThreads / 32;
+constexpr int kSpmvCtasPerSm = FOLP_SPMV_CTAS_PER_SM;
+constexpr int kNarrowMax = 32;              // rows up to this length are "narrow"
+constexpr int kTilePad = 8;                 // slack behind the arrays
 enum TileKind : int { kTileThreadPerRow = 0, kTileWarpPerRow = 1, kTileLongChunk = 2 };
 
 struct Tile {
-  int row_begin, row_end;  // rows [row_begin,row_end); long chunk: the single row
+  // hot half: one 16-byte load gives a role everything it needs for the common kinds
+  int row_begin;           // first row (long chunk: the single row)
   int nnz_begin, nnz_end;  // nonzeros [nnz_begin,nnz_end)
-  int kind;
+  int rows_kind;           // (kind << 16) | number of rows
+  // long rows only
   int long_id;             // index of the long row (kTileLongChunk)
   int chunk_first;         // index into long_partials of this row's first chunk
   int chunk_count;         // chunks of this long row
   int chunk_index;         // which chunk of the long row this tile is
-  int reserved;
 };
+static_assert(sizeof(Tile) == 32, "two 16-byte halves");
 
 struct SpmvMat {
   int rows = 0, cols = 0;

@@ -430,7 +430,7 @@ void launch_dist_primal(const Bufs& B, cudaStream_t s) {
 void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
   EpiDual ed;
   ed.B = B;
-  k_spmv<EpiDual><<<spmv_grid(A, B.grid_spmv), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
+  k_spmv<EpiDual><<<spmv_grid(A, B.grid_spmv), kSpmvThreads, 0, s>>>(A, ed);
 }
 void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s);
 void launch_dist_interaction(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
@@ -459,28 +459,15 @@ struct EpiTransPartial {
 void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s) {
   EpiTransPartial ep;
   ep.B = B;
-  const int g = At.ntiles < B.grid_spmv ? (At.ntiles < 1 ? 1 : At.ntiles) : B.grid_spmv;
-  k_spmv<EpiTransPartial><<<g, kSpmvThreads, kSpmvSmemBytes, s>>>(At, ep);
+  k_spmv<EpiTransPartial><<<spmv_grid(At, B.grid_spmv), kSpmvThreads, 0, s>>>(At, ep);
 }
 
-int spmv_configure() {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(k_spmv<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kSpmvSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_spmv<EpiDual>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kSpmvSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_spmv<EpiTrans>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kSpmvSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_spmv<EpiTransPartial>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kSpmvSmemBytes);
-  return e;
-}
+int spmv_configure() { return cudaSuccess; }  // no dynamic shared memory to opt into
 
+// grid_spmv = resident CTAs of k_spmv on the device; fewer when there is less work
 static int spmv_grid(const SpmvMat& A, int grid_spmv) {
-  int g = A.ntiles < grid_spmv ? A.ntiles : grid_spmv;
+  const int need = (A.ntiles + kSpmvWarps - 1) / kSpmvWarps;
+  const int g = need < grid_spmv ? need : grid_spmv;
   return g < 1 ? 1 : g;
 }
 
@@ -496,8 +483,8 @@ void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, in
   et.g_dual = g2;
   for (int a = 0; a < attempts; ++a) {
     k_primal<<<g1, kVecThreads, 0, s>>>(B);
-    k_spmv<EpiDual><<<g2, kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
-    k_spmv<EpiTrans><<<g3, kSpmvThreads, kSpmvSmemBytes, s>>>(At, et);
+    k_spmv<EpiDual><<<g2, kSpmvThreads, 0, s>>>(A, ed);
+    k_spmv<EpiTrans><<<g3, kSpmvThreads, 0, s>>>(At, et);
   }
 }
 
@@ -514,9 +501,9 @@ void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& A
   cudaEventRecord(ev[0], s);
   k_primal<<<g1, kVecThreads, 0, s>>>(B);
   cudaEventRecord(ev[1], s);
-  k_spmv<EpiDual><<<g2, kSpmvThreads, kSpmvSmemBytes, s>>>(A, ed);
+  k_spmv<EpiDual><<<g2, kSpmvThreads, 0, s>>>(A, ed);
   cudaEventRecord(ev[2], s);
-  k_spmv<EpiTrans><<<g3, kSpmvThreads, kSpmvSmemBytes, s>>>(At, et);
+  k_spmv<EpiTrans><<<g3, kSpmvThreads, 0, s>>>(At, et);
   cudaEventRecord(ev[3], s);
 }
 
@@ -524,7 +511,7 @@ void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid
   EpiPlain ep;
   ep.in = in;
   ep.out = out;
-  k_spmv<EpiPlain><<<spmv_grid(A, grid), kSpmvThreads, kSpmvSmemBytes, s>>>(A, ep);
+  k_spmv<EpiPlain><<<spmv_grid(A, grid), kSpmvThreads, 0, s>>>(A, ep);
 }
 
 // ---------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// folp_spmv.cuh -- the tiled fp64 CSR SpMV kernel template and its epilogues.
+// folp_spmv.cuh -- the fp64 CSR SpMV kernel template and its epilogues.
 //
 // One kernel serves A*xbar fused with the dual step (compute_dual_gradient +
 // compute_next_dual_solution + project_dual!, sp.jl:1102-1107, pdhg.jl:472-494,
@@ -7,282 +7,130 @@
 // the evaluation block. A' is held as its own CSR (= the caller's CSC), so both
 // products are row-gather kernels.
 //
-// Data movement: a CTA walks its tiles; thread 0 streams each tile's values
-// (fp64) and column indices (int32) into shared memory with two 1-D bulk async
-// copies (TMA engine, mbarrier completion, L2 evict-first), double buffered so
-// the next tile's copy overlaps this tile's arithmetic. Phase A turns the
-// staged values into products in place: thread t owns nonzeros t, t+256, ...
-// (conflict-free shared-memory reads) and gathers the input vector through L2
-// with ld.global.nc, eight independent gathers in flight -- on B200 the random
-// 8-byte gather (~0.9 per clock per SM, measured) bounds this kernel, not HBM.
-// Phase B sums each row's products: short rows by one thread in ascending
-// column order -- the summation order of the reference's stdlib kernels -- so
-// such rows are bit-identical to the CPU oracle; rows longer than 32 nonzeros
-// use a warp, rows longer than a tile use several CTAs.
+// What bounds it (measured, DESIGN.md section 5, tools/gather_bench.cu): every
+// nonzero costs one random 8-byte gather of the input vector -- one slot of the
+// SM's load/store pipe and one L2 sector -- and a B200 sustains ~0.8 of those per
+// clock per SM (~0.5 when the vector no longer fits L2), which is less than what
+// HBM could stream for this format. The design therefore spends as little else
+// of the load/store pipe per nonzero as it can and keeps it saturated:
+//   * one lane owns one row; thanks to the position-major group layout
+//     (folp_internal.cuh) the 32 lanes of a warp read CONSECUTIVE values and
+//     column indices at every position: 3 coalesced wavefronts per 32 nonzeros,
+//     straight from global memory (streaming, evict-first) into registers. There is
+//     no shared-memory staging: a TMA-fed shared-memory ring (kept for the record in
+//     experimental/) costs the same pipe slots to read back, needs a second pass
+//     for the row sums and measured 15-40 % slower;
+//   * each lane gathers, multiplies and adds in ascending column order in a
+//     register and runs the fused epilogue on its row: no products written back;
+//   * latency is hidden by occupancy (1024 threads per SM, four independent
+//     gathers per lane and round), not by a software pipeline.
+// Rows of up to 32 nonzeros are summed by one lane in ascending column order --
+// the summation order of the reference's stdlib kernels -- so such rows are
+// bit-identical to the CPU oracle; longer rows use a warp, rows longer than
+// kChunkNnz several warps whose partial sums are combined in chunk order.
 #pragma once
 #include "folp_internal.cuh"
 
 namespace folp {
 
-// ---- shared-memory stage layout (bytes; every offset a multiple of 16) --------
-constexpr int kOffVals = 0;                                   // fp64 values -> products
-constexpr int kOffCols = kOffVals + (kTileNnz + kTilePad) * 8;   // int32 column indices
-constexpr int kOffRowp = kOffCols + (kTileNnz + kTilePad) * 4;   // int32 row pointers
-constexpr int kOffIn = kOffRowp + (kTileRows + 8) * 4;           // up to 3 epilogue input vectors
-constexpr int kInStride = (kTileRows + 4) * 8;
-constexpr int kOffDesc = kOffIn + 3 * kInStride;                 // the Tile descriptor
-constexpr int kSpmvStageBytes = kOffDesc + 64;
-constexpr int kSpmvStages = FOLP_STAGES;
-constexpr int kSpmvSmemBytes = kSpmvStages * kSpmvStageBytes;
-static_assert(kSpmvStageBytes % 16 == 0 && kOffCols % 16 == 0 && kOffRowp % 16 == 0 &&
-                  kOffIn % 16 == 0 && kInStride % 16 == 0 && kOffDesc % 16 == 0,
-              "bulk copies need 16-byte aligned destinations");
-static_assert(kSpmvSmemBytes <= 227 * 1024 - 1024, "stage ring must fit one SM");
-constexpr int kGatherThreads = kGatherWarps * 32;
-constexpr int kReduceThreads = kReduceWarps * 32;
-static_assert(kSpmvThreads == 32 + kGatherThreads + kReduceThreads, "role split");
-static_assert(kTileNnz % kGatherThreads == 0, "phase A unroll");
-static_assert(kTileRows <= kReduceThreads, "one row per reduce thread");
+#ifndef FOLP_GATHER_UNROLL
+#define FOLP_GATHER_UNROLL 4
+#endif
+constexpr int kGatherUnroll = FOLP_GATHER_UNROLL;  // independent gathers per lane and round
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// barrier among the reduce warps only (named barrier 1)
-__device__ __forceinline__ void reduce_group_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kReduceThreads) : "memory");
-}
-__device__ __forceinline__ void bulk_load_plain(void* dst_smem, const void* src_gmem,
-                                                uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
+// streaming loads of the matrix arrays: read once per product, keep them out of the way
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+
+// hot half of a work-item descriptor
+struct TileHot {
+  int row_begin, nnz_begin, nnz_end, rows_kind;
+  __device__ __forceinline__ int rows() const { return rows_kind & 0xffff; }
+  __device__ __forceinline__ int kind() const { return rows_kind >> 16; }
+};
+__device__ __forceinline__ TileHot load_hot(const Tile* tiles, int idx) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(tiles + idx));
+  TileHot h;
+  h.row_begin = v.x; h.nnz_begin = v.y; h.nnz_end = v.z; h.rows_kind = v.w;
+  return h;
 }
 
-// Warp-specialised persistent kernel, one CTA per SM. Roles:
-//   warp 0         producer: one lane issues every global read of a tile as 1-D bulk
-//                  async copies (TMA engine, mbarrier completion) into a 6-stage
-//                  ring: values + column indices (L2 evict-first), the tile's row
-//                  pointers and the epilogue's per-row input vectors
-//   warps 1..16    gather: turn the staged values into products in place
-//                  (conflict-free shared-memory reads, 4 independent L2 gathers in
-//                  flight per thread, 2048 per tile)
-//   warps 17..24   reduce: one row per thread, products summed in ascending column
-//                  order, fused epilogue fed from shared memory
-// The roles are connected by mbarriers only (full -> products -> empty): the
-// gather path of the L1/LSU (~0.9 random 8-byte gathers per clock per SM,
-// measured) is the binding resource and never waits for a row sum, an epilogue
-// operand or a descriptor; nothing in the loop depends on a global-load latency
-// except the gathers themselves.
 template <class Epi>
-__global__ void __launch_bounds__(kSpmvThreads, 1) k_spmv(SpmvMat A, Epi epi) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t s_full[kSpmvStages], s_prod[kSpmvStages], s_empty[kSpmvStages];
+__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A, Epi epi) {
   __shared__ double s_red[32];
-  __shared__ int s_flag;
-
   if (!epi.begin()) return;
   const double* __restrict__ xin = epi.input();
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int st = 0; st < kSpmvStages; ++st) {
-      mbar_init(&s_full[st], 1);
-      mbar_init(&s_prod[st], kGatherWarps);
-      mbar_init(&s_empty[st], kReduceWarps);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int my_tiles = (A.ntiles > static_cast<int>(blockIdx.x))
-                           ? (A.ntiles - static_cast<int>(blockIdx.x) + gridDim.x - 1) / gridDim.x
-                           : 0;
-
-  if (warp == 0) {
-    // ---------------- producer ----------------
-    if (lane == 0 && my_tiles > 0) {
-      const uint64_t policy = policy_evict_first();
-      Tile t = A.tiles[blockIdx.x];
-      for (int i = 0; i < my_tiles; ++i) {
-        const int st = i % kSpmvStages;
-        unsigned char* sb = smem_raw + st * kSpmvStageBytes;
-        Tile tn = t;
-        if (i + 1 < my_tiles) tn = A.tiles[blockIdx.x + (i + 1) * gridDim.x];  // prefetch
-        if (i >= kSpmvStages) mbar_wait(&s_empty[st], ((i / kSpmvStages) - 1) & 1);
-        *reinterpret_cast<Tile*>(sb + kOffDesc) = t;
-        const int kb = t.nnz_begin & ~3;
-        const uint32_t cnt = static_cast<uint32_t>(((t.nnz_end + 3) & ~3) - kb);
-        uint32_t bytes = cnt * 12u;
-        uint32_t rp_cnt = 0, in_cnt = 0;
-        const int rb4 = t.row_begin & ~3, rb2 = t.row_begin & ~1;
-        if (t.kind != kTileLongChunk) {
-          rp_cnt = static_cast<uint32_t>(((t.row_end + 1 + 3) & ~3) - rb4);
-          in_cnt = static_cast<uint32_t>(((t.row_end + 1) & ~1) - rb2);
-          bytes += rp_cnt * 4u + static_cast<uint32_t>(Epi::kNumIn) * in_cnt * 8u;
-        }
-        mbar_expect_tx(&s_full[st], bytes);
-        bulk_load(sb + kOffVals, A.vals + kb, cnt * 8u, &s_full[st], policy);
-        bulk_load(sb + kOffCols, A.colidx + kb, cnt * 4u, &s_full[st], policy);
-        if (t.kind != kTileLongChunk) {
-          bulk_load_plain(sb + kOffRowp, A.rowptr + rb4, rp_cnt * 4u, &s_full[st]);
-#pragma unroll
-          for (int v = 0; v < Epi::kNumIn; ++v)
-            bulk_load_plain(sb + kOffIn + v * kInStride, epi.in_ptr(v) + rb2, in_cnt * 8u,
-                            &s_full[st]);
-        }
-        t = tn;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int warps_total = gridDim.x * kSpmvWarps;
+  for (int item = blockIdx.x * kSpmvWarps + (threadIdx.x >> 5); item < A.ntiles;
+       item += warps_total) {
+    const TileHot t = load_hot(A.tiles, item);
+    const int kind = t.kind();
+    if (kind == kTileThreadPerRow) {
+      // ---- up to 32 narrow rows, one per lane ----
+      const bool valid = lane < t.rows();
+      const int r = t.row_begin + lane;
+      int len = 0;
+      double in0 = 0.0, in1 = 0.0, in2 = 0.0;
+      if (valid) {
+        len = __ldg(A.rowptr + r + 1) - __ldg(A.rowptr + r);
+        if (Epi::kNumIn > 0) in0 = epi.in_ptr(0)[r];
+        if (Epi::kNumIn > 1) in1 = epi.in_ptr(1)[r];
+        if (Epi::kNumIn > 2) in2 = epi.in_ptr(2)[r];
       }
-    }
-  } else if (warp <= kGatherWarps) {
-    // ---------------- gather ----------------
-    // Software-pipelined across tiles: the gathers of tile i+1 are issued before the
-    // products of tile i are formed, so every warp keeps kPer..2*kPer L2 gathers in
-    // flight and the LSU never drains at a tile boundary.
-    const int gt = tid - 32;
-    constexpr int kPer = kTileNnz / kGatherThreads;
-    double xv[kPer];
-    int kb = 0, ke = 0;
-    auto fetch = [&](int i) {
-      const int st = i % kSpmvStages;
-      unsigned char* sb = smem_raw + st * kSpmvStageBytes;
-      mbar_wait(&s_full[st], (i / kSpmvStages) & 1);
-      const Tile* td = reinterpret_cast<const Tile*>(sb + kOffDesc);
-      const int nb = td->nnz_begin, ne = td->nnz_end;
-      const int base = nb & ~3;
-      kb = nb - base;
-      ke = ne - base;
-      const int* __restrict__ sc = reinterpret_cast<const int*>(sb + kOffCols);
-      int c[kPer];
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      int off = t.nnz_begin;  // first entry of the current position
+      double s = 0.0;
+      for (int p0 = 0; p0 < maxlen; p0 += kGatherUnroll) {
+        int c[kGatherUnroll];
+        double a[kGatherUnroll], x[kGatherUnroll];
 #pragma unroll
-      for (int u = 0; u < kPer; ++u) {
-        const int k = kb + gt + u * kGatherThreads;
-        c[u] = k < ke ? sc[k] : -1;
-      }
-#pragma unroll
-#ifdef FOLP_ABLATE_GATHER  // development: timing without the L2 gathers (wrong results)
-      for (int u = 0; u < kPer; ++u) xv[u] = c[u] >= 0 ? 1.0 + c[u] : 0.0;
-#else
-      for (int u = 0; u < kPer; ++u) xv[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
-#endif
-    };
-    if (my_tiles > 0) fetch(0);
-    for (int i = 0; i < my_tiles; ++i) {
-      const int st = i % kSpmvStages;
-      double* __restrict__ sv = reinterpret_cast<double*>(smem_raw + st * kSpmvStageBytes + kOffVals);
-      double xc[kPer];
-#pragma unroll
-      for (int u = 0; u < kPer; ++u) xc[u] = xv[u];
-      const int kbc = kb, kec = ke;
-      if (i + 1 < my_tiles) fetch(i + 1);
-#pragma unroll
-      for (int u = 0; u < kPer; ++u) {
-        const int k = kbc + gt + u * kGatherThreads;
-        if (k < kec) sv[k] = sv[k] * xc[u];
-      }
-      // products were written through the generic proxy; the stage is refilled by
-      // the async proxy once the reduce warps release it
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_prod[st]);
-    }
-  } else {
-    // ---------------- reduce ----------------
-    const int rt = tid - 32 - kGatherThreads;
-    const int rwarp = rt >> 5;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int st = i % kSpmvStages;
-      unsigned char* sb = smem_raw + st * kSpmvStageBytes;
-      mbar_wait(&s_prod[st], (i / kSpmvStages) & 1);
-#ifdef FOLP_ABLATE_REDUCE  // development: timing without row sums / epilogue (wrong results)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
-      continue;
-#endif
-      const Tile t = *reinterpret_cast<const Tile*>(sb + kOffDesc);
-      const int base = t.nnz_begin & ~3;
-      const double* __restrict__ sv = reinterpret_cast<const double*>(sb + kOffVals);
-      const int* __restrict__ rp = reinterpret_cast<const int*>(sb + kOffRowp);
-      const double* __restrict__ in0 = reinterpret_cast<const double*>(sb + kOffIn);
-      const double* __restrict__ in1 = reinterpret_cast<const double*>(sb + kOffIn + kInStride);
-      const double* __restrict__ in2 =
-          reinterpret_cast<const double*>(sb + kOffIn + 2 * kInStride);
-      const int rb4 = t.row_begin & ~3, rb2 = t.row_begin & ~1;
-      if (t.kind == kTileThreadPerRow) {
-        const int r = t.row_begin + rt;
-        if (r < t.row_end) {
-          const int k0 = rp[r - rb4] - base, k1 = rp[r - rb4 + 1] - base;
-          // ascending column order; the shared-memory loads are issued four at a time
-          // so that only the additions are serialised
-          double s = 0.0;
-          int k = k0;
-          for (; k + 4 <= k1; k += 4) {
-            const double a0 = sv[k], a1 = sv[k + 1], a2 = sv[k + 2], a3 = sv[k + 3];
-            s += a0;
-            s += a1;
-            s += a2;
-            s += a3;
-          }
-          for (; k < k1; ++k) s += sv[k];
-          const int li = r - rb2;
-          epi.row(r, s, Epi::kNumIn > 0 ? in0[li] : 0.0, Epi::kNumIn > 1 ? in1[li] : 0.0,
-                  Epi::kNumIn > 2 ? in2[li] : 0.0);
+        for (int u = 0; u < kGatherUnroll; ++u) {
+          const bool act = len > p0 + u;
+          const unsigned m = __ballot_sync(0xffffffffu, act);
+          const int k = off + __popc(m & lt_mask);
+          off += __popc(m);
+          c[u] = act ? ld_stream(A.colidx + k) : -1;
+          a[u] = act ? ld_stream(A.vals + k) : 0.0;
         }
-      } else if (t.kind == kTileWarpPerRow) {
-        for (int r = t.row_begin + rwarp; r < t.row_end; r += kReduceWarps) {
-          const int k0 = rp[r - rb4] - base, k1 = rp[r - rb4 + 1] - base;
-          double s = 0.0;
-          for (int k = k0 + lane; k < k1; k += 32) s += sv[k];
-          s = warp_sum(s);
-          const int li = r - rb2;
-          if (lane == 0)
-            epi.row(r, s, Epi::kNumIn > 0 ? in0[li] : 0.0, Epi::kNumIn > 1 ? in1[li] : 0.0,
-                    Epi::kNumIn > 2 ? in2[li] : 0.0);
-        }
-      } else {  // one chunk of a row longer than a tile
-        const int k0 = t.nnz_begin - base, k1 = t.nnz_end - base;
-        double s = 0.0;
-        for (int k = k0 + rt; k < k1; k += kReduceThreads) s += sv[k];
-        s = warp_sum(s);
-        if (lane == 0) s_red[rwarp] = s;
-        reduce_group_sync();
-        if (rt == 0) {
-          double tot = 0.0;
 #pragma unroll
-          for (int w = 0; w < kReduceWarps; ++w) tot += s_red[w];
-          A.long_partials[t.chunk_first + t.chunk_index] = tot;
+        for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u)
+          if (c[u] >= 0) s += a[u] * x[u];  // ascending column order
+      }
+      if (valid) epi.row(r, s, in0, in1, in2);
+    } else {
+      // ---- one warp on (a chunk of) one row, plain CSR order ----
+      double s = 0.0;
+      for (int k = t.nnz_begin + lane; k < t.nnz_end; k += 32)
+        s += ld_stream(A.vals + k) * __ldg(xin + ld_stream(A.colidx + k));
+      s = warp_sum(s);
+      const int r = t.row_begin;
+      bool emit = kind == kTileWarpPerRow;
+      if (kind == kTileLongChunk) {
+        const Tile full = A.tiles[item];
+        unsigned done = 0;
+        if (lane == 0) {
+          A.long_partials[full.chunk_first + full.chunk_index] = s;
           __threadfence();
-          const unsigned done = atomicAdd(A.long_tickets + t.long_id, 1u);
-          s_flag = (done == static_cast<unsigned>(t.chunk_count) - 1u);
-          if (s_flag) A.long_tickets[t.long_id] = 0u;
+          done = atomicAdd(A.long_tickets + full.long_id, 1u);
         }
-        reduce_group_sync();
-        if (s_flag) {  // last chunk of this row: combine in chunk order
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == static_cast<unsigned>(full.chunk_count) - 1u) {  // last chunk: combine in order
           __threadfence();
           double v = 0.0;
-          for (int q = rt; q < t.chunk_count; q += kReduceThreads)
-            v += __ldcg(A.long_partials + t.chunk_first + q);
-          v = warp_sum(v);
-          if (lane == 0) s_red[rwarp] = v;
-          reduce_group_sync();
-          if (rt == 0) {
-            double tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < kReduceWarps; ++w) tot += s_red[w];
-            const int r = t.row_begin;
-            epi.row(r, tot, Epi::kNumIn > 0 ? epi.in_ptr(0)[r] : 0.0,
-                    Epi::kNumIn > 1 ? epi.in_ptr(1)[r] : 0.0,
-                    Epi::kNumIn > 2 ? epi.in_ptr(2)[r] : 0.0);
-          }
+          for (int q = lane; q < full.chunk_count; q += 32)
+            v += __ldcg(A.long_partials + full.chunk_first + q);
+          s = warp_sum(v);
+          if (lane == 0) A.long_tickets[full.long_id] = 0u;
+          emit = true;
         }
-        reduce_group_sync();
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (emit && lane == 0)
+        epi.row(r, s, Epi::kNumIn > 0 ? epi.in_ptr(0)[r] : 0.0,
+                Epi::kNumIn > 1 ? epi.in_ptr(1)[r] : 0.0, Epi::kNumIn > 2 ? epi.in_ptr(2)[r] : 0.0);
     }
   }
   __syncthreads();
@@ -290,8 +138,8 @@ __global__ void __launch_bounds__(kSpmvThreads, 1) k_spmv(SpmvMat A, Epi epi) {
 }
 
 // ---- epilogues ---------------------------------------------------------------
-// An epilogue names up to three per-row input vectors (in_ptr) that the producer
-// stages next to the matrix tile; row() receives their values for its row.
+// An epilogue names up to three per-row input vectors (in_ptr); row() receives
+// their values for its row.
 
 // out = A * in
 struct EpiPlain {
