@@ -32,6 +32,7 @@ WORKLOADS = {
     "c2": (1_000_000, 1_000_000, 10),      # BASELINE.json configs[1]
     "target": (10_000_000, 10_000_000, 10),  # north_star target size
     "small": (100_000, 100_000, 10),
+    "half": (1_000_000, 500_000, 10),       # one rank's row block of c2 at 2 GPUs
 }
 
 

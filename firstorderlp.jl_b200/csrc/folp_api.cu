@@ -70,9 +70,10 @@ struct folp_handle {
   double* d_rows = nullptr;        // staging for row-indexed gathers, world * m_pad
   double* d_cols = nullptr;        // staging for column-indexed gathers, world * n_pad
   double* h_sc = nullptr;          // pinned, world * kScBlock
-  // peer-memory exchange region {xbar | p_full | sc_recv | flags} and the peers' mappings
+  // peer-memory exchange region {xbar | y_full | sc_recv | scx | flags} and the peers' mappings
   void* region = nullptr;
   void* peer_region[kMaxWorld] = {};
+  unsigned long long xchg_seq = 0;  // evaluation-block scalar exchanges done so far (same on every rank)
 };
 
 #define TRY(expr) FOLP_CUDA_TRY(h, expr)
@@ -277,8 +278,8 @@ extern "C" int folp_partition(int64_t m, int64_t n, int64_t nnz, const int64_t* 
 // ---------------------------------------------------------------------------
 // Peer-memory exchange: every rank opens every other rank's region through CUDA IPC
 // (NVLink / NVSwitch peer access), so that take_step needs no NCCL call: K1 pushes its
-// slice of xbar into all copies, k_interaction pulls the partial products, four scalars
-// and three flags per attempt travel as plain stores. Falls back to the NCCL exchanges
+// slice of xbar into all copies, K2 pushes its rows of y+, four scalars and three flags per
+// attempt travel as plain stores. Falls back to the NCCL exchanges
 // (FOLP_NO_P2P=1, more than kMaxWorld ranks, or IPC refused on any rank).
 // ---------------------------------------------------------------------------
 static int setup_peer_exchange(folp_handle* h) {
@@ -343,15 +344,21 @@ static int setup_peer_exchange(folp_handle* h) {
     B.p2p = 0;
     return FOLP_OK;
   }
-  const size_t full = static_cast<size_t>(P) * h->n_pad;
+  const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
   for (int r = 0; r < P; ++r) {
     double* base = static_cast<double*>(r == h->rank ? h->region : h->peer_region[r]);
     B.xbar_peer[r] = base;
-    B.pfull_peer[r] = base + full;
-    B.sc_peer[r] = base + 2 * full;
-    B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + 2 * full + static_cast<size_t>(P) * kScBlock);
+    B.yfull_peer[r] = base + fx;
+    B.sc_peer[r] = base + fx + fy;
+    B.scx_peer[r] = base + fx + fy + static_cast<size_t>(P) * kScBlock;
+    B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock);
   }
   B.p2p = 1;
+  if (const char* d = getenv("FOLP_DEBUG_FLAGS")) B.dbg = atoi(d);
+  if (B.dbg & 4) {  // probe: gather from private copies of the exchanged vectors
+    B.xbar_priv = h->d_cols;
+    B.yfull_priv = h->d_rows;
+  }
   return FOLP_OK;
 }
 
@@ -499,21 +506,23 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       std::vector<int> lci(ci2.begin() + k0, ci2.begin() + k1);
       std::vector<double> lv(v2.begin() + k0, v2.begin() + k1);
       if ((rc = build_matrix(h, &h->A, static_cast<int>(h->m), static_cast<int>(n), lrp, lci, lv))) return rc;
-      // A_r': all n rows, local columns (row indices ascend inside a CSC column, so the
-      // local entries of a column are one contiguous run)
-      std::vector<int> trp(static_cast<size_t>(n) + 1, 0), tci;
-      std::vector<double> tv;
-      tci.reserve(static_cast<size_t>(h->nnz));
-      tv.reserve(static_cast<size_t>(h->nnz));
-      for (int64_t j = 0; j < n; ++j) {
-        for (int k = rp[j]; k < rp[j + 1]; ++k)
-          if (ci[k] >= h->row0 && ci[k] < row1) {
-            tci.push_back(static_cast<int>(ci[k] - h->row0));
-            tv.push_back(v[k]);
-          }
-        trp[j + 1] = static_cast<int>(tci.size());
-      }
-      if ((rc = build_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(h->m), trp, tci, tv))) return rc;
+      // (A[:, slice])': the local columns of the caller's CSC, i.e. n_local rows of full length.
+      // Their column indices (= global rows of A) are remapped into the padded rank-major
+      // layout of y_full: row i of rank q -> q * m_pad + (i - row_begin[q]).
+      const int64_t c1 = h->col0 + h->n;
+      const int t0 = rp[h->col0], t1 = rp[c1];
+      std::vector<int> trp(static_cast<size_t>(h->n) + 1);
+      for (int64_t j = 0; j <= h->n; ++j) trp[j] = rp[h->col0 + j] - t0;
+      std::vector<int> owner_off(static_cast<size_t>(m) + 1, 0);  // global row -> padded index
+      for (int q = 0; q < P; ++q)
+        for (int64_t i = h->row_begin[q]; i < h->row_begin[q + 1]; ++i)
+          owner_off[i] = static_cast<int>(q * h->m_pad + (i - h->row_begin[q]));
+      std::vector<int> tci(static_cast<size_t>(t1 - t0));
+      for (int k = t0; k < t1; ++k) tci[k - t0] = owner_off[ci[k]];
+      std::vector<double> tv(v.begin() + t0, v.begin() + t1);
+      if ((rc = build_matrix(h, &h->At, static_cast<int>(h->n), static_cast<int>(P * h->m_pad), trp, tci, tv)))
+        return rc;
+      h->nnz = (k1 - k0) + (t1 - t0);
     }
   }
 
@@ -540,20 +549,22 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     if ((rc = dev_zeros(h, &B.xbar, n))) return rc;
   } else {
     // one allocation, so that one CUDA IPC handle exposes everything a peer touches
-    const size_t full = static_cast<size_t>(P) * h->n_pad;
-    const size_t region_doubles = 2 * full + static_cast<size_t>(P) * kScBlock +
+    const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
+    const size_t region_doubles = fx + fy + 3 * static_cast<size_t>(P) * kScBlock +
                                   kNumFlagKinds * kMaxWorld + 16;
     TRY(cudaMalloc(&h->region, region_doubles * sizeof(double)));
     TRY(cudaMemsetAsync(h->region, 0, region_doubles * sizeof(double), h->stream));
     double* base = static_cast<double*>(h->region);
     B.xbar = base;
-    B.p_full = base + full;
-    B.sc_recv = base + 2 * full;
-    B.flags = reinterpret_cast<unsigned long long*>(base + 2 * full + static_cast<size_t>(P) * kScBlock);
-    if ((rc = dev_zeros(h, &B.aty_rs, na))) return rc;
+    B.y_full = base + fx;
+    B.m_pad = static_cast<int>(h->m_pad);
+    B.sc_recv = base + fx + fy;
+    B.scx = base + fx + fy + static_cast<size_t>(P) * kScBlock;
+    B.flags = reinterpret_cast<unsigned long long*>(base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock);
+    if ((rc = dev_zeros(h, &B.col_tmp, na))) return rc;
     if ((rc = dev_zeros(h, &B.sc_send, kScBlock))) return rc;
-    if ((rc = dev_zeros(h, &h->d_rows, P * ma))) return rc;
-    if ((rc = dev_zeros(h, &h->d_cols, full))) return rc;
+    if ((rc = dev_zeros(h, &h->d_rows, fy))) return rc;
+    if ((rc = dev_zeros(h, &h->d_cols, fx))) return rc;
     if ((rc = setup_peer_exchange(h))) return rc;
   }
   if ((rc = dev_upload(h, &B.c, at(p->objective_vector, c0), nl, 0.0))) return rc;
@@ -687,15 +698,27 @@ static int allgather_cols(folp_handle* h, const double* slice, double* full) {
                               h->stream));
   return FOLP_OK;
 }
-// full partial vectors (world * n_pad) -> their sum on this rank's slice
-static int reduce_scatter_cols(folp_handle* h, const double* full, double* slice) {
-  NCCL_TRY(h->nccl->ReduceScatter(full, slice, static_cast<size_t>(h->n_pad), ncclDouble, ncclSum,
-                                  h->comm, h->stream));
-  return FOLP_OK;
-}
-// B.sc_send -> B.sc_recv (device resident, consumed by k_finalize_dist / k_tr_combine)
+// B.sc_send -> B.sc_recv (device resident, consumed by k_finalize_dist); NCCL mode of take_step
 static int exchange_scalars_dev(folp_handle* h) {
   NCCL_TRY(h->nccl->AllGather(h->B.sc_send, h->B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
+  return FOLP_OK;
+}
+// Evaluation-block exchange: every rank contributes src[0..count) (device, kScBlock readable); returns
+// the device buffer holding world * kScBlock doubles, rank-major. Peer mode: one tiny kernel pushing
+// into alternating receive buffers; otherwise an NCCL allgather.
+static int exchange_block(folp_handle* h, const double* src, int count, const double** recv) {
+  Bufs& B = h->B;
+  if (B.p2p) {
+    h->xchg_seq += 1;
+    const int parity = static_cast<int>(h->xchg_seq & 1);
+    launch_exchange(B, src, count, h->xchg_seq, parity, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 1;
+    *recv = B.scx + static_cast<size_t>(parity) * h->world * kScBlock;
+    return FOLP_OK;
+  }
+  NCCL_TRY(h->nccl->AllGather(src, B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
+  *recv = B.sc_recv;
   return FOLP_OK;
 }
 // h->h_red[off .. off+count) <- the global value of the reduced scalars B.red[off ...):
@@ -708,10 +731,20 @@ static int pull_red(folp_handle* h, int off, int count, int nsum) {
     TRY(cudaStreamSynchronize(h->stream));
     return FOLP_OK;
   }
-  NCCL_TRY(h->nccl->AllGather(h->B.red + off, h->B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
-  TRY(cudaMemcpyAsync(h->h_sc, h->B.sc_recv, sizeof(double) * h->world * kScBlock,
-                      cudaMemcpyDeviceToHost, h->stream));
+  const double* recv = nullptr;
+  int rc = exchange_block(h, h->B.red + off, kScBlock, &recv);
+  if (rc) return rc;
+  TRY(cudaMemcpyAsync(h->h_sc, recv, sizeof(double) * h->world * kScBlock, cudaMemcpyDeviceToHost,
+                      h->stream));
   TRY(cudaStreamSynchronize(h->stream));
+  if (h->B.p2p) {
+    unsigned timed_out = 0;
+    TRY(cudaMemcpy(&timed_out, h->B.counters + 6, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (timed_out) {
+      h->err = "peer exchange timed out: a rank of the row partition stopped responding";
+      return FOLP_CUDA_ERROR;
+    }
+  }
   for (int k = 0; k < count; ++k) {
     double v = h->h_sc[k];
     for (int r = 1; r < h->world; ++r) {
@@ -737,16 +770,16 @@ static int spmv_A(folp_handle* h, const double* v_slice, double* out_rows) {
 }
 // out = (A' * w) on the local slice where w is dual-indexed, held as local rows
 static int spmv_At(folp_handle* h, const double* w_rows, double* out_slice) {
-  if (h->world == 1) {
-    launch_spmv_plain(h->At, w_rows, out_slice, h->B.grid_spmv, h->stream);
-    CHECK_LAUNCH();
-    h->launches += 1;
-    return FOLP_OK;
+  const double* in = w_rows;
+  if (h->world > 1) {  // the column-slice matrix gathers from the padded rank-major full vector
+    NCCL_TRY(h->nccl->AllGather(w_rows, h->d_rows, static_cast<size_t>(h->m_pad), ncclDouble, h->comm,
+                                h->stream));
+    in = h->d_rows;
   }
-  launch_spmv_plain(h->At, w_rows, h->B.p_full, h->B.grid_spmv, h->stream);
+  launch_spmv_plain(h->At, in, out_slice, h->B.grid_spmv, h->stream);
   CHECK_LAUNCH();
   h->launches += 1;
-  return reduce_scatter_cols(h, h->B.p_full, out_slice);
+  return FOLP_OK;
 }
 // host_out (global length) <- a primal-indexed device vector held as slices
 static int fetch_cols(folp_handle* h, const double* slice, double* host_out) {
@@ -793,10 +826,11 @@ static int launch_attempts_any(folp_handle* h, int attempts) {
     if (!B.p2p)
       NCCL_TRY(h->nccl->AllGather(B.xbar + static_cast<size_t>(h->rank) * h->n_pad, B.xbar,
                                   static_cast<size_t>(h->n_pad), ncclDouble, h->comm, h->stream));
-    launch_dist_dual(B, h->A, h->stream);
-    launch_dist_trans_partial(B, h->At, h->stream);
-    if (!B.p2p && (rc = reduce_scatter_cols(h, B.p_full, B.aty_rs))) return rc;
-    launch_dist_interaction(B, h->A, h->stream);  // peer mode: pulls and sums the partial products
+    launch_dist_dual(B, h->A, h->stream);  // peer mode: pushes its rows of y+ to every rank
+    if (!B.p2p)
+      NCCL_TRY(h->nccl->AllGather(B.y_full + static_cast<size_t>(h->rank) * h->m_pad, B.y_full,
+                                  static_cast<size_t>(h->m_pad), ncclDouble, h->comm, h->stream));
+    launch_dist_trans(B, h->A, h->At, h->stream);
     if (!B.p2p && (rc = exchange_scalars_dev(h))) return rc;
     launch_dist_finalize(B, h->stream);
   }
@@ -825,7 +859,7 @@ static int enqueue_attempts(folp_handle* h, int attempts) {
     }
     TRY(cudaGraphLaunch(it->second, h->stream));
   }
-  h->launches += (h->world == 1 ? 3 : 5) * static_cast<int64_t>(attempts);
+  h->launches += (h->world == 1 ? 3 : 4) * static_cast<int64_t>(attempts);
   return FOLP_OK;
 }
 
@@ -884,8 +918,9 @@ static int tr_round(folp_handle* h, const TrProblem& P, int passes, bool init) {
   int rc;
   auto stage = [&](int st) -> int {
     launch_tr_stage(h->B, P, h->d_trs, st, h->stream);
-    if ((rc = exchange_scalars_dev(h))) return rc;
-    launch_tr_combine(h->B, P, h->d_trs, st, h->stream);
+    const double* recv = nullptr;
+    if ((rc = exchange_block(h, h->B.sc_send, 16, &recv))) return rc;
+    launch_tr_combine(h->B, P, h->d_trs, st, recv, h->stream);
     h->launches += 2;
     return FOLP_OK;
   };
@@ -1258,8 +1293,8 @@ extern "C" int folp_get_solution(folp_handle* h, int which, int unscaled, double
   } else {
     px = B.x[s->cur]; py = B.y[s->cur];
   }
-  // sp.jl:65-67; tr_t / tr_d / aty_rs are free scratch outside a trust-region solve / attempt
-  double* sx = h->world > 1 ? B.aty_rs : B.tr_t;
+  // sp.jl:65-67; tr_t / tr_d / col_tmp are free scratch outside a trust-region solve / attempt
+  double* sx = h->world > 1 ? B.col_tmp : B.tr_t;
   double* sy = B.tr_d;
   launch_scale_div(px, unscaled ? B.D : nullptr, sx, B.n, B.grid_vec, h->stream);
   launch_scale_div(py, unscaled ? B.E : nullptr, sy, B.m, B.grid_vec, h->stream);
@@ -1402,7 +1437,7 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
     if (B.m)
       TRY(cudaMemcpyAsync(B.tr_t, in + h->row0, sizeof(double) * B.m, cudaMemcpyHostToDevice,
                           h->stream));
-    double* d_out = h->world > 1 ? B.aty_rs : B.tr_d;
+    double* d_out = h->world > 1 ? B.col_tmp : B.tr_d;
     if ((rc = spmv_At(h, B.tr_t, d_out))) return rc;
     if ((rc = fetch_cols(h, d_out, out))) return rc;
   }
@@ -1419,7 +1454,7 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
   s->target_iterations = INT64_MAX / 4;
   s->active = s->numerical_error ? 0 : 1;
   if ((rc = push_state(h))) return rc;
-  const int nk = h->world == 1 ? 3 : 5;  // kernels (and, without peer memory, NCCL calls) per attempt
+  const int nk = h->world == 1 ? 3 : 4;  // kernels (and, without peer memory, NCCL calls) per attempt
   std::vector<cudaEvent_t> ev(static_cast<size_t>((nk + 1) * attempts));
   for (auto& e : ev) TRY(cudaEventCreate(&e));
   for (int64_t a = 0; a < attempts; ++a) {
@@ -1434,17 +1469,19 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
     if (!B.p2p)
       NCCL_TRY(h->nccl->AllGather(B.xbar + static_cast<size_t>(h->rank) * h->n_pad, B.xbar,
                                   static_cast<size_t>(h->n_pad), ncclDouble, h->comm, h->stream));
+    if (B.dbg & 4) launch_copy(B.xbar, h->d_cols, static_cast<int64_t>(h->world) * h->n_pad, h->stream);
     TRY(cudaEventRecord(e[1], h->stream));
     launch_dist_dual(B, h->A, h->stream);
+    if (!B.p2p)
+      NCCL_TRY(h->nccl->AllGather(B.y_full + static_cast<size_t>(h->rank) * h->m_pad, B.y_full,
+                                  static_cast<size_t>(h->m_pad), ncclDouble, h->comm, h->stream));
+    if (B.dbg & 4) launch_copy(B.y_full, h->d_rows, static_cast<int64_t>(h->world) * h->m_pad, h->stream);
     TRY(cudaEventRecord(e[2], h->stream));
-    launch_dist_trans_partial(B, h->At, h->stream);
-    if (!B.p2p && (rc = reduce_scatter_cols(h, B.p_full, B.aty_rs))) return rc;
-    TRY(cudaEventRecord(e[3], h->stream));
-    launch_dist_interaction(B, h->A, h->stream);
+    launch_dist_trans(B, h->A, h->At, h->stream);
     if (!B.p2p && (rc = exchange_scalars_dev(h))) return rc;
-    TRY(cudaEventRecord(e[4], h->stream));
+    TRY(cudaEventRecord(e[3], h->stream));
     launch_dist_finalize(B, h->stream);
-    TRY(cudaEventRecord(e[5], h->stream));
+    TRY(cudaEventRecord(e[4], h->stream));
   }
   CHECK_LAUNCH();
   h->launches += nk * attempts;

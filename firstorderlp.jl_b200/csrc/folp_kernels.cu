@@ -28,11 +28,15 @@ __device__ __forceinline__ unsigned long long p2p_value(const DevState& s, int k
 }
 // One thread, after the data it publishes was fenced system-wide: raise this rank's flag of
 // `kind` on every rank.
+// (Loops over ranks run to the constant kMaxWorld and are unrolled: a run-time index into the
+// pointer tables of the kernel-parameter struct would force the whole struct into local memory.)
 __device__ __forceinline__ void p2p_signal(const Bufs& B, int kind, unsigned long long v) {
-  for (int r = 0; r < B.world; ++r) {
-    unsigned long long* f = B.flag_peer[r] + kind * kMaxWorld + B.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
-  }
+#pragma unroll
+  for (int r = 0; r < kMaxWorld; ++r)
+    if (r < B.world) {
+      unsigned long long* f = B.flag_peer[r] + kind * kMaxWorld + B.rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+    }
 }
 // One thread: wait until every rank's flag of `kind` has reached v. Gives up after ~2 s so
 // that a lost peer surfaces as an error instead of a hung device.
@@ -45,15 +49,26 @@ __device__ __forceinline__ void p2p_wait(const Bufs& B, int kind, unsigned long 
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
       if (cur >= v) break;
       if (++spins > 20000000ll) {
-        B.st->p2p_timeout = 1;
+        atomicExch(B.counters + 6, 1u);  // sticky; the host turns it into an error
         return;
       }
       __nanosleep(64);
     }
   }
 }
+// "Last block done" for data that peers will read. Every block orders its (remote) stores
+// before its ticket with a gpu-scope fence; the last block, having observed every ticket, issues
+// the ONE system-scope fence before the flag goes out (causality order is transitive across the
+// two scopes). A system-scope fence per block is correct too, but those serialise device-wide
+// (~20 ns each, 600-1200 blocks per kernel). True in all threads of exactly one block.
+__device__ __forceinline__ bool last_block_arrive_sys(unsigned* counter) {
+  const bool last = last_block_arrive(counter);
+  if (last && threadIdx.x == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+  return last;
+}
 // All threads of a CTA: block until the exchange has arrived.
 __device__ __forceinline__ void p2p_wait_cta(const Bufs& B, int kind) {
+  if (B.dbg & 2) return;
   if (threadIdx.x == 0) p2p_wait(B, kind, p2p_value(*B.st, kind));
   __syncthreads();
 }
@@ -109,6 +124,8 @@ __device__ __forceinline__ double primal_elem(const PrimalCtx& k, double x, doub
   return d;
 }
 
+// DIST: partitioned mode (world > 1); the single-GPU instantiation carries no exchange code.
+template <bool DIST>
 __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   __shared__ double sh[32];
   const DevState& s = *B.st;
@@ -149,9 +166,10 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     if (avg) reinterpret_cast<double2*>(B.sum_x)[j] = sx;
     if (k.do_primal) reinterpret_cast<double2*>(xn)[j] = xp;
     reinterpret_cast<double2*>(B.xbar + B.xbar_off)[j] = xb;
-    if (B.p2p) {  // push the slice into every peer's copy of xbar (posted NVLink stores)
-      for (int r = 0; r < B.world; ++r)
-        if (r != B.rank) reinterpret_cast<double2*>(B.xbar_peer[r] + B.xbar_off)[j] = xb;
+    if (DIST && B.p2p && !(B.dbg & 1)) {  // push the slice into every peer's copy of xbar (posted NVLink stores)
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < B.world && r != B.rank) reinterpret_cast<double2*>(B.xbar_peer[r] + B.xbar_off)[j] = xb;
     }
     acc += d0 * d0;
     acc += d1 * d1;
@@ -163,21 +181,18 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     if (avg) B.sum_x[j] = sx;
     if (k.do_primal) xn[j] = xp;
     B.xbar[B.xbar_off + j] = xb;
-    if (B.p2p) {
-      for (int r = 0; r < B.world; ++r)
-        if (r != B.rank) B.xbar_peer[r][B.xbar_off + j] = xb;
+    if (DIST && B.p2p) {
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < B.world && r != B.rank) B.xbar_peer[r][B.xbar_off + j] = xb;
     }
     acc += d * d;
   }
   const double t = block_reduce<false>(acc, sh);
   if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 0)[blockIdx.x] = t;
-  if (B.p2p) {  // the last block to finish announces this rank's slice on every rank
-    __threadfence_system();
-    if (last_block_arrive(B.counters + 4) && threadIdx.x == 0) {
-      __threadfence_system();
-      p2p_signal(B, 0, p2p_value(s, 0));
-    }
-  }
+  // the last block to finish announces this rank's slice on every rank
+  if (DIST && B.p2p && last_block_arrive_sys(B.counters + 4) && threadIdx.x == 0)
+    p2p_signal(B, 0, p2p_value(s, 0));
 }
 
 // ---------------------------------------------------------------------------
@@ -268,7 +283,8 @@ __device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double d
 // ---------------------------------------------------------------------------
 // K2 epilogue: dual step on row i given (A*xbar)_i
 // ---------------------------------------------------------------------------
-struct EpiDual {
+template <bool DIST>
+struct EpiDualT {
   static constexpr int kNumIn = 3;  // y, b, sum_y
   Bufs B;
   const double* yc;
@@ -286,10 +302,10 @@ struct EpiDual {
     pend = s.pending_avg & 1;
     w = s.pending_w;
     acc = 0.0;
-    if (B.p2p) p2p_wait_cta(B, 0);  // every rank's slice of xbar has landed
+    if (DIST && B.p2p) p2p_wait_cta(B, 0);  // every rank's slice of xbar has landed
     return true;
   }
-  __device__ const double* input() const { return B.xbar; }
+  __device__ const double* input() const { return B.xbar_priv ? B.xbar_priv : B.xbar; }
   __device__ const double* in_ptr(int v) const { return v == 0 ? yc : (v == 1 ? B.b : B.sum_y); }
   __device__ void row(int i, double ax, double yv, double bi, double sy) {
     if (pend) B.sum_y[i] = sy + yv * w;  // deferred add_to_dual_solution_weighted_average
@@ -297,19 +313,31 @@ struct EpiDual {
     double yp = yv + f * g;
     if (i >= B.neq) yp = fmax(yp, 0.0);  // project_dual!, sp.jl:110-117
     yn[i] = yp;
+    if (DIST) {  // the transposed product of every rank gathers the full new dual iterate
+      const size_t at = static_cast<size_t>(B.rank) * B.m_pad + i;
+      B.y_full[at] = yp;
+      if (B.p2p && !(B.dbg & 1)) {
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+          if (r < B.world && r != B.rank) B.yfull_peer[r][at] = yp;
+      }
+    }
     const double d = yp - yv;
     acc += d * d;
   }
   __device__ void finish(double* sh) {
     const double t = block_reduce<false>(acc, sh);
     if (threadIdx.x == 0) part_ptr(B, kSlotDual, 0)[blockIdx.x] = t;
+    if (DIST && B.p2p && last_block_arrive_sys(B.counters + 5) && threadIdx.x == 0)
+      p2p_signal(B, 1, p2p_value(*B.st, 1));
   }
 };
 
 // ---------------------------------------------------------------------------
 // K3 epilogue: (A'*y+)_j, interaction dot, and the scalar rule in the last CTA
 // ---------------------------------------------------------------------------
-struct EpiTrans {
+template <bool DIST>
+struct EpiTransT {
   static constexpr int kNumIn = 3;  // x, x+, A'y
   Bufs B;
   int g_primal, g_dual;  // grids of K1 and K2 (number of partials they wrote)
@@ -325,9 +353,12 @@ struct EpiTrans {
     atn = sel(B.aty, s.cur ^ 1);
     inter = 0.0;
     dp2 = 0.0;
+    if (DIST && B.p2p) p2p_wait_cta(B, 1);  // every rank's rows of y+ have landed
     return true;
   }
-  __device__ const double* input() const { return sel(B.y, B.st->cur ^ 1); }
+  __device__ const double* input() const {
+    return DIST ? (B.yfull_priv ? B.yfull_priv : B.y_full) : sel(B.y, B.st->cur ^ 1);
+  }
   __device__ const double* in_ptr(int v) const { return v == 0 ? xc : (v == 1 ? xn : atc); }
   __device__ void row(int j, double at, double xcj, double xnj, double atcj) {
     atn[j] = at;
@@ -348,62 +379,21 @@ struct EpiTrans {
     const double dy2 = reduce_partials<false>(part_ptr(B, kSlotDual, 0), g_dual, sh);
     const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
     const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
-    if (threadIdx.x == 0) finalize_attempt(B.st, dx2, dy2, it, dp);
-  }
-};
-
-// ---------------------------------------------------------------------------
-// row-partitioned take_step (world > 1). Same arithmetic as the fused single-GPU
-// kernels, cut where the exchanges sit:
-//   k_primal (slice)  -> allgather xbar -> k_spmv<EpiDual> (local rows)
-//   -> k_spmv<EpiPlain> p = A_r' y_r+  -> reduce-scatter -> k_interaction (slice)
-//   -> allgather {|dx|^2, |dy|^2, dx.dA'y, |dA'y|^2} -> k_finalize_dist
-// Every rank sums the gathered scalars in rank order, so all ranks take the same
-// accept/reject decision and step size bit for bit.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kVecThreads) k_interaction(Bufs B, int g_primal, int g_dual) {
-  __shared__ double sh[32];
-  const DevState& s = *B.st;
-  if (!s.active) return;
-  const double* __restrict__ xc = sel(B.x, s.cur);
-  const double* __restrict__ xn = sel(B.x, s.cur ^ 1);
-  const double* __restrict__ atc = sel(B.aty, s.cur);
-  double* __restrict__ atn = sel(B.aty, s.cur ^ 1);
-  double inter = 0.0, dp2 = 0.0;
-  const int stride = gridDim.x * blockDim.x;
-  if (B.p2p) p2p_wait_cta(B, 1);  // every rank's partial product is complete
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < B.n; j += stride) {
-    double at;
-    if (B.p2p) {  // pull this slice of every rank's partial product, summed in rank order
-      at = 0.0;
-      for (int r = 0; r < B.world; ++r) at += __ldcg(B.pfull_peer[r] + B.xbar_off + j);
-    } else {
-      at = B.aty_rs[j];  // NCCL reduce-scatter result
-    }
-    atn[j] = at;
-    const double dx = xn[j] - xc[j];
-    const double dat = at - atc[j];
-    inter += dx * dat;  // pdhg.jl:542-544
-    dp2 += dat * dat;   // pdhg.jl:615 (Malitsky-Pock)
-  }
-  const double a = block_reduce<false>(inter, sh);
-  const double b = block_reduce<false>(dp2, sh);
-  if (threadIdx.x == 0) {
-    part_ptr(B, kSlotTrans, 0)[blockIdx.x] = a;
-    part_ptr(B, kSlotTrans, 1)[blockIdx.x] = b;
-  }
-  if (!last_block_arrive(B.counters + kSlotTrans)) return;
-  const double dx2 = reduce_partials<false>(part_ptr(B, kSlotPrimal, 0), g_primal, sh);
-  const double dy2 = reduce_partials<false>(part_ptr(B, kSlotDual, 0), g_dual, sh);
-  const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
-  const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
-  if (threadIdx.x == 0) {
-    if (B.p2p) {  // push the four scalars into every rank's slot for this rank, then announce
-      const double t[4] = {dx2, dy2, it, dp};
-      for (int r = 0; r < B.world; ++r)
-        for (int k = 0; k < 4; ++k) B.sc_peer[r][B.rank * kScBlock + k] = t[k];
+    if (threadIdx.x != 0) return;
+    if (!DIST) {
+      finalize_attempt(B.st, dx2, dy2, it, dp);
+    } else if (B.p2p) {  // push the four scalars into every rank's slot for this rank, then announce
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < B.world) {
+          double* slot = B.sc_peer[r] + B.rank * kScBlock;
+          slot[0] = dx2;
+          slot[1] = dy2;
+          slot[2] = it;
+          slot[3] = dp;
+        }
       __threadfence_system();
-      p2p_signal(B, 2, p2p_value(s, 2));
+      p2p_signal(B, 2, p2p_value(*B.st, 2));
     } else {
       B.sc_send[0] = dx2;
       B.sc_send[1] = dy2;
@@ -411,56 +401,58 @@ __global__ void __launch_bounds__(kVecThreads) k_interaction(Bufs B, int g_prima
       B.sc_send[3] = dp;
     }
   }
-}
+};
 
+// ---------------------------------------------------------------------------
+// partitioned take_step (world > 1). Rank r owns a block of rows of A (CSR, for A*xbar and
+// the dual step) AND a slice of columns of A (CSR of A[:, slice]', for A'*y+ and the primal
+// step), so both products have full-length rows, need no cross-rank reduction and are summed
+// in the same order as on one GPU. Same arithmetic as the single-GPU kernels, with the
+// exchanges where a product needs the other side's full vector:
+//   k_primal (slice, pushes xbar)  -> [xbar on every rank] -> k_spmv<EpiDual> (local rows,
+//   pushes y+) -> [y+ on every rank] -> k_spmv<EpiTrans> (local slice, interaction) ->
+//   [{|dx|^2, |dy|^2, dx.dA'y, |dA'y|^2} of every rank] -> k_finalize_dist
+// Every rank sums the gathered scalars in rank order, so all ranks take the same
+// accept/reject decision and step size bit for bit.
+// ---------------------------------------------------------------------------
 __global__ void k_finalize_dist(Bufs B) {
   if (threadIdx.x != 0 || !B.st->active) return;
-  if (B.p2p) p2p_wait(B, 2, p2p_value(*B.st, 2));
+  if (B.p2p) {
+    p2p_wait(B, 2, p2p_value(*B.st, 2));
+    if (__ldcg(B.counters + 6)) B.st->p2p_timeout = 1;  // stops the batch, see finalize_attempt
+  }
   double t[4] = {0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < B.world; ++r)
     for (int k = 0; k < 4; ++k) t[k] += __ldcg(B.sc_recv + r * kScBlock + k);
   finalize_attempt(B.st, t[0], t[1], t[2], t[3]);
 }
 
+using EpiDual = EpiDualT<false>;
+using EpiTrans = EpiTransT<false>;
+using EpiDualDist = EpiDualT<true>;
+using EpiTransDist = EpiTransT<true>;
+
 static int spmv_grid(const SpmvMat& A, int grid_spmv);
+// every block of a pushing kernel ends with one system-scope fence, and those serialise:
+// the partitioned primal step uses fewer, longer-running blocks
+static int dist_primal_grid(const Bufs& B) { return B.grid_vec / 2; }
 
 void launch_dist_primal(const Bufs& B, cudaStream_t s) {
-  k_primal<<<B.grid_vec, kVecThreads, 0, s>>>(B);
+  k_primal<true><<<dist_primal_grid(B), kVecThreads, 0, s>>>(B);
 }
 void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
-  EpiDual ed;
+  EpiDualDist ed;
   ed.B = B;
-  k_spmv<EpiDual><<<spmv_grid(A, B.grid_spmv), kSpmvThreads, 0, s>>>(A, ed);
+  k_spmv<EpiDualDist><<<spmv_grid(A, B.grid_spmv), kSpmvThreads, 0, s>>>(A, ed);
 }
-void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s);
-void launch_dist_interaction(const Bufs& B, const SpmvMat& A, cudaStream_t s) {
-  k_interaction<<<B.grid_vec, kVecThreads, 0, s>>>(B, B.grid_vec, spmv_grid(A, B.grid_spmv));
+void launch_dist_trans(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaStream_t s) {
+  EpiTransDist et;
+  et.B = B;
+  et.g_primal = dist_primal_grid(B);
+  et.g_dual = spmv_grid(A, B.grid_spmv);
+  k_spmv<EpiTransDist><<<spmv_grid(At, B.grid_spmv), kSpmvThreads, 0, s>>>(At, et);
 }
 void launch_dist_finalize(const Bufs& B, cudaStream_t s) { k_finalize_dist<<<1, 32, 0, s>>>(B); }
-
-// K3 of the row-partitioned mode: p = A_r' * y_r+ into this rank's p_full
-struct EpiTransPartial {
-  static constexpr int kNumIn = 0;
-  Bufs B;
-  __device__ bool begin() { return B.st->active != 0; }
-  __device__ const double* input() const { return sel(B.y, B.st->cur ^ 1); }
-  __device__ const double* in_ptr(int) const { return nullptr; }
-  __device__ void row(int r, double s, double, double, double) { B.p_full[r] = s; }
-  __device__ void finish(double*) {
-    if (!B.p2p) return;
-    __threadfence_system();
-    if (last_block_arrive(B.counters + 5) && threadIdx.x == 0) {
-      __threadfence_system();
-      p2p_signal(B, 1, p2p_value(*B.st, 1));
-    }
-  }
-};
-
-void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s) {
-  EpiTransPartial ep;
-  ep.B = B;
-  k_spmv<EpiTransPartial><<<spmv_grid(At, B.grid_spmv), kSpmvThreads, 0, s>>>(At, ep);
-}
 
 int spmv_configure() { return cudaSuccess; }  // no dynamic shared memory to opt into
 
@@ -482,7 +474,7 @@ void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, in
   et.g_primal = g1;
   et.g_dual = g2;
   for (int a = 0; a < attempts; ++a) {
-    k_primal<<<g1, kVecThreads, 0, s>>>(B);
+    k_primal<false><<<g1, kVecThreads, 0, s>>>(B);
     k_spmv<EpiDual><<<g2, kSpmvThreads, 0, s>>>(A, ed);
     k_spmv<EpiTrans><<<g3, kSpmvThreads, 0, s>>>(At, et);
   }
@@ -499,7 +491,7 @@ void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& A
   et.g_primal = g1;
   et.g_dual = g2;
   cudaEventRecord(ev[0], s);
-  k_primal<<<g1, kVecThreads, 0, s>>>(B);
+  k_primal<false><<<g1, kVecThreads, 0, s>>>(B);
   cudaEventRecord(ev[1], s);
   k_spmv<EpiDual><<<g2, kSpmvThreads, 0, s>>>(A, ed);
   cudaEventRecord(ev[2], s);
@@ -1008,7 +1000,8 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_final(Bufs B, TrProblem P, T
 }
 
 // row-partitioned mode: applies the rank-ordered totals of the exchanged local sums
-__global__ void k_tr_combine(Bufs B, TrProblem P, TrState* trs, int stage) {
+__global__ void k_tr_combine(Bufs B, TrProblem P, TrState* trs, int stage,
+                             const double* __restrict__ recv) {
   if (threadIdx.x != 0) return;
   double r[TI_TOTAL];
   const int count = stage == kTrInit ? TI_TOTAL : (stage == kTrPass ? 6 : 2);
@@ -1016,7 +1009,7 @@ __global__ void k_tr_combine(Bufs B, TrProblem P, TrState* trs, int stage) {
     const bool is_max = stage == kTrInit && k == TI_max_t;
     double v = is_max ? -CUDART_INF : 0.0;
     for (int q = 0; q < B.world; ++q) {
-      const double w = B.sc_recv[q * kScBlock + k];
+      const double w = __ldcg(recv + q * kScBlock + k);
       v = is_max ? fmax(v, w) : v + w;
     }
     r[k] = v;
@@ -1043,8 +1036,31 @@ void launch_tr_stage(const Bufs& B, const TrProblem& P, TrState* d_trs, int stag
   else if (stage == kTrPass) k_tr_pass<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
   else k_tr_final<<<B.grid_vec, kVecThreads, 0, s>>>(B, P, d_trs);
 }
-void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s) {
-  k_tr_combine<<<1, 32, 0, s>>>(B, P, d_trs, stage);
+void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage,
+                       const double* recv, cudaStream_t s) {
+  k_tr_combine<<<1, 32, 0, s>>>(B, P, d_trs, stage, recv);
+}
+
+__global__ void k_exchange(Bufs B, const double* __restrict__ src, int count, unsigned long long seq,
+                           int parity) {
+  const int k = threadIdx.x;
+  if (k < count) {
+    const double v = src[k];
+    const size_t slot = static_cast<size_t>(parity) * B.world * kScBlock + B.rank * kScBlock + k;
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < B.world) B.scx_peer[r][slot] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p2p_signal(B, 3, seq);
+    p2p_wait(B, 3, seq);
+  }
+}
+void launch_exchange(const Bufs& B, const double* src, int count, unsigned long long seq, int parity,
+                     cudaStream_t s) {
+  k_exchange<<<1, kScBlock, 0, s>>>(B, src, count, seq, parity);
 }
 
 // ---------------------------------------------------------------------------

@@ -6,7 +6,7 @@
 namespace folp {
 
 constexpr int kMaxWorld = 8;
-constexpr int kNumFlagKinds = 3;  // xbar pushed | partial A'y ready | step-rule scalars pushed
+constexpr int kNumFlagKinds = 4;  // xbar pushed | partial A'y ready | step-rule scalars pushed | evaluation scalars
 
 // Device pointers of one rank. Lengths: n_loc primal slice, m_loc dual rows.
 struct Bufs {
@@ -34,19 +34,26 @@ struct Bufs {
   // writes [xbar_off, xbar_off + n).
   int world = 1, rank = 0;
   int xbar_off = 0;
-  double* p_full = nullptr;    // this rank's partial A_r' * y_r, world * n_pad doubles
-  double* aty_rs = nullptr;    // reduce-scatter result: (A' y+) on the local slice
+  double* y_full = nullptr;    // the FULL new dual iterate, world * m_pad doubles (rank-major, padded)
+  int m_pad = 0;               // rows per rank in y_full; this rank writes [rank*m_pad, rank*m_pad + m)
+  double* col_tmp = nullptr;   // scratch, one padded primal slice
   double* sc_send = nullptr;   // kScBlock scalars this rank contributes to an exchange
   double* sc_recv = nullptr;   // world * kScBlock scalars, rank-major
   // ---- peer-memory exchange (CUDA IPC over NVLink / NVSwitch), replaces NCCL inside take_step ----
-  // Every rank exposes one region {xbar, p_full, sc_recv, flags}; *_peer[r] is rank r's copy
+  // Every rank exposes one region {xbar, y_full, sc_recv, scx, flags}; *_peer[r] is rank r's copy
   // (this rank's own entries are the local pointers above).
   int p2p = 0;
+  int dbg = 0;  // development probes (FOLP_DEBUG_FLAGS): 1 = skip the remote pushes, 2 = skip flag waits
+  const double* xbar_priv = nullptr;   // when set: K2 gathers from this private copy of xbar
+  const double* yfull_priv = nullptr;  // when set: K3 gathers from this private copy of y_full
   double* xbar_peer[kMaxWorld] = {};
-  double* pfull_peer[kMaxWorld] = {};
+  double* yfull_peer[kMaxWorld] = {};
   double* sc_peer[kMaxWorld] = {};
   unsigned long long* flag_peer[kMaxWorld] = {};
   unsigned long long* flags = nullptr;  // local flags [kNumFlagKinds][kMaxWorld]: kind k, source rank r
+  // evaluation-block scalar exchanges: two alternating receive buffers of world * kScBlock doubles
+  double* scx = nullptr;                // local
+  double* scx_peer[kMaxWorld] = {};
 };
 constexpr int kScBlock = 64;
 
@@ -94,12 +101,11 @@ struct TrProblem {
 
 void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, int attempts,
                           cudaStream_t s);
-// The pieces of one attempt in row-partitioned mode; folp_api.cu interleaves them with the
-// NCCL exchanges (allgather xbar | reduce-scatter A'y | allgather of the 4 step-rule scalars).
+// The pieces of one attempt in partitioned mode; without peer memory folp_api.cu interleaves them
+// with the NCCL exchanges (allgather xbar | allgather y+ | allgather of the 4 step-rule scalars).
 void launch_dist_primal(const Bufs& B, cudaStream_t s);
 void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s);
-void launch_dist_trans_partial(const Bufs& B, const SpmvMat& At, cudaStream_t s);
-void launch_dist_interaction(const Bufs& B, const SpmvMat& A, cudaStream_t s);
+void launch_dist_trans(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaStream_t s);
 void launch_dist_finalize(const Bufs& B, cudaStream_t s);
 // one attempt with events ev[0..3] recorded before/between/after the three kernels
 void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaEvent_t* ev,
@@ -120,7 +126,13 @@ void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bo
 // the rank-ordered totals to the TrState.
 enum TrStage : int { kTrInit = 0, kTrPass = 1, kTrFinal = 2 };
 void launch_tr_stage(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s);
-void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage, cudaStream_t s);
+void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int stage,
+                       const double* recv, cudaStream_t s);
+// peer-memory scalar exchange of the evaluation block: pushes src[0..count) into slot `rank` of
+// every rank's receive buffer `parity` and waits until all ranks have done the same (`seq` is the
+// host-side count of such exchanges, identical on every rank)
+void launch_exchange(const Bufs& B, const double* src, int count, unsigned long long seq, int parity,
+                     cudaStream_t s);
 void launch_scale_div(const double* in, const double* scale, double* out, int len, int grid,
                       cudaStream_t s);
 void launch_fill(double* p, double v, int64_t len, cudaStream_t s);

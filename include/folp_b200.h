@@ -231,13 +231,13 @@ typedef struct folp_eval {
 typedef struct folp_handle folp_handle;
 
 /* Multi-GPU: one process per GPU (torchrun). Each rank passes the FULL scaled
- * problem; the library keeps only its shard of the 1-D row partition: a
- * contiguous block of constraint rows balanced by nonzeros (A_r in CSR and
- * A_r' in CSR, y, b, dual averages) and an equal slice of the primal side
- * (x, c, l, u, A'y, primal averages). Per take_step attempt the ranks exchange
- * the extrapolated primal (allgather), the partial products A_r' y_r
- * (reduce-scatter) and four step-rule scalars (allgather, summed in rank order
- * so that every rank takes the same decision). Every rank must make the same
+ * problem; the library keeps only its shard: a contiguous block of constraint
+ * rows balanced by nonzeros (A[rows,:] in CSR, y, b, dual averages) for A*xbar
+ * and the dual step, and an equal slice of the columns (A[:,slice]' in CSR, x,
+ * c, l, u, A'y, primal averages) for A'*y and the primal step. Per take_step
+ * attempt the ranks exchange the extrapolated primal (allgather), the new dual
+ * iterate (allgather) and four step-rule scalars (summed in rank order so that
+ * every rank takes the same decision); no product needs a cross-rank reduction. Every rank must make the same
  * sequence of calls; records and solutions returned are the global ones on
  * every rank. nccl_unique_id is the 128-byte ncclUniqueId created on rank 0 by
  * folp_nccl_unique_id() and broadcast by the host's own plumbing
@@ -262,8 +262,8 @@ int folp_partition(int64_t num_constraints, int64_t num_variables, int64_t num_n
                    int64_t* row_begin_out, int64_t* col_begin_out);
 
 /* How take_step exchanges data between ranks: 0 = single GPU (none), 1 = NCCL
- * collectives, 2 = peer memory (CUDA IPC over NVLink: K1 pushes xbar, the
- * interaction kernel pulls the partial products; no NCCL call per attempt). */
+ * collectives, 2 = peer memory (CUDA IPC over NVLink: K1 pushes its slice of
+ * xbar, K2 its rows of y+ into every rank's copy; no NCCL call per attempt). */
 int folp_exchange_mode(folp_handle* h);
 
 /* What this rank holds: rows [row_begin,row_end), primal slice [col_begin,col_end). */
@@ -330,9 +330,9 @@ int folp_counters(folp_handle* h, int64_t* kernel_launches,
 /* Measurement hook for bench.py: runs `attempts` real take_step attempts
  * (un-graphed) with CUDA events on the library's stream around each kernel, and
  * returns the accumulated device milliseconds in ms_out[8]: single GPU
- * {primal step, A*xbar + dual step, A'*y + interaction/step rule}; row-
- * partitioned {primal slice (+ xbar exchange), A_r*xbar + dual step, partial
- * A_r'*y (+ reduce-scatter), interaction (+ scalar exchange), step rule}; the
+ * {primal step, A*xbar + dual step, A'*y + interaction/step rule};
+ * partitioned {primal slice (+ xbar exchange), A[rows,:]*xbar + dual step (+ y
+ * exchange), A[:,slice]'*y + interaction (+ scalar exchange), step rule}; the
  * rest 0. *attempts_run = attempts that did work. The solver state advances. */
 int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[8],
                                 int64_t* attempts_run);

@@ -47,8 +47,7 @@ def main():
         per = [k / args.attempts for k in kms]
         if distributed.state() is not None:
             out = {"rank": rank, "exchange": s.shard_info()["exchange"],
-                   "us": {k: v * 1e3 for k, v in zip(("primal", "dual", "trans_partial", "interaction",
-                                                       "finalize"), per)}, "iter_us": sum(per) * 1e3}
+                   "us": {k: v * 1e3 for k, v in zip(("primal", "dual", "trans", "finalize"), per)}, "iter_us": sum(per) * 1e3}
             s.close()
             print(json.dumps(out), flush=True)
             continue
