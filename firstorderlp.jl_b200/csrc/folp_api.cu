@@ -12,7 +12,9 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <atomic>
 #include <new>
+#include <thread>
 
 #include "folp_kernels.cuh"
 #include "folp_nccl.h"
@@ -25,6 +27,27 @@ thread_local std::string g_create_error;
 double now_sec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+
+// Splits [begin, end) over up to 8 host threads (folp_create's O(nnz) loops: index conversion,
+// transposition, position-major packing). fn(lo, hi, thread_index).
+template <class F>
+void parallel_for(int64_t begin, int64_t end, int64_t min_chunk, F fn) {
+  const int64_t len = end - begin;
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), std::max<int64_t>(1, len / min_chunk)));
+  if (T <= 1) {
+    if (len > 0) fn(begin, end, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(static_cast<size_t>(T));
+  for (int t = 0; t < T; ++t) {
+    const int64_t lo = begin + len * t / T, hi = begin + len * (t + 1) / T;
+    th.emplace_back([=, &fn] { fn(lo, hi, t); });
+  }
+  for (auto& x : th) x.join();
+}
+constexpr int kMaxHostThreads = 8;
 }  // namespace
 
 struct folp_handle {
@@ -130,8 +153,6 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
   tiles.reserve(static_cast<size_t>(rows) / 32 + 16);
   int nlong = 0, nchunks_total = 0;
   int r = 0;
-  std::vector<int> tc;
-  std::vector<double> tv;
   while (r < rows) {
     const int len = rowptr[r + 1] - rowptr[r];
     if (len > kChunkNnz) {  // long row: chunks
@@ -166,19 +187,28 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
     t.nnz_end = rowptr[g1];
     t.rows_kind = (kTileThreadPerRow << 16) | (g1 - g0);
     tiles.push_back(t);
-    // position-major inside the group (each row keeps its own order)
-    const int kb = rowptr[g0], ke = rowptr[g1];
-    tc.assign(colidx.begin() + kb, colidx.begin() + ke);
-    tv.assign(vals.begin() + kb, vals.begin() + ke);
-    int out = kb;
-    for (int pos = 0; out < ke; ++pos)
-      for (int q = g0; q < g1; ++q)
-        if (rowptr[q + 1] - rowptr[q] > pos) {
-          colidx[out] = tc[rowptr[q] - kb + pos];
-          vals[out] = tv[rowptr[q] - kb + pos];
-          ++out;
-        }
   }
+  // position-major inside every narrow group (each row keeps its own order); groups are independent
+  parallel_for(0, static_cast<int64_t>(tiles.size()), 1 << 12, [&](int64_t lo, int64_t hi, int) {
+    std::vector<int> tc;
+    std::vector<double> tv;
+    for (int64_t ti = lo; ti < hi; ++ti) {
+      const Tile& t = tiles[ti];
+      if ((t.rows_kind >> 16) != kTileThreadPerRow) continue;
+      const int g0 = t.row_begin, g1 = g0 + (t.rows_kind & 0xffff);
+      const int kb = rowptr[g0], ke = rowptr[g1];
+      tc.assign(colidx.begin() + kb, colidx.begin() + ke);
+      tv.assign(vals.begin() + kb, vals.begin() + ke);
+      int out = kb;
+      for (int pos = 0; out < ke; ++pos)
+        for (int q = g0; q < g1; ++q)
+          if (rowptr[q + 1] - rowptr[q] > pos) {
+            colidx[out] = tc[rowptr[q] - kb + pos];
+            vals[out] = tv[rowptr[q] - kb + pos];
+            ++out;
+          }
+    }
+  });
   M->ntiles = static_cast<int>(tiles.size());
   M->nlong = nlong;
   const size_t pad = 16;
@@ -454,12 +484,16 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     std::vector<int> rp(static_cast<size_t>(n) + 1), ci(static_cast<size_t>(nnz));
     std::vector<double> v(static_cast<size_t>(nnz));
     for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - base) : 0;
-    for (int64_t k = 0; k < nnz; ++k) {
-      const int64_t r = p->rowval[k] - base;
-      if (r < 0 || r >= m) { h->err = "row index out of range"; return FOLP_INVALID_ARGUMENT; }
-      ci[k] = static_cast<int>(r);
-      v[k] = p->nzval[k];
-    }
+    std::atomic<int> bad_row{0};
+    parallel_for(0, nnz, 1 << 18, [&](int64_t lo, int64_t hi, int) {
+      for (int64_t k = lo; k < hi; ++k) {
+        const int64_t r = p->rowval[k] - base;
+        if (r < 0 || r >= m) { bad_row.store(1); return; }
+        ci[k] = static_cast<int>(r);
+        v[k] = p->nzval[k];
+      }
+    });
+    if (bad_row.load()) { h->err = "row index out of range"; return FOLP_INVALID_ARGUMENT; }
     for (int64_t j = 0; j < n; ++j)
       if (rp[j] > rp[j + 1] || rp[j] < 0 || rp[j + 1] > nnz) {
         h->err = "colptr is not monotone";
@@ -468,15 +502,57 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     // transpose
     std::vector<int> rp2(static_cast<size_t>(m) + 1, 0), ci2(static_cast<size_t>(nnz));
     std::vector<double> v2(static_cast<size_t>(nnz));
-    for (int64_t k = 0; k < nnz; ++k) rp2[ci[k] + 1] += 1;
-    for (int64_t i = 0; i < m; ++i) rp2[i + 1] += rp2[i];
-    std::vector<int> fillp(rp2.begin(), rp2.end() - 1);
-    for (int64_t j = 0; j < n; ++j)
-      for (int k = rp[j]; k < rp[j + 1]; ++k) {
-        const int pos = fillp[ci[k]]++;
-        ci2[pos] = static_cast<int>(j);  // ascending j inside each row
-        v2[pos] = v[k];
+    {
+      // stable counting sort by row, parallel over column blocks: thread t counts the rows of its
+      // columns, the per-thread offsets are prefix sums over (row, thread), then every thread
+      // scatters its own columns -- ascending j inside each row, independent of the thread count
+      std::vector<int64_t> cut(kMaxHostThreads + 1, n);
+      int T = 0;
+      std::vector<std::vector<int>> hist;
+      {
+        unsigned hw = std::thread::hardware_concurrency();
+        T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u),
+                                               std::max<int64_t>(1, nnz / (1 << 20))));
+        // balance the blocks by nonzeros
+        for (int t = 0; t <= T; ++t) {
+          const int64_t target = nnz * t / T;
+          cut[t] = std::lower_bound(rp.begin(), rp.end(), static_cast<int>(target)) - rp.begin();
+        }
+        cut[0] = 0;
+        cut[T] = n;
+        hist.assign(static_cast<size_t>(T), std::vector<int>());
       }
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+          std::vector<int>& hh = hist[t];
+          hh.assign(static_cast<size_t>(m), 0);
+          for (int k = rp[cut[t]]; k < rp[cut[t + 1]]; ++k) hh[ci[k]] += 1;
+        });
+      for (auto& x : th) x.join();
+      th.clear();
+      int64_t run = 0;
+      for (int64_t i = 0; i < m; ++i) {
+        rp2[i] = static_cast<int>(run);
+        for (int t = 0; t < T; ++t) {
+          const int c = hist[t][i];
+          hist[t][i] = static_cast<int>(run);  // becomes thread t's write cursor for row i
+          run += c;
+        }
+      }
+      rp2[m] = static_cast<int>(run);
+      for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+          std::vector<int>& cur = hist[t];
+          for (int64_t j = cut[t]; j < cut[t + 1]; ++j)
+            for (int k = rp[j]; k < rp[j + 1]; ++k) {
+              const int pos = cur[ci[k]]++;
+              ci2[pos] = static_cast<int>(j);
+              v2[pos] = v[k];
+            }
+        });
+      for (auto& x : th) x.join();
+    }
     int rc;
     if (P == 1) {
       h->row_begin[1] = m;

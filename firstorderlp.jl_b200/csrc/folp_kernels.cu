@@ -154,16 +154,17 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   const int n2 = B.n >> 1;
   for (int j = t0; j < n2; j += stride) {
     const double2 x = reinterpret_cast<const double2*>(xc)[j];
-    const double2 c = reinterpret_cast<const double2*>(B.c)[j];
-    const double2 a = reinterpret_cast<const double2*>(at)[j];
-    const double2 l = reinterpret_cast<const double2*>(B.l)[j];
-    const double2 u = reinterpret_cast<const double2*>(B.u)[j];
-    double2 sx = avg ? reinterpret_cast<const double2*>(B.sum_x)[j] : make_double2(0.0, 0.0);
+    // read-once streams go past L2 (evict-first): at n >= 1e7 L2 is needed for the gathered vectors
+    const double2 c = __ldcs(reinterpret_cast<const double2*>(B.c) + j);
+    const double2 a = __ldcs(reinterpret_cast<const double2*>(at) + j);
+    const double2 l = __ldcs(reinterpret_cast<const double2*>(B.l) + j);
+    const double2 u = __ldcs(reinterpret_cast<const double2*>(B.u) + j);
+    double2 sx = avg ? __ldcs(reinterpret_cast<const double2*>(B.sum_x) + j) : make_double2(0.0, 0.0);
     double2 xp = rd_xn ? reinterpret_cast<const double2*>(xn)[j] : make_double2(0.0, 0.0);
     double2 xb;
     const double d0 = primal_elem(k, x.x, xp.x, c.x, a.x, l.x, u.x, sx.x, xb.x);
     const double d1 = primal_elem(k, x.y, xp.y, c.y, a.y, l.y, u.y, sx.y, xb.y);
-    if (avg) reinterpret_cast<double2*>(B.sum_x)[j] = sx;
+    if (avg) __stcs(reinterpret_cast<double2*>(B.sum_x) + j, sx);
     if (k.do_primal) reinterpret_cast<double2*>(xn)[j] = xp;
     reinterpret_cast<double2*>(B.xbar + B.xbar_off)[j] = xb;
     if (DIST && B.p2p && !(B.dbg & 1)) {  // push the slice into every peer's copy of xbar (posted NVLink stores)
@@ -308,7 +309,7 @@ struct EpiDualT {
   __device__ const double* input() const { return B.xbar_priv ? B.xbar_priv : B.xbar; }
   __device__ const double* in_ptr(int v) const { return v == 0 ? yc : (v == 1 ? B.b : B.sum_y); }
   __device__ void row(int i, double ax, double yv, double bi, double sy) {
-    if (pend) B.sum_y[i] = sy + yv * w;  // deferred add_to_dual_solution_weighted_average
+    if (pend) __stcs(B.sum_y + i, sy + yv * w);  // deferred add_to_dual_solution_weighted_average
     const double g = bi - ax;        // compute_dual_gradient, sp.jl:1102-1107
     double yp = yv + f * g;
     if (i >= B.neq) yp = fmax(yp, 0.0);  // project_dual!, sp.jl:110-117

@@ -36,6 +36,9 @@ namespace folp {
 #ifndef FOLP_GATHER_UNROLL
 #define FOLP_GATHER_UNROLL 4
 #endif
+#ifndef FOLP_PIPELINE
+#define FOLP_PIPELINE 0
+#endif
 constexpr int kGatherUnroll = FOLP_GATHER_UNROLL;  // independent gathers per lane and round
 
 // streaming loads of the matrix arrays: read once per product, keep them out of the way
@@ -75,16 +78,16 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
       double in0 = 0.0, in1 = 0.0, in2 = 0.0;
       if (valid) {
         len = __ldg(A.rowptr + r + 1) - __ldg(A.rowptr + r);
-        if (Epi::kNumIn > 0) in0 = epi.in_ptr(0)[r];
-        if (Epi::kNumIn > 1) in1 = epi.in_ptr(1)[r];
-        if (Epi::kNumIn > 2) in2 = epi.in_ptr(2)[r];
+        // per-row operands are read once: stream them past L2 so that the gathered vector stays
+        if (Epi::kNumIn > 0) in0 = ld_stream(epi.in_ptr(0) + r);
+        if (Epi::kNumIn > 1) in1 = ld_stream(epi.in_ptr(1) + r);
+        if (Epi::kNumIn > 2) in2 = ld_stream(epi.in_ptr(2) + r);
       }
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
       int off = t.nnz_begin;  // first entry of the current position
       double s = 0.0;
-      for (int p0 = 0; p0 < maxlen; p0 += kGatherUnroll) {
-        int c[kGatherUnroll];
-        double a[kGatherUnroll], x[kGatherUnroll];
+      // one round = kGatherUnroll positions: coalesced streaming loads of this lane's columns / values
+      auto load_round = [&](int p0, int (&c)[kGatherUnroll], double (&a)[kGatherUnroll]) {
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u) {
           const bool act = len > p0 + u;
@@ -94,12 +97,41 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
           c[u] = act ? ld_stream(A.colidx + k) : -1;
           a[u] = act ? ld_stream(A.vals + k) : 0.0;
         }
+      };
+#if FOLP_PIPELINE
+      // software pipeline: the next round's stream loads are issued before this round's gathers
+      // are consumed, so a row costs one exposed stream latency instead of one per round
+      int c[kGatherUnroll], cn[kGatherUnroll];
+      double a[kGatherUnroll], an[kGatherUnroll], x[kGatherUnroll];
+      if (maxlen > 0) load_round(0, c, a);
+      for (int p0 = 0; p0 < maxlen; p0 += kGatherUnroll) {
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
+        const bool more = p0 + kGatherUnroll < maxlen;  // warp-uniform
+        if (more) load_round(p0 + kGatherUnroll, cn, an);
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u)
+          if (c[u] >= 0) s += a[u] * x[u];  // ascending column order
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < kGatherUnroll; ++u) {
+            c[u] = cn[u];
+            a[u] = an[u];
+          }
+        }
+      }
+#else
+      for (int p0 = 0; p0 < maxlen; p0 += kGatherUnroll) {
+        int c[kGatherUnroll];
+        double a[kGatherUnroll], x[kGatherUnroll];
+        load_round(p0, c, a);
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u)
           if (c[u] >= 0) s += a[u] * x[u];  // ascending column order
       }
+#endif
       if (valid) epi.row(r, s, in0, in1, in2);
     } else {
       // ---- one warp on (a chunk of) one row, plain CSR order ----
