@@ -6,6 +6,7 @@
 // decisions sp.jl:688-846, primal weight sp.jl:862-891); every vector lives in
 // HBM and every O(n), O(m), O(nnz) operation is a kernel in folp_kernels.cu.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -61,6 +62,7 @@ struct folp_handle {
   double cache[4] = {0, 0, 0, 0};
   double objective_constant = 0.0;
   SpmvMat A, At;
+  SpmvMat Q;  // CSR of the scaled objective matrix (QP only; B.has_q)
   Bufs B;
   std::vector<void*> allocs;
   // pinned host mirrors
@@ -141,17 +143,29 @@ static int dev_upload(folp_handle* h, double** p, const double* src, size_t coun
   return FOLP_OK;
 }
 
-// Cuts the rows into warp-sized work items (see folp_internal.cuh), stores the nonzeros of
-// narrow groups position-major, and uploads the arrays.
-static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
-                        const std::vector<int>& rowptr, std::vector<int>& colidx,
-                        std::vector<double>& vals) {
-  M->rows = rows;
-  M->cols = cols;
-  M->nnz = rowptr[rows];
+// Host half of the matrix set-up: cuts the rows into warp-sized work items (see
+// folp_internal.cuh) and rewrites colidx / vals so that narrow groups are position-major.
+// Pure host code (no CUDA call), also reachable through folp_debug_host_spmv.
+struct PackedMatrix {
   std::vector<Tile> tiles;
-  tiles.reserve(static_cast<size_t>(rows) / 32 + 16);
+  std::vector<int> rowid;  // slot -> row; identity outside sorted windows
+  bool any_sorted = false;
   int nlong = 0, nchunks_total = 0;
+};
+static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<int>& colidx,
+                        std::vector<double>& vals, PackedMatrix* out) {
+  std::vector<Tile>& tiles = out->tiles;
+  std::vector<int>& rowid = out->rowid;
+  bool& any_sorted = out->any_sorted;
+  int& nlong = out->nlong;
+  int& nchunks_total = out->nchunks_total;
+  tiles.reserve(static_cast<size_t>(rows) / 32 + 16);
+  struct Window { int first_tile, w0, w1, sorted; };
+  std::vector<Window> windows;
+  rowid.resize(static_cast<size_t>(rows));
+  for (int q = 0; q < rows; ++q) rowid[q] = q;
+  const bool sort_rows = getenv("FOLP_NO_ROW_SORT") == nullptr;
+  constexpr int kGatherUnrollHost = 4;  // = FOLP_GATHER_UNROLL of folp_spmv.cuh
   int r = 0;
   while (r < rows) {
     const int len = rowptr[r + 1] - rowptr[r];
@@ -171,44 +185,102 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
       r += 1;
       continue;
     }
-    Tile t{};
-    t.row_begin = r;
-    t.nnz_begin = rowptr[r];
     if (len > kNarrowMax) {  // wide row: one warp
+      Tile t{};
+      t.row_begin = r;
+      t.nnz_begin = rowptr[r];
       t.nnz_end = rowptr[r + 1];
       t.rows_kind = (kTileWarpPerRow << 16) | 1;
       tiles.push_back(t);
       r += 1;
       continue;
     }
-    const int g0 = r;
-    while (r < rows && r - g0 < 32 && rowptr[r + 1] - rowptr[r] <= kNarrowMax) r += 1;
-    const int g1 = r;
-    t.nnz_end = rowptr[g1];
-    t.rows_kind = (kTileThreadPerRow << 16) | (g1 - g0);
-    tiles.push_back(t);
+    // a run of consecutive narrow rows, cut into windows of kSortWindow rows
+    const int run0 = r;
+    while (r < rows && rowptr[r + 1] - rowptr[r] <= kNarrowMax) r += 1;
+    for (int w0 = run0; w0 < r; w0 += kSortWindow) {
+      const int w1 = std::min(r, w0 + kSortWindow);
+      windows.push_back(Window{static_cast<int>(tiles.size()), w0, w1, 0});
+      // rounds of kGatherUnroll positions the warps spend on this window, identity vs sorted order
+      auto rounds = [&](const int* ids) {
+        int total = 0;
+        for (int g = w0; g < w1; g += 32) {
+          int mx = 0;
+          for (int q = g; q < std::min(w1, g + 32); ++q) {
+            const int row = ids ? ids[q - w0] : q;
+            mx = std::max(mx, rowptr[row + 1] - rowptr[row]);
+          }
+          total += (mx + kGatherUnrollHost - 1) / kGatherUnrollHost;
+        }
+        return total;
+      };
+      // stable counting sort of the window's rows by decreasing length (lengths <= kNarrowMax)
+      int ids[kSortWindow], start[kNarrowMax + 2] = {0};
+      for (int q = w0; q < w1; ++q) start[kNarrowMax - (rowptr[q + 1] - rowptr[q]) + 1] += 1;
+      for (int b = 0; b <= kNarrowMax; ++b) start[b + 1] += start[b];
+      for (int q = w0; q < w1; ++q) ids[start[kNarrowMax - (rowptr[q + 1] - rowptr[q])]++] = q;
+      const bool sorted = sort_rows && 8 * rounds(ids) <= 7 * rounds(nullptr);
+      windows.back().sorted = sorted ? 1 : 0;
+      if (sorted) {
+        any_sorted = true;
+        for (int q = w0; q < w1; ++q) rowid[q] = ids[q - w0];
+      }
+      int k = rowptr[w0];
+      for (int g = w0; g < w1; g += 32) {
+        const int cnt = std::min(w1, g + 32) - g;
+        Tile t{};
+        t.row_begin = g;  // first row, or first slot of rowid
+        t.nnz_begin = k;
+        for (int q = g; q < g + cnt; ++q) k += rowptr[rowid[q] + 1] - rowptr[rowid[q]];
+        t.nnz_end = k;
+        t.rows_kind = ((sorted ? kTileThreadPerRowSorted : kTileThreadPerRow) << 16) | cnt;
+        tiles.push_back(t);
+      }
+    }
   }
-  // position-major inside every narrow group (each row keeps its own order); groups are independent
-  parallel_for(0, static_cast<int64_t>(tiles.size()), 1 << 12, [&](int64_t lo, int64_t hi, int) {
+  // position-major inside every narrow group (each row keeps its own order). A window's groups
+  // permute the window's own range [rowptr[w0], rowptr[w1]); windows are independent.
+  parallel_for(0, static_cast<int64_t>(windows.size()), 1 << 9, [&](int64_t lo, int64_t hi, int) {
     std::vector<int> tc;
     std::vector<double> tv;
-    for (int64_t ti = lo; ti < hi; ++ti) {
-      const Tile& t = tiles[ti];
-      if ((t.rows_kind >> 16) != kTileThreadPerRow) continue;
-      const int g0 = t.row_begin, g1 = g0 + (t.rows_kind & 0xffff);
-      const int kb = rowptr[g0], ke = rowptr[g1];
+    for (int64_t wi = lo; wi < hi; ++wi) {
+      const Window& w = windows[wi];
+      const int kb = rowptr[w.w0], ke = rowptr[w.w1];
       tc.assign(colidx.begin() + kb, colidx.begin() + ke);
       tv.assign(vals.begin() + kb, vals.begin() + ke);
       int out = kb;
-      for (int pos = 0; out < ke; ++pos)
-        for (int q = g0; q < g1; ++q)
-          if (rowptr[q + 1] - rowptr[q] > pos) {
-            colidx[out] = tc[rowptr[q] - kb + pos];
-            vals[out] = tv[rowptr[q] - kb + pos];
-            ++out;
+      for (int g = w.w0; g < w.w1; g += 32) {
+        const int g1 = std::min(w.w1, g + 32);
+        int left = 0;
+        for (int q = g; q < g1; ++q) left += rowptr[rowid[q] + 1] - rowptr[rowid[q]];
+        for (int pos = 0; left > 0; ++pos)
+          for (int q = g; q < g1; ++q) {
+            const int row = rowid[q];
+            if (rowptr[row + 1] - rowptr[row] > pos) {
+              colidx[out] = tc[rowptr[row] - kb + pos];
+              vals[out] = tv[rowptr[row] - kb + pos];
+              ++out;
+              --left;
+            }
           }
+      }
     }
   });
+}
+
+// Uploads a packed matrix.
+static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
+                        const std::vector<int>& rowptr, std::vector<int>& colidx,
+                        std::vector<double>& vals) {
+  M->rows = rows;
+  M->cols = cols;
+  M->nnz = rowptr[rows];
+  PackedMatrix pk;
+  pack_matrix(rows, rowptr, colidx, vals, &pk);
+  const std::vector<Tile>& tiles = pk.tiles;
+  const std::vector<int>& rowid = pk.rowid;
+  const bool any_sorted = pk.any_sorted;
+  const int nlong = pk.nlong, nchunks_total = pk.nchunks_total;
   M->ntiles = static_cast<int>(tiles.size());
   M->nlong = nlong;
   const size_t pad = 16;
@@ -217,6 +289,11 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
   if ((rc = dev_alloc(h, &M->colidx, static_cast<size_t>(M->nnz) + pad))) return rc;
   if ((rc = dev_alloc(h, &M->vals, static_cast<size_t>(M->nnz) + pad))) return rc;
   if ((rc = dev_alloc(h, &M->tiles, tiles.size()))) return rc;
+  if (any_sorted) {
+    if ((rc = dev_alloc(h, &M->rowid, static_cast<size_t>(rows)))) return rc;
+    TRY(cudaMemcpyAsync(M->rowid, rowid.data(), static_cast<size_t>(rows) * sizeof(int),
+                        cudaMemcpyHostToDevice, h->stream));
+  }
   if ((rc = dev_alloc(h, &M->long_partials, static_cast<size_t>(nchunks_total)))) return rc;
   if ((rc = dev_alloc(h, &M->long_tickets, static_cast<size_t>(nlong)))) return rc;
   TRY(cudaMemsetAsync(M->colidx, 0, (static_cast<size_t>(M->nnz) + pad) * sizeof(int), h->stream));
@@ -395,8 +472,24 @@ static int setup_peer_exchange(folp_handle* h) {
 // ---------------------------------------------------------------------------
 // folp_create
 // ---------------------------------------------------------------------------
+// FOLP_TIMING=1: wall-clock phases of folp_create on stderr (development aid)
+struct PhaseTimer {
+  bool on = getenv("FOLP_TIMING") != nullptr;
+  double t0 = now_sec(), last = t0;
+  void mark(const char* what) {
+    if (!on) return;
+    const double t = now_sec();
+    fprintf(stderr, "[folp_create] %-28s %8.2f ms\n", what, (t - last) * 1e3);
+    last = t;
+  }
+  void total() {
+    if (on) fprintf(stderr, "[folp_create] %-28s %8.2f ms\n", "TOTAL", (now_sec() - t0) * 1e3);
+  }
+};
+
 static int create_impl(folp_handle* h, const folp_problem* p, const folp_params* q,
                        const folp_dist* dist) {
+  PhaseTimer pt;
   const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
   if (n < 0 || m < 0 || nnz < 0 || p->num_equalities < 0 || p->num_equalities > m ||
       (p->index_base != 0 && p->index_base != 1)) {
@@ -416,11 +509,21 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     h->err = "per-GPU shard exceeds 32-bit indexing (n+m or nnz >= 2^31)";
     return FOLP_UNSUPPORTED;
   }
-  for (int64_t k = 0; k < p->q_num_nonzeros; ++k)
-    if (p->q_nzval && p->q_nzval[k] != 0.0) {
-      h->err = "quadratic objectives are not supported by the B200 path yet (LP only)";
-      return FOLP_UNSUPPORTED;
-    }
+  bool has_q = false;  // is_linear_programming_problem, quadratic_programming.jl: iszero(Q)
+  for (int64_t k = 0; k < p->q_num_nonzeros && !has_q; ++k)
+    if (p->q_nzval && p->q_nzval[k] != 0.0) has_q = true;
+  if (has_q && (!p->q_colptr || !p->q_rowval)) {
+    h->err = "null objective-matrix arrays";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  if (has_q && q->step_size_policy == FOLP_STEP_MALITSKY_POCK) {  // pdhg.jl:560-565
+    h->err = "the Malitsky-Pock step size policy supports linear programs only";
+    return FOLP_UNSUPPORTED;
+  }
+  if (has_q && dist && dist->world_size > 1) {
+    h->err = "quadratic objectives are not supported in partitioned (multi-GPU) mode";
+    return FOLP_UNSUPPORTED;
+  }
   if (q->termination_evaluation_frequency < 1) {
     h->err = "termination_evaluation_frequency must be >= 1";
     return FOLP_INVALID_ARGUMENT;
@@ -476,6 +579,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     NCCL_TRY(h->nccl->CommInitRank(&h->comm, h->world, id, h->rank));
   }
 
+  pt.mark("device, stream, pinned state");
   // ---- matrices: A' in CSR is the caller's CSC; A in CSR by counting sort ----
   const int base = p->index_base;
   const int P = h->world;
@@ -499,6 +603,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         h->err = "colptr is not monotone";
         return FOLP_INVALID_ARGUMENT;
       }
+    pt.mark("index conversion");
     // transpose
     std::vector<int> rp2(static_cast<size_t>(m) + 1, 0), ci2(static_cast<size_t>(nnz));
     std::vector<double> v2(static_cast<size_t>(nnz));
@@ -553,6 +658,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         });
       for (auto& x : th) x.join();
     }
+    pt.mark("transpose");
     int rc;
     if (P == 1) {
       h->row_begin[1] = m;
@@ -602,8 +708,42 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     }
   }
 
+  pt.mark("pack + upload matrices");
+  // ---- objective matrix: CSR of Q by a stable counting sort of the caller's CSC ----
+  if (has_q) {
+    const int64_t qnnz = p->q_num_nonzeros;
+    if (qnnz >= (int64_t{1} << 31) - 64) {
+      h->err = "objective matrix exceeds 32-bit indexing";
+      return FOLP_UNSUPPORTED;
+    }
+    std::vector<int> qrp(static_cast<size_t>(n) + 1, 0), qci(static_cast<size_t>(qnnz));
+    std::vector<double> qv(static_cast<size_t>(qnnz));
+    for (int64_t j = 0; j < n; ++j)
+      if (p->q_colptr[j] > p->q_colptr[j + 1] || p->q_colptr[j] - base < 0 ||
+          p->q_colptr[j + 1] - base > qnnz) {
+        h->err = "objective-matrix colptr is not monotone";
+        return FOLP_INVALID_ARGUMENT;
+      }
+    for (int64_t k = 0; k < qnnz; ++k) {
+      const int64_t r = p->q_rowval[k] - base;
+      if (r < 0 || r >= n) { h->err = "objective-matrix row index out of range"; return FOLP_INVALID_ARGUMENT; }
+      qrp[r + 1] += 1;
+    }
+    for (int64_t i = 0; i < n; ++i) qrp[i + 1] += qrp[i];
+    std::vector<int> cursor(qrp.begin(), qrp.end() - 1);
+    for (int64_t j = 0; j < n; ++j)
+      for (int64_t k = p->q_colptr[j] - base; k < p->q_colptr[j + 1] - base; ++k) {
+        const int pos = cursor[p->q_rowval[k] - base]++;
+        qci[pos] = static_cast<int>(j);
+        qv[pos] = p->q_nzval[k];
+      }
+    int rcq;
+    if ((rcq = build_matrix(h, &h->Q, static_cast<int>(n), static_cast<int>(n), qrp, qci, qv))) return rcq;
+  }
+
   // ---- vectors: primal-indexed arrays hold the local slice, dual-indexed arrays the local rows ----
   Bufs& B = h->B;
+  B.has_q = has_q ? 1 : 0;
   const int64_t nl = h->n, ml = h->m;            // local lengths
   const int64_t na = std::max(h->n_pad, nl);     // allocation lengths (exchange strides)
   const int64_t ma = std::max(h->m_pad, ml);
@@ -676,6 +816,13 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
                        at(p->orig_right_hand_side ? p->orig_right_hand_side : p->right_hand_side, r0),
                        ml, 0.0)))
     return rc;
+  if (has_q) {
+    for (int k = 0; k < 2; ++k)
+      if ((rc = dev_zeros(h, &B.qx[k], na))) return rc;
+    if ((rc = dev_zeros(h, &B.dxv, na))) return rc;
+    if ((rc = dev_zeros(h, &B.qx_avg, na))) return rc;
+    if ((rc = dev_zeros(h, &B.last_qx, na))) return rc;
+  }
   if ((rc = dev_zeros(h, &B.tr_t, std::max(nl + ml, P > 1 ? P * std::max(na, ma) : n + m)))) return rc;
   if ((rc = dev_zeros(h, &B.tr_d, std::max(nl + ml, n + m)))) return rc;
   if ((rc = dev_zeros(h, &B.part, static_cast<size_t>(kNumSlots) * kMaxScalars * kMaxPartialBlocks)))
@@ -685,6 +832,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   TRY(cudaMemsetAsync(B.counters, 0, 8 * sizeof(unsigned), h->stream));
   if ((rc = dev_alloc(h, &h->d_trs, 1))) return rc;
 
+  pt.mark("vectors");
   // ---- PdhgSolverState scalars, pdhg.jl:805-819 ----
   DevState s;
   memset(&s, 0, sizeof(s));
@@ -705,6 +853,8 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   if ((rc = push_state(h))) return rc;
   TRY(cudaStreamSynchronize(h->stream));
   h->start_time = now_sec();
+  pt.mark("state");
+  pt.total();
   return FOLP_OK;
 }
 
@@ -736,7 +886,14 @@ extern "C" int folp_create(const folp_problem* problem, const folp_params* param
   return FOLP_OK;
 }
 
-extern "C" void folp_destroy(folp_handle* h) { free_handle(h); }
+extern "C" void folp_destroy(folp_handle* h) {
+  if (h && getenv("FOLP_TIMING"))
+    fprintf(stderr, "[folp_destroy] iterations %lld, launches %lld, trust-region solves %lld, passes %lld, "
+                    "take_step seconds %.4f\n",
+            static_cast<long long>(h->hs ? h->hs->iterations : 0), static_cast<long long>(h->launches),
+            static_cast<long long>(h->tr_solves), static_cast<long long>(h->tr_passes), h->basic_time);
+  free_handle(h);
+}
 
 extern "C" const char* folp_last_error(const folp_handle* h) {
   return h ? h->err.c_str() : g_create_error.c_str();
@@ -892,7 +1049,7 @@ static int fetch_rows(folp_handle* h, const double* rows, double* host_out) {
 // ---------------------------------------------------------------------------
 static int launch_attempts_any(folp_handle* h, int attempts) {
   if (h->world == 1) {
-    launch_step_attempts(h->B, h->A, h->At, attempts, h->stream);
+    launch_step_attempts(h->B, h->A, h->At, h->Q, attempts, h->stream);
     return FOLP_OK;
   }
   const Bufs& B = h->B;
@@ -935,7 +1092,7 @@ static int enqueue_attempts(folp_handle* h, int attempts) {
     }
     TRY(cudaGraphLaunch(it->second, h->stream));
   }
-  h->launches += (h->world == 1 ? 3 : 4) * static_cast<int64_t>(attempts);
+  h->launches += (h->world == 1 ? (h->B.has_q ? 5 : 3) : 4) * static_cast<int64_t>(attempts);
   return FOLP_OK;
 }
 
@@ -1030,14 +1187,14 @@ static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
 // bound_optimal_objective (tr.jl:271-360), EUCLIDEAN_NORM, at a point whose
 // products A*x and A'*y are already in HBM.
 static int euclidean_gap(folp_handle* h, const double* px, const double* atp, const double* py,
-                         const double* axp, double wp, double wd, double radius,
+                         const double* axp, const double* qxp, double wp, double wd, double radius,
                          BoundResult* out) {
   TrProblem P{px, atp, py, axp, wp, wd, radius, 1, 1,
-              h->prm.use_approximate_localized_duality_gap};
+              h->prm.use_approximate_localized_duality_gap, h->B.has_q ? qxp : nullptr};
   TrState t;
   int rc = tr_solve(h, P, &t);
   if (rc) return rc;
-  out->lagrangian_value = ((0.0 + t.cx) - t.x_aty) + t.y_b + h->objective_constant;
+  out->lagrangian_value = ((0.5 * t.xqx + t.cx) - t.x_aty) + t.y_b + h->objective_constant;
   out->lower_bound_value = out->lagrangian_value + t.v_primal;
   out->upper_bound_value = out->lagrangian_value - t.v_dual;
   return FOLP_OK;
@@ -1111,12 +1268,13 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
     const double d_avg = sqrt(avg_px * avg_px + avg_dy * avg_dy);
     const double d_cur = sqrt(cur_px * cur_px + cur_dy * cur_dy);
     BoundResult g_avg, g_cur;
-    if ((rc = euclidean_gap(h, B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, d_avg, &g_avg)))
+    if ((rc = euclidean_gap(h, B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, B.qx_avg, wp, wd, d_avg,
+                            &g_avg)))
       return rc;
     if ((rc = spmv_A(h, B.x[s->cur], B.ax_cur))) return rc;
     have_ax_cur = 1;
-    if ((rc = euclidean_gap(h, B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, d_cur,
-                            &g_cur)))
+    if ((rc = euclidean_gap(h, B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, B.qx[s->cur], wp,
+                            wd, d_cur, &g_cur)))
       return rc;
     // should_reset_to_average, sp.jl:530-547
     const double cur_ng = get_gap(g_cur) / d_cur, avg_ng = get_gap(g_avg) / d_avg;
@@ -1135,8 +1293,8 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
     if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) {  // sp.jl:549-593
       const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);
       BoundResult g_last;
-      if ((rc = euclidean_gap(h, B.last_x, B.last_aty, B.last_y, B.last_ax, wp, wd, d_last,
-                              &g_last)))
+      if ((rc = euclidean_gap(h, B.last_x, B.last_aty, B.last_y, B.last_ax, B.last_qx, wp, wd,
+                              d_last, &g_last)))
         return rc;
       const double ncg = get_gap(candidate_gap) / candidate_distance;
       const double nlg = get_gap(g_last) / d_last;
@@ -1200,6 +1358,10 @@ static int evaluate(folp_handle* h, folp_eval* out) {
   launch_make_avg(B, use_current, h->stream);
   if ((rc = spmv_A(h, B.avg_x, B.ax_avg))) return rc;
   if ((rc = spmv_At(h, B.avg_y, B.aty_avg))) return rc;
+  if (B.has_q) {  // Q * avg_x: objective values, primal gradient, Lagrangian, ray norm
+    launch_spmv_plain(h->Q, B.avg_x, B.qx_avg, B.grid_spmv, h->stream);
+    h->launches += 1;
+  }
   launch_stats_n(B, B.red, h->stream);
   launch_stats_m(B, B.red + kMaxScalars, h->stream);
   CHECK_LAUNCH();
@@ -1232,14 +1394,15 @@ static int evaluate(folp_handle* h, folp_eval* out) {
   const double eps_ratio = prm->eps_optimal_absolute / prm->eps_optimal_relative;
   const double c0 = h->objective_constant;
   // compute_convergence_information, isu.jl:228-280
-  e.primal_objective = c0 + sn[SN_cx] + 0.0;
+  const double xqx = B.has_q ? sn[SN_xqx] : 0.0;  // xhat' Q_O xhat
+  e.primal_objective = c0 + sn[SN_cx] + 0.5 * xqx;  // isu.jl:67-74
   e.l_inf_primal_residual = jl_max(jl_max(sm[SM_pres_max], sn[SN_lviol_max]), sn[SN_uviol_max]);
   e.l2_primal_residual = sqrt(sm[SM_pres2] + sn[SN_lviol2] + sn[SN_uviol2]);
   e.relative_l_inf_primal_residual = e.l_inf_primal_residual / (eps_ratio + h->cache[1]);
   e.relative_l2_primal_residual = e.l2_primal_residual / (eps_ratio + h->cache[3]);
   e.l_inf_primal_variable = sn[SN_x_max];
   e.l2_primal_variable = sqrt(sn[SN_x2]);
-  e.dual_objective = (sm[SM_by] + c0 - 0.0) + sn[SN_rcobj];
+  e.dual_objective = (sm[SM_by] + c0 - 0.5 * xqx) + sn[SN_rcobj];  // isu.jl:186-190
   e.l_inf_dual_residual = jl_max(sm[SM_yneg_max], sn[SN_dres_max]);
   e.l2_dual_residual = sqrt(sm[SM_yneg2] + sn[SN_dres2]);
   e.relative_l_inf_dual_residual = e.l_inf_dual_residual / (eps_ratio + h->cache[0]);
@@ -1259,7 +1422,7 @@ static int evaluate(folp_handle* h, folp_eval* out) {
     e.max_primal_ray_infeasibility =
         jl_max(jl_max(sm[SM_ray_act_max], sn[SN_ray_l_max]), sn[SN_ray_u_max]) / inv;
     e.primal_ray_linear_objective = sn[SN_cx] / inv;
-    e.primal_ray_quadratic_norm = 0.0;
+    e.primal_ray_quadratic_norm = B.has_q ? sn[SN_qx_max] / inv : 0.0;  // isu.jl:311-313
     const double dobj = sm[SM_by] + sn[SN_ray_rcobj];
     const double sf = jl_max(sm[SM_y_max], sn[SN_ray_rc_max]);
     if (sf != 0.0) {
@@ -1277,9 +1440,10 @@ static int evaluate(folp_handle* h, folp_eval* out) {
   {  // update_objective_bound_estimates, sp.jl:1015-1047
     const double rp_ = jl_max(1e-8, sqrt(wp * sn[SN_xs2]));
     const double rd_ = jl_max(1e-8, sqrt(wd * sm[SM_ys2]));
-    const double L = ((0.0 + sn[SN_cs_x]) - sn[SN_x_aty]) + sm[SM_bs_y] + c0;
+    const double L = ((0.5 * (B.has_q ? sn[SN_xs_qxs] : 0.0) + sn[SN_cs_x]) - sn[SN_x_aty]) +
+                     sm[SM_bs_y] + c0;  // sp.jl:1109-1120
     TrProblem Pp{B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp / (rp_ * rp_), wd / (rd_ * rd_), 1.0,
-                 1, 0, 0};
+                 1, 0, 0, B.has_q ? B.qx_avg : nullptr};
     TrProblem Pd = Pp;
     Pd.use_primal = 0; Pd.use_dual = 1;
     TrState tp, td;
@@ -1478,9 +1642,14 @@ extern "C" int folp_debug_set_state(folp_handle* h, const double* x, const doubl
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   Bufs& B = h->B;
-  if (x && B.n)
+  if (x && B.n) {
     TRY(cudaMemcpyAsync(B.x[s->cur], x + h->col0, sizeof(double) * B.n, cudaMemcpyHostToDevice,
                         h->stream));
+    if (B.has_q) {
+      launch_spmv_plain(h->Q, B.x[s->cur], B.qx[s->cur], B.grid_spmv, h->stream);
+      h->launches += 1;
+    }
+  }
   if (y) {
     if (B.m)
       TRY(cudaMemcpyAsync(B.y[s->cur], y + h->row0, sizeof(double) * B.m, cudaMemcpyHostToDevice,
@@ -1536,7 +1705,7 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
   for (int64_t a = 0; a < attempts; ++a) {
     cudaEvent_t* e = ev.data() + (nk + 1) * a;
     if (h->world == 1) {
-      launch_step_attempt_timed(h->B, h->A, h->At, e, h->stream);
+      launch_step_attempt_timed(h->B, h->A, h->At, h->Q, e, h->stream);
       continue;
     }
     const Bufs& B = h->B;
@@ -1560,7 +1729,7 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
     TRY(cudaEventRecord(e[4], h->stream));
   }
   CHECK_LAUNCH();
-  h->launches += nk * attempts;
+  h->launches += (nk + (h->B.has_q ? 2 : 0)) * attempts;
   if ((rc = pull_state(h))) return rc;
   for (int k = 0; k < 8; ++k) ms_out[k] = 0.0;
   for (int64_t a = 0; a < attempts; ++a)
@@ -1593,6 +1762,89 @@ extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, dou
   float ms = 0.f;
   TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   *ms_out = ms / reps;
+  return FOLP_OK;
+}
+
+// Host emulation of k_spmv's traversal of a packed matrix (test hook, no CUDA call): packs the
+// CSR matrix exactly as folp_create does and walks the work items lane by lane with the
+// kernel's slot arithmetic (ballot + popcounts), so that the packing can be checked on a
+// machine without a GPU. y = A * x; stats = {tiles, sorted groups, narrow rounds, long rows}.
+extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr,
+                                    const int64_t* colidx, const double* vals, const double* x,
+                                    double* y, int64_t* stats) {
+  if (rows < 0 || cols < 0 || !rowptr || !y || (rowptr[rows] > 0 && (!colidx || !vals || !x)))
+    return FOLP_INVALID_ARGUMENT;
+  const int64_t nnz = rowptr[rows];
+  if (rows + cols >= (int64_t{1} << 31) - 64 || nnz >= (int64_t{1} << 31) - 64) return FOLP_UNSUPPORTED;
+  std::vector<int> rp(static_cast<size_t>(rows) + 1), ci(static_cast<size_t>(nnz));
+  std::vector<double> v(vals, vals + nnz);
+  for (int64_t i = 0; i <= rows; ++i) rp[i] = static_cast<int>(rowptr[i]);
+  for (int64_t k = 0; k < nnz; ++k) {
+    if (colidx[k] < 0 || colidx[k] >= cols) return FOLP_INVALID_ARGUMENT;
+    ci[k] = static_cast<int>(colidx[k]);
+  }
+  PackedMatrix pk;
+  pack_matrix(static_cast<int>(rows), rp, ci, v, &pk);
+  int64_t n_sorted = 0, n_rounds = 0;
+  std::vector<double> partial(static_cast<size_t>(std::max(pk.nchunks_total, 1)), 0.0);
+  for (int64_t i = 0; i < rows; ++i) y[i] = 0.0;  // empty rows are covered by narrow groups too
+  for (const Tile& t : pk.tiles) {
+    const int kind = t.rows_kind >> 16, cnt = t.rows_kind & 0xffff;
+    if (kind == kTileThreadPerRow || kind == kTileThreadPerRowSorted) {
+      n_sorted += kind == kTileThreadPerRowSorted;
+      int row[32], len[32];
+      double s[32];
+      int maxlen = 0;
+      for (int lane = 0; lane < 32; ++lane) {
+        row[lane] = -1; len[lane] = 0; s[lane] = 0.0;
+        if (lane < cnt) {
+          row[lane] = kind == kTileThreadPerRowSorted ? pk.rowid[t.row_begin + lane] : t.row_begin + lane;
+          len[lane] = rp[row[lane] + 1] - rp[row[lane]];
+          maxlen = std::max(maxlen, len[lane]);
+        }
+      }
+      int off = t.nnz_begin;
+      for (int p = 0; p < maxlen; ++p) {
+        unsigned m = 0;
+        for (int lane = 0; lane < 32; ++lane)
+          if (len[lane] > p) m |= 1u << lane;
+        for (int lane = 0; lane < 32; ++lane)
+          if (len[lane] > p) {
+            const int k = off + __builtin_popcount(m & ((1u << lane) - 1u));
+            s[lane] += v[k] * x[ci[k]];
+          }
+        off += __builtin_popcount(m);
+      }
+      if (off != t.nnz_end) return FOLP_INVALID_ARGUMENT;  // the group's range is exactly consumed
+      n_rounds += (maxlen + 3) / 4;
+      for (int lane = 0; lane < cnt; ++lane) y[row[lane]] = s[lane];
+    } else {
+      double lane_sum[32] = {0.0};
+      for (int k = t.nnz_begin; k < t.nnz_end; ++k) lane_sum[(k - t.nnz_begin) & 31] += v[k] * x[ci[k]];
+      auto tree = [](double* a) {  // warp_sum's xor-shuffle tree
+        for (int o = 16; o > 0; o >>= 1)
+          for (int l = 0; l < o; ++l) a[l] += a[l + o];  // lane l of the next level; same pairing as xor
+        return a[0];
+      };
+      const double sum = tree(lane_sum);
+      if (kind == kTileWarpPerRow) {
+        y[t.row_begin] = sum;
+      } else {
+        partial[t.chunk_first + t.chunk_index] = sum;
+        if (t.chunk_index == t.chunk_count - 1) {
+          double ls[32] = {0.0};
+          for (int q = 0; q < t.chunk_count; ++q) ls[q & 31] += partial[t.chunk_first + q];
+          y[t.row_begin] = tree(ls);
+        }
+      }
+    }
+  }
+  if (stats) {
+    stats[0] = static_cast<int64_t>(pk.tiles.size());
+    stats[1] = n_sorted;
+    stats[2] = n_rounds;
+    stats[3] = pk.nlong;
+  }
   return FOLP_OK;
 }
 

@@ -60,6 +60,12 @@ struct DevState {
 //                 CONSECUTIVE values / column indices (the slot of lane l at position p is
 //                 base + #entries of earlier positions + #lanes < l that reach p: a ballot
 //                 and two popcounts) -- fully coalesced loads with no staging.
+//   sorted group  the same, but its rows were picked from a window of kSortWindow consecutive
+//                 narrow rows in order of decreasing length (rowid[slot] names the row of
+//                 a slot), so that the 32 lanes of a warp run out of nonzeros together.
+//                 Only windows where that saves rounds are sorted (columns of a random
+//                 matrix, power-law degrees); the others keep the identity order and never
+//                 read rowid. A row's own nonzeros keep their ascending column order.
 //   wide row      one row of 33 .. kChunkNnz nonzeros, plain CSR order, one warp.
 //   long chunk    kChunkNnz nonzeros of a longer row; the partial sums are combined in
 //                 chunk order by the last chunk to finish (deterministic).
@@ -76,11 +82,13 @@ constexpr int kSpmvWarps = kSpmvThreads / 32;
 constexpr int kSpmvCtasPerSm = FOLP_SPMV_CTAS_PER_SM;
 constexpr int kNarrowMax = 32;              // rows up to this length are "narrow"
 constexpr int kTilePad = 8;                 // slack behind the arrays
-enum TileKind : int { kTileThreadPerRow = 0, kTileWarpPerRow = 1, kTileLongChunk = 2 };
+constexpr int kSortWindow = 256;            // rows per length-sorted window = the 8 groups a CTA works on together
+enum TileKind : int { kTileThreadPerRow = 0, kTileWarpPerRow = 1, kTileLongChunk = 2,
+                      kTileThreadPerRowSorted = 3 };
 
 struct Tile {
   // hot half: one 16-byte load gives a role everything it needs for the common kinds
-  int row_begin;           // first row (long chunk: the single row)
+  int row_begin;           // first row (long chunk: the single row; sorted group: first slot of rowid)
   int nnz_begin, nnz_end;  // nonzeros [nnz_begin,nnz_end)
   int rows_kind;           // (kind << 16) | number of rows
   // long rows only
@@ -95,6 +103,7 @@ struct SpmvMat {
   int rows = 0, cols = 0;
   int64_t nnz = 0;
   int* rowptr = nullptr;     // rows+1 (device)
+  int* rowid = nullptr;      // rows: slot -> row inside length-sorted windows (nullptr: no sorted group)
   int* colidx = nullptr;     // nnz + pad
   double* vals = nullptr;    // nnz + pad
   Tile* tiles = nullptr;

@@ -101,18 +101,19 @@ __device__ __forceinline__ void attempt_params(const DevState& s, double& trial,
 // One element of K1. Returns dx; writes x+ / xbar / sum_x through the references.
 struct PrimalCtx {
   double f, theta, w, w_old;
-  bool do_primal, pend, pend_old;
+  bool do_primal, pend, pend_old, has_q;
 };
+// qx = (Q * x)_j, read only when k.has_q
 __device__ __forceinline__ double primal_elem(const PrimalCtx& k, double x, double& xn, double c,
                                               double at, double l, double u, double& sx,
-                                              double& xbar) {
+                                              double& xbar, double qx = 0.0) {
   if (k.pend || k.pend_old) {  // deferred add_to_primal_solution_weighted_average (sp.jl:252-263)
     if (k.pend_old) sx += xn * k.w_old;  // xn still holds the previous iterate (pdhg.jl:621-627)
     if (k.pend) sx += x * k.w;
   }
   double xp;
   if (k.do_primal) {
-    const double g = c - at;  // sp.jl:1093-1100 with Q = 0
+    const double g = k.has_q ? (qx + c) - at : c - at;  // sp.jl:1093-1100
     xp = x - k.f * g;
     xp = fmin(u, fmax(l, xp));  // sp.jl:82-93
     xn = xp;
@@ -141,10 +142,12 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   k.pend_old = (s.pending_avg & 2) != 0;
   k.w = s.pending_w;
   k.w_old = s.mp_old_step;
+  k.has_q = B.has_q != 0;
   const int cur = s.cur;
   const double* __restrict__ xc = sel(B.x, cur);
   double* __restrict__ xn = sel(B.x, cur ^ 1);
   const double* __restrict__ at = sel(B.aty, cur);
+  const double* __restrict__ qxc = sel(B.qx, cur);
   const bool avg = k.pend || k.pend_old;
   const bool rd_xn = k.pend_old || !k.do_primal;
   double acc = 0.0;
@@ -162,8 +165,10 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     double2 sx = avg ? __ldcs(reinterpret_cast<const double2*>(B.sum_x) + j) : make_double2(0.0, 0.0);
     double2 xp = rd_xn ? reinterpret_cast<const double2*>(xn)[j] : make_double2(0.0, 0.0);
     double2 xb;
-    const double d0 = primal_elem(k, x.x, xp.x, c.x, a.x, l.x, u.x, sx.x, xb.x);
-    const double d1 = primal_elem(k, x.y, xp.y, c.y, a.y, l.y, u.y, sx.y, xb.y);
+    const double2 q = k.has_q ? reinterpret_cast<const double2*>(qxc)[j] : make_double2(0.0, 0.0);
+    const double d0 = primal_elem(k, x.x, xp.x, c.x, a.x, l.x, u.x, sx.x, xb.x, q.x);
+    const double d1 = primal_elem(k, x.y, xp.y, c.y, a.y, l.y, u.y, sx.y, xb.y, q.y);
+    if (k.has_q) reinterpret_cast<double2*>(B.dxv)[j] = make_double2(d0, d1);
     if (avg) __stcs(reinterpret_cast<double2*>(B.sum_x) + j, sx);
     if (k.do_primal) reinterpret_cast<double2*>(xn)[j] = xp;
     reinterpret_cast<double2*>(B.xbar + B.xbar_off)[j] = xb;
@@ -178,7 +183,9 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   if ((B.n & 1) && t0 == 0) {
     const int j = B.n - 1;
     double sx = avg ? B.sum_x[j] : 0.0, xp = rd_xn ? xn[j] : 0.0, xb;
-    const double d = primal_elem(k, xc[j], xp, B.c[j], at[j], B.l[j], B.u[j], sx, xb);
+    const double d = primal_elem(k, xc[j], xp, B.c[j], at[j], B.l[j], B.u[j], sx, xb,
+                                 k.has_q ? qxc[j] : 0.0);
+    if (k.has_q) B.dxv[j] = d;
     if (avg) B.sum_x[j] = sx;
     if (k.do_primal) xn[j] = xp;
     B.xbar[B.xbar_off + j] = xb;
@@ -199,7 +206,9 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
 // ---------------------------------------------------------------------------
 // scalar rule at the end of an attempt
 // ---------------------------------------------------------------------------
-__device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double dy2, double inter, double dp2) {
+// qd = dx' * Q * dx (0 for an LP)
+__device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double dy2, double inter,
+                                              double dp2, double qd) {
   DevState s = *st;
   double trial, theta;
   attempt_params(s, trial, theta);
@@ -210,7 +219,7 @@ __device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double d
     const double ndx = sqrt(dx2), ndy = sqrt(dy2);
     const double movement =
         0.5 * s.primal_weight * (ndx * ndx) + (0.5 / s.primal_weight) * (ndy * ndy);
-    const double interaction = fabs(inter);
+    const double interaction = fabs(inter) + fabs(0.5 * qd);  // pdhg.jl:536-544
     s.last_interaction = interaction;
     s.last_movement = movement;
     s.kkt_passes += 1;
@@ -342,6 +351,7 @@ struct EpiTransT {
   static constexpr int kNumIn = 3;  // x, x+, A'y
   Bufs B;
   int g_primal, g_dual;  // grids of K1 and K2 (number of partials they wrote)
+  int g_q = 0;           // grid of the dx' Q dx kernel (QP only), 0 for an LP
   const double *xc, *xn, *atc;
   double* atn;
   double inter, dp2;
@@ -380,9 +390,10 @@ struct EpiTransT {
     const double dy2 = reduce_partials<false>(part_ptr(B, kSlotDual, 0), g_dual, sh);
     const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
     const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
+    const double qd = g_q ? reduce_partials<false>(part_ptr(B, kSlotPrimal, 1), g_q, sh) : 0.0;
     if (threadIdx.x != 0) return;
     if (!DIST) {
-      finalize_attempt(B.st, dx2, dy2, it, dp);
+      finalize_attempt(B.st, dx2, dy2, it, dp, qd);
     } else if (B.p2p) {  // push the four scalars into every rank's slot for this rank, then announce
 #pragma unroll
       for (int r = 0; r < kMaxWorld; ++r)
@@ -425,8 +436,48 @@ __global__ void k_finalize_dist(Bufs B) {
   double t[4] = {0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < B.world; ++r)
     for (int k = 0; k < 4; ++k) t[k] += __ldcg(B.sc_recv + r * kScBlock + k);
-  finalize_attempt(B.st, t[0], t[1], t[2], t[3]);
+  finalize_attempt(B.st, t[0], t[1], t[2], t[3], 0.0);  // partitioned mode is LP only
 }
+
+// ---------------------------------------------------------------------------
+// quadratic objective: two products with Q (CSR) between K2 and K3 of an attempt.
+//   EpiQx    qx[next] = Q * x+          the Q*x term of the NEXT primal gradient (sp.jl:1093-1100)
+//   EpiQDot  sum_j dx_j (Q * dx)_j      the objective part of the interaction (pdhg.jl:536-541);
+//            computed from dx itself, not as a difference of products (no cancellation)
+// ---------------------------------------------------------------------------
+struct EpiQx {
+  static constexpr int kNumIn = 0;
+  Bufs B;
+  const double* in;
+  double* out;
+  __device__ bool begin() {
+    const DevState& s = *B.st;
+    if (!s.active) return false;
+    in = sel(B.x, s.cur ^ 1);
+    out = sel(B.qx, s.cur ^ 1);
+    return true;
+  }
+  __device__ const double* input() const { return in; }
+  __device__ const double* in_ptr(int) const { return nullptr; }
+  __device__ void row(int j, double s, double, double, double) { out[j] = s; }
+  __device__ void finish(double*) {}
+};
+struct EpiQDot {
+  static constexpr int kNumIn = 1;  // dx
+  Bufs B;
+  double acc;
+  __device__ bool begin() {
+    acc = 0.0;
+    return B.st->active != 0;
+  }
+  __device__ const double* input() const { return B.dxv; }
+  __device__ const double* in_ptr(int) const { return B.dxv; }
+  __device__ void row(int, double s, double dxj, double, double) { acc += dxj * s; }
+  __device__ void finish(double* sh) {
+    const double t = block_reduce<false>(acc, sh);
+    if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 1)[blockIdx.x] = t;
+  }
+};
 
 using EpiDual = EpiDualT<false>;
 using EpiTrans = EpiTransT<false>;
@@ -464,38 +515,53 @@ static int spmv_grid(const SpmvMat& A, int grid_spmv) {
   return g < 1 ? 1 : g;
 }
 
-void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, int attempts,
-                          cudaStream_t s) {
+static void launch_q_products(const Bufs& B, const SpmvMat& Q, int gq, cudaStream_t s) {
+  EpiQx ex;
+  ex.B = B;
+  EpiQDot eq;
+  eq.B = B;
+  k_spmv<EpiQx><<<gq, kSpmvThreads, 0, s>>>(Q, ex);
+  k_spmv<EpiQDot><<<gq, kSpmvThreads, 0, s>>>(Q, eq);
+}
+
+void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q,
+                          int attempts, cudaStream_t s) {
   const int g1 = B.grid_vec;
   const int g2 = spmv_grid(A, B.grid_spmv), g3 = spmv_grid(At, B.grid_spmv);
+  const int gq = B.has_q ? spmv_grid(Q, B.grid_spmv) : 0;
   EpiDual ed;
   ed.B = B;
   EpiTrans et;
   et.B = B;
   et.g_primal = g1;
   et.g_dual = g2;
+  et.g_q = gq;
   for (int a = 0; a < attempts; ++a) {
     k_primal<false><<<g1, kVecThreads, 0, s>>>(B);
     k_spmv<EpiDual><<<g2, kSpmvThreads, 0, s>>>(A, ed);
+    if (gq) launch_q_products(B, Q, gq, s);
     k_spmv<EpiTrans><<<g3, kSpmvThreads, 0, s>>>(At, et);
   }
 }
 
-void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaEvent_t* ev,
-                               cudaStream_t s) {
+void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q,
+                               cudaEvent_t* ev, cudaStream_t s) {
   const int g1 = B.grid_vec;
   const int g2 = spmv_grid(A, B.grid_spmv), g3 = spmv_grid(At, B.grid_spmv);
+  const int gq = B.has_q ? spmv_grid(Q, B.grid_spmv) : 0;
   EpiDual ed;
   ed.B = B;
   EpiTrans et;
   et.B = B;
   et.g_primal = g1;
   et.g_dual = g2;
+  et.g_q = gq;
   cudaEventRecord(ev[0], s);
   k_primal<false><<<g1, kVecThreads, 0, s>>>(B);
   cudaEventRecord(ev[1], s);
   k_spmv<EpiDual><<<g2, kSpmvThreads, 0, s>>>(A, ed);
   cudaEventRecord(ev[2], s);
+  if (gq) launch_q_products(B, Q, gq, s);  // timed with K3
   k_spmv<EpiTrans><<<g3, kSpmvThreads, 0, s>>>(At, et);
   cudaEventRecord(ev[3], s);
 }
@@ -605,14 +671,22 @@ __global__ void __launch_bounds__(kVecThreads) k_stats_n(Bufs B, double* red_out
     const double xa = B.avg_x[j], at = B.aty_avg[j], Dj = B.D[j];
     const double xh = xa / Dj;  // sp.jl:65-67, isu.jl:436
     const double q = at * Dj;
+    // Q_O xhat = D .* (Q_P avg_x): Q_P = D^-1 Q_O D^-1 (preprocess.jl:99-113)
+    const double qxa = B.has_q ? B.qx_avg[j] : 0.0;
+    const double qh = qxa * Dj;
     const double c = B.c_orig[j], l = B.l_orig[j], u = B.u_orig[j];
     s[SN_cx] += c * xh;  // isu.jl:67-74
+    if (B.has_q) {
+      s[SN_xqx] += xh * qh;  // x' Q x of isu.jl:67-74 and :186
+      s[SN_xs_qxs] += xa * qxa;  // sp.jl:1109-1120 on the scaled problem
+      mx[SN_qx_max - SN_NSUM] = fmax(mx[SN_qx_max - SN_NSUM], fabs(qh));  // isu.jl:311-313
+    }
     const double lv = fmax(l - xh, 0.0), uv = fmax(xh - u, 0.0);  // isu.jl:52-55
     s[SN_lviol2] += lv * lv;
     s[SN_uviol2] += uv * uv;
     mx[SN_lviol_max - SN_NSUM] = fmax(mx[SN_lviol_max - SN_NSUM], lv);
     mx[SN_uviol_max - SN_NSUM] = fmax(mx[SN_uviol_max - SN_NSUM], uv);
-    const double g = c - q;  // sp.jl:1081-1091
+    const double g = B.has_q ? (qh + c) - q : c - q;  // sp.jl:1081-1091
     const double bound = g > 0.0 ? l : u;  // isu.jl:128-147
     const double rc = isfinite(bound) ? g : 0.0;
     const double dres = g - rc;  // isu.jl:171-178
@@ -729,6 +803,11 @@ __global__ void __launch_bounds__(kVecThreads) k_apply_restart(Bufs B, int to_av
     B.sum_x[j] = 0.0;
     B.last_x[j] = xc[j];
     B.last_aty[j] = atc[j];
+    if (B.has_q) {
+      double* __restrict__ qc = sel(B.qx, st.cur);
+      if (to_average) qc[j] = B.qx_avg[j];
+      B.last_qx[j] = qc[j];
+    }
   }
   for (int i = t0; i < B.m; i += stride) {
     if (to_average) yc[i] = B.avg_y[i];
@@ -756,8 +835,9 @@ void launch_apply_restart(const Bufs& B, int to_average, int have_ax_cur, cudaSt
 // ---------------------------------------------------------------------------
 enum TrInit {
   TI_g2 = 0, TI_H0, TI_Hinf, TI_Ltot, TI_cnt0, TI_cx, TI_xaty, TI_yb, TI_norm2, TI_gdp, TI_gdd,
-  TI_NSUM, TI_max_t = TI_NSUM, TI_TOTAL
+  TI_xqx, TI_NSUM, TI_max_t = TI_NSUM, TI_TOTAL
 };
+static_assert(TI_TOTAL <= 16, "trust-region sums travel in one 16-scalar exchange");
 
 struct TrElem {
   double x0, g, lb, ub, w;
@@ -766,7 +846,7 @@ __device__ __forceinline__ TrElem tr_elem(const Bufs& B, const TrProblem& P, int
   TrElem e;
   if (idx < B.n) {
     e.x0 = P.px[idx];
-    e.g = B.c[idx] - P.atp[idx];  // sp.jl:1081-1091 (Q = 0)
+    e.g = P.qxp ? (P.qxp[idx] + B.c[idx]) - P.atp[idx] : B.c[idx] - P.atp[idx];  // sp.jl:1081-1091
     e.lb = B.l[idx];
     e.ub = B.u[idx];
     e.w = P.wp;
@@ -811,7 +891,7 @@ __device__ void tr_setup(TrState* trs, const double* r, const TrProblem& P) {
   t.tau = 0.0;
   t.done = 0; t.zero_value = 0; t.approx = P.approx; t.passes = 0;
   t.approx_scale = 1.0;
-  t.cx = r[TI_cx]; t.x_aty = r[TI_xaty]; t.y_b = r[TI_yb];
+  t.cx = r[TI_cx]; t.x_aty = r[TI_xaty]; t.y_b = r[TI_yb]; t.xqx = r[TI_xqx];
   t.v_primal = 0.0; t.v_dual = 0.0;
   if (P.approx) {
     const double nrm = sqrt(r[TI_norm2]);
@@ -872,6 +952,7 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_init(Bufs B, TrProblem P, Tr
     if (primal) {  // compute_lagrangian_value, sp.jl:1109-1120
       s[TI_cx] += e.x0 * B.c[idx];
       s[TI_xaty] += e.x0 * P.atp[idx];
+      if (P.qxp) s[TI_xqx] += e.x0 * P.qxp[idx];
     } else {
       s[TI_yb] += e.x0 * B.b[idx - B.n];
     }

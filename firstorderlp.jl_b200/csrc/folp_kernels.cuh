@@ -23,6 +23,11 @@ struct Bufs {
   double *D = nullptr, *E = nullptr;         // variable_rescaling, constraint_rescaling
   double *c_orig = nullptr, *l_orig = nullptr, *u_orig = nullptr, *b_orig = nullptr;
   double *tr_t = nullptr, *tr_d = nullptr;   // trust-region scratch, n+m each
+  // ---- quadratic objective (has_q: the scaled objective matrix has a nonzero entry) ----
+  // qx[k] = Q * x[k] travels with the iterate buffers (same parity), dxv holds x+ - x of the
+  // running attempt, qx_avg / last_qx are Q times the evaluated / the last restart point.
+  int has_q = 0;
+  double *qx[2] = {nullptr, nullptr}, *dxv = nullptr, *qx_avg = nullptr, *last_qx = nullptr;
   // reductions
   double* part = nullptr;     // kMaxScalars * kMaxPartialBlocks doubles per slot, 4 slots
   double* red = nullptr;      // reduced scalars, kMaxScalars per slot
@@ -63,10 +68,11 @@ constexpr int kNumSlots = 4;
 // n-pass statistics (isu.jl:228-349 on the original problem + Lagrangian pieces)
 enum StatN {
   SN_cx = 0, SN_lviol2, SN_uviol2, SN_dres2, SN_rcobj, SN_x2, SN_ray_rcobj, SN_cs_x, SN_x_aty,
-  SN_xs2, SN_NSUM,
+  SN_xs2, SN_xqx, SN_xs_qxs, SN_NSUM,
   SN_lviol_max = SN_NSUM, SN_uviol_max, SN_dres_max, SN_x_max, SN_ray_l_max, SN_ray_u_max,
-  SN_ray_dres_max, SN_ray_rc_max, SN_TOTAL
+  SN_ray_dres_max, SN_ray_rc_max, SN_qx_max, SN_TOTAL
 };
+static_assert(SN_TOTAL <= kMaxScalars, "statistics block fits one reduction slot");
 enum StatM {
   SM_pres2 = 0, SM_by, SM_y2, SM_yneg2, SM_bs_y, SM_ys2, SM_NSUM,
   SM_pres_max = SM_NSUM, SM_y_max, SM_yneg_max, SM_ray_act_max, SM_TOTAL
@@ -90,6 +96,7 @@ struct TrState {
   // Lagrangian pieces and results
   double cx, x_aty, y_b;
   double v_primal, v_dual;  // objective_vector . (solution - center), per segment
+  double xqx;               // center' * Q * center (0 for an LP)
 };
 
 struct TrProblem {
@@ -97,10 +104,12 @@ struct TrProblem {
   const double *py, *axp;   // dual center and A * primal center
   double wp, wd, radius;
   int use_primal, use_dual, approx;
+  const double* qxp;        // Q * primal center; nullptr for an LP
 };
 
-void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, int attempts,
-                          cudaStream_t s);
+// Q: CSR of the objective matrix, used only when B.has_q
+void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q,
+                          int attempts, cudaStream_t s);
 // The pieces of one attempt in partitioned mode; without peer memory folp_api.cu interleaves them
 // with the NCCL exchanges (allgather xbar | allgather y+ | allgather of the 4 step-rule scalars).
 void launch_dist_primal(const Bufs& B, cudaStream_t s);
@@ -108,8 +117,8 @@ void launch_dist_dual(const Bufs& B, const SpmvMat& A, cudaStream_t s);
 void launch_dist_trans(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaStream_t s);
 void launch_dist_finalize(const Bufs& B, cudaStream_t s);
 // one attempt with events ev[0..3] recorded before/between/after the three kernels
-void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, cudaEvent_t* ev,
-                               cudaStream_t s);
+void launch_step_attempt_timed(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q,
+                               cudaEvent_t* ev, cudaStream_t s);
 void launch_spmv_plain(const SpmvMat& A, const double* in, double* out, int grid, cudaStream_t s);
 void launch_copy(const double* in, double* out, int64_t len, cudaStream_t s);
 void launch_flush_avg(const Bufs& B, cudaStream_t s);

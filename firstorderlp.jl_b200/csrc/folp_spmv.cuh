@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
        item += warps_total) {
     const TileHot t = load_hot(A.tiles, item);
     const int kind = t.kind();
-    if (kind == kTileThreadPerRow) {
+    if (kind == kTileThreadPerRow || kind == kTileThreadPerRowSorted) {
       // ---- up to 32 narrow rows, one per lane ----
       const bool valid = lane < t.rows();
-      const int r = t.row_begin + lane;
+      int r = t.row_begin + lane;
+      if (kind == kTileThreadPerRowSorted && valid) r = __ldg(A.rowid + r);
       int len = 0;
       double in0 = 0.0, in1 = 0.0, in2 = 0.0;
       if (valid) {

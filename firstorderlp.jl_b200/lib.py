@@ -24,7 +24,7 @@ _LIB: Optional[C.CDLL] = None
 EXPORTS = [
     "folp_nccl_unique_id", "folp_partition", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
-    "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
+    "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_host_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
 
 
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.folp_debug_spmv.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
         L.folp_debug_profile_attempts.argtypes = [C.c_void_p, C.c_int64, _pd, C.POINTER(C.c_int64)]
         L.folp_debug_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, _pd]
+        L.folp_debug_host_spmv.argtypes = [C.c_int64, C.c_int64, _pi64, _pi64, _pd, _pd, _pd, _pi64]
         L.folp_debug_stream.argtypes = [C.c_void_p]
         L.folp_debug_stream.restype = C.c_void_p
         L.folp_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), _pd, C.POINTER(C.c_int64)]
@@ -96,6 +97,27 @@ def _d(a) -> np.ndarray:
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(_pd)
+
+
+def host_packed_spmv(A_csr, x):
+    """y = A * x evaluated on the HOST through the library's packed work-item layout
+    (folp_debug_host_spmv): checks the packing without a GPU. Returns (y, stats)."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix(A_csr)
+    A.sort_indices()
+    _pi64 = C.POINTER(C.c_int64)
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int64)
+    v = _d(A.data)
+    xx = _d(x)
+    y = np.empty(A.shape[0], dtype=np.float64)
+    stats = np.zeros(4, dtype=np.int64)
+    rc = lib().folp_debug_host_spmv(A.shape[0], A.shape[1], rp.ctypes.data_as(_pi64),
+                                    ci.ctypes.data_as(_pi64), _p(v), _p(xx), _p(y),
+                                    stats.ctypes.data_as(_pi64))
+    if rc != 0:
+        raise FolpError(rc, "folp_debug_host_spmv")
+    return y, dict(zip(("tiles", "sorted_groups", "narrow_rounds", "long_rows"), stats.tolist()))
 
 
 def nccl_unique_id() -> bytes:

@@ -84,6 +84,34 @@ def random_sparse_lp(num_variables: int, num_constraints: int, nnz_per_row: int 
     return (lp, x, y) if return_solution else lp
 
 
+def random_sparse_qp(num_variables: int, num_constraints: int, nnz_per_row: int = 10,
+                     q_rank_rows: int | None = None, q_nnz_per_row: int = 3,
+                     seed: int = 20260117, upper_fraction: float = 0.0):
+    """random_sparse_lp plus a sparse symmetric positive semidefinite objective matrix
+    Q = B'B + diag(d): B has `q_rank_rows` rows of `q_nnz_per_row` N(0,1) entries, d >= 0 is zero on
+    half of the variables. The linear term is shifted so that the planted pair of the LP
+    stays optimal (c <- c - Q x*): same feasible set, known optimum."""
+    lp, x, _ = random_sparse_lp(num_variables, num_constraints, nnz_per_row, seed, upper_fraction,
+                                return_solution=True)
+    rng = np.random.default_rng(seed + 7)
+    n = int(num_variables)
+    r = int(q_rank_rows) if q_rank_rows is not None else max(1, n // 4)
+    cols = rng.integers(0, n, size=(r, q_nnz_per_row), dtype=np.int64)
+    vals = rng.standard_normal((r, q_nnz_per_row))
+    rows = np.repeat(np.arange(r, dtype=np.int64), q_nnz_per_row)
+    B = sp.csr_matrix((vals.ravel(), (rows, cols.ravel())), shape=(r, n))
+    B.sum_duplicates()
+    d = rng.uniform(0.0, 1.0, n)
+    d[rng.random(n) < 0.5] = 0.0
+    Q = sp.csc_matrix(B.T @ B + sp.diags(d))
+    Q = sp.csc_matrix((Q + Q.T) * 0.5)  # exactly symmetric
+    Q.eliminate_zeros()
+    Q.sort_indices()
+    lp.objective_matrix = Q
+    lp.objective_vector = lp.objective_vector - Q @ x
+    return lp
+
+
 def barabasi_albert_edges(num_nodes: int, k: int, rng) -> np.ndarray:
     """Preferential attachment: each new node links to k distinct earlier nodes
     chosen proportionally to degree (repeated-nodes list construction)."""

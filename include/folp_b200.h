@@ -341,6 +341,16 @@ int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[
  * SpMV kernel (A * x when transpose == 0, A' * y otherwise) on the live iterate. */
 int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, double* ms_out);
 
+/* Test hook without any CUDA call: packs a 0-based CSR matrix into the library's
+ * work-item layout exactly as folp_create does and evaluates y = A * x on the
+ * HOST by walking that layout with the kernel's own slot arithmetic, so that the
+ * packing (position-major groups, length-sorted windows, wide rows, long-row
+ * chunks) can be verified on a machine without a GPU. stats (may be NULL) =
+ * {work items, length-sorted groups, narrow-group rounds, long rows}. It is not a
+ * solver path: nothing in the library calls it. */
+int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colidx,
+                         const double* vals, const double* x, double* y, int64_t* stats);
+
 /* The CUDA stream (cudaStream_t) all kernels of this handle are launched on,
  * so a caller can bracket calls with its own events. */
 void* folp_debug_stream(folp_handle* h);

@@ -21,7 +21,7 @@ import scipy.sparse as sp
 import folp_b200
 from folp_b200 import RestartScheme, TerminationReason, _marshal
 from folp_b200.lib import Solver
-from folp_b200.synthetic import netlib_shaped_lp, pagerank_lp, random_sparse_lp
+from folp_b200.synthetic import netlib_shaped_lp, pagerank_lp, random_sparse_lp, random_sparse_qp
 from oracle import oracle
 from shared_problems import example_lp, generate_pdhg_params
 
@@ -118,7 +118,8 @@ def test_spmv_empty_matrix():
 # ---------------------------------------------------------------------------
 # (i) single attempts from identical state
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("make", [lambda: random_sparse_lp(4000, 3000, 10, seed=11), _ragged_lp])
+@pytest.mark.parametrize("make", [lambda: random_sparse_lp(4000, 3000, 10, seed=11), _ragged_lp,
+                                  lambda: random_sparse_qp(3000, 2000, 8, seed=12)])
 def test_single_attempt_parity(make):
     problem = make()
     params = generate_pdhg_params(iteration_limit=100, l_inf_ruiz_iterations=4,
@@ -182,7 +183,8 @@ _EVAL_FIELDS = [
     "relative_l2_primal_residual", "relative_l_inf_dual_residual", "relative_l2_dual_residual",
     "relative_optimality_gap", "l_inf_primal_variable", "l2_primal_variable",
     "l_inf_dual_variable", "l2_dual_variable", "max_primal_ray_infeasibility",
-    "primal_ray_linear_objective", "max_dual_ray_infeasibility", "dual_ray_objective",
+    "primal_ray_linear_objective", "primal_ray_quadratic_norm", "max_dual_ray_infeasibility",
+    "dual_ray_objective",
     "cumulative_kkt_matrix_passes", "step_size", "primal_weight", "lagrangian_value",
     "estimated_lower_bound", "estimated_upper_bound",
 ]
@@ -251,6 +253,46 @@ def test_eval_records_match_oracle(scheme):
     eo, n_restart, records = _run_lockstep(problem, params)
     assert eo.termination_reason == TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
     assert n_restart >= 3 and records == 10 + 14
+
+
+@pytest.mark.parametrize("scheme,policy", [(RestartScheme.ADAPTIVE_NORMALIZED, "adaptive"),
+                                           (RestartScheme.NO_RESTARTS, "adaptive"),
+                                           (RestartScheme.ADAPTIVE_LOCALIZED, "constant")])
+def test_eval_records_match_oracle_qp(scheme, policy):
+    """Quadratic objective (S1, S7, E7, E11, E13, E19 with Q != 0): every record of 120 iterations."""
+    problem = random_sparse_qp(1200, 900, 6, seed=33, upper_fraction=0.1)
+    params = generate_pdhg_params(iteration_limit=120, l_inf_ruiz_iterations=10,
+                                  pock_chambolle_alpha=1.0, restart_scheme=scheme,
+                                  step_size_policy=policy)
+    params.termination_evaluation_frequency = 8
+    eo, n_restart, records = _run_lockstep(problem, params)
+    assert eo.termination_reason == TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
+    assert eo.primal_ray_quadratic_norm > 0.0
+    assert records == 10 + 14
+
+
+def test_qp_full_solve_matches_oracle():
+    """A QP solved to 1e-6 with the CLI defaults: same reason, and the GPU-reported KKT record
+    equals the oracle's evaluation of the GPU's returned point."""
+    problem = random_sparse_qp(400, 300, 6, seed=43)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    eps = 1e-6
+    params.termination_criteria.eps_optimal_absolute = eps
+    params.termination_criteria.eps_optimal_relative = eps
+    params.termination_criteria.iteration_limit = 100000
+    out_o = oracle.optimize(params, problem)
+    out_g = folp_b200.optimize(params, problem)
+    assert out_g.termination_reason == out_o.termination_reason == \
+        TerminationReason.TERMINATION_REASON_OPTIMAL
+    fin = out_g.iteration_stats[-1].convergence_information[0]
+    chk = _kkt_of(problem, out_g.primal_solution, out_g.dual_solution, eps)
+    ref = max(abs(chk.primal_objective), abs(chk.dual_objective), 1.0)
+    assert abs(fin.primal_objective - chk.primal_objective) <= 1e-12 * ref
+    assert abs(fin.dual_objective - chk.dual_objective) <= 1e-10 * ref
+    assert abs(fin.l2_primal_residual - chk.l2_primal_residual) <= 1e-10 * max(1.0, chk.l2_primal_residual)
+    assert abs(fin.l2_dual_residual - chk.l2_dual_residual) <= 1e-10 * max(1.0, chk.l2_dual_residual)
+    fo = out_o.iteration_stats[-1].convergence_information[0]
+    assert abs(fin.primal_objective - fo.primal_objective) <= 10 * eps * ref
 
 
 # ---------------------------------------------------------------------------

@@ -1,0 +1,74 @@
+"""The library's matrix packing (position-major 32-row groups, length-sorted
+windows, wide rows, long-row chunks) checked on the HOST: folp_debug_host_spmv
+packs exactly as folp_create does and walks the layout with the kernel's slot
+arithmetic. Rows of <= 32 nonzeros must reproduce the serial ascending-column
+sum bit for bit (the summation order of the reference's stdlib kernels,
+SparseArrays `*`)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from folp_b200.lib import host_packed_spmv
+from folp_b200.synthetic import pagerank_lp, random_sparse_lp
+
+
+def _serial(A, x):
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    y = np.zeros(A.shape[0])
+    for i in range(A.shape[0]):
+        s = 0.0
+        for k in range(A.indptr[i], A.indptr[i + 1]):
+            s += A.data[k] * x[A.indices[k]]
+        y[i] = s
+    return y
+
+
+def _ragged(seed, rows=3000, n=5000):
+    rng = np.random.default_rng(seed)
+    lens = np.concatenate([np.zeros(9, int), rng.poisson(10, rows), np.full(5, 100),
+                           np.array([9000, 4097, 4096, 33, 32, 31])])
+    lens = np.minimum(lens, n)
+    rng.shuffle(lens)
+    ind, ptr, val = [], [0], []
+    for k in lens:
+        ind += list(np.sort(rng.choice(n, size=int(k), replace=False)))
+        val += list(rng.standard_normal(int(k)))
+        ptr.append(len(ind))
+    return sp.csr_matrix((val, ind, ptr), shape=(len(lens), n))
+
+
+@pytest.mark.parametrize("make", [
+    lambda: random_sparse_lp(4000, 3000, 10, seed=5).constraint_matrix.tocsr(),       # rows ~10: identity
+    lambda: random_sparse_lp(4000, 3000, 10, seed=5).constraint_matrix.T.tocsr(),     # Poisson columns: sorted
+    lambda: pagerank_lp(3000).constraint_matrix.T.tocsr(),                            # power-law + dense row
+    lambda: pagerank_lp(3000).constraint_matrix.tocsr(),
+    lambda: _ragged(1), lambda: _ragged(2, rows=257), lambda: sp.csr_matrix((5, 7)),
+    lambda: sp.csr_matrix(np.ones((1, 40))),
+])
+def test_packed_layout_reproduces_serial_row_sums(make):
+    A = make()
+    x = np.random.default_rng(0).standard_normal(A.shape[1])
+    y, stats = host_packed_spmv(A, x)
+    ref = _serial(A, x)
+    row_len = np.diff(A.indptr)
+    narrow = row_len <= 32
+    assert np.array_equal(y[narrow], ref[narrow])          # bit-identical: same summation order
+    scale = max(1.0, np.max(np.abs(ref)) if ref.size else 1.0)
+    assert np.max(np.abs(y - ref), initial=0.0) <= 1e-13 * scale
+    assert stats["long_rows"] == int((row_len > 4096).sum())
+
+
+def test_length_sorted_windows_save_rounds_on_poisson_columns(monkeypatch):
+    At = random_sparse_lp(20000, 20000, 10, seed=7).constraint_matrix.T.tocsr()
+    x = np.ones(At.shape[1])
+    y1, s1 = host_packed_spmv(At, x)
+    monkeypatch.setenv("FOLP_NO_ROW_SORT", "1")
+    y0, s0 = host_packed_spmv(At, x)
+    assert np.array_equal(y0, y1)
+    assert s0["sorted_groups"] == 0 and s1["sorted_groups"] > 0
+    assert s1["narrow_rounds"] <= 0.8 * s0["narrow_rounds"]
+    # rows of (almost) equal length keep the identity order: no indirection for A itself
+    A = random_sparse_lp(20000, 20000, 10, seed=7).constraint_matrix.tocsr()
+    _, s = host_packed_spmv(A, np.ones(A.shape[1]))
+    assert s["sorted_groups"] == 0
