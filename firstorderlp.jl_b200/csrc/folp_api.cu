@@ -82,6 +82,7 @@ struct folp_handle {
   folp_eval last_eval{};
   int64_t launches = 0;
   int64_t tr_passes = 0, tr_solves = 0;
+  int tr_grid = 0;  // > 0: trust-region solves run as one cooperative kernel on this many blocks
   std::map<int, cudaGraphExec_t> step_graphs;
   bool use_graphs = true;
   // ---- row-partitioned mode (folp_dist.world_size > 1) ----
@@ -152,8 +153,10 @@ struct PackedMatrix {
   bool any_sorted = false;
   int nlong = 0, nchunks_total = 0;
 };
+// warps_total = warps of the grid k_spmv runs on: work item i goes to warp i % warps_total in
+// that warp's trip i / warps_total (static striding, see k_spmv).
 static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<int>& colidx,
-                        std::vector<double>& vals, PackedMatrix* out) {
+                        std::vector<double>& vals, int warps_total, PackedMatrix* out) {
   std::vector<Tile>& tiles = out->tiles;
   std::vector<int>& rowid = out->rowid;
   bool& any_sorted = out->any_sorted;
@@ -223,7 +226,17 @@ static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<in
       windows.back().sorted = sorted ? 1 : 0;
       if (sorted) {
         any_sorted = true;
-        for (int q = w0; q < w1; ++q) rowid[q] = ids[q - w0];
+        // The groups of a sorted window differ in length by design, and work item i always
+        // lands on warp i % warps_total: without care the same warp of every CTA would get the
+        // longest group of every window it visits. Rotate the order of the window's FULL groups
+        // by the trip number, so that a warp meets every rank in turn.
+        const int full = (w1 - w0) / 32;  // groups of exactly 32 rows; a shorter tail group stays last
+        const int rot = full > 1 ? static_cast<int>((tiles.size() / static_cast<size_t>(warps_total)) % full) : 0;
+        for (int g = 0; g < full; ++g) {
+          const int src = ((g + rot) % full) * 32;
+          for (int q = 0; q < 32; ++q) rowid[w0 + g * 32 + q] = ids[src + q];
+        }
+        for (int q = w0 + full * 32; q < w1; ++q) rowid[q] = ids[q - w0];
       }
       int k = rowptr[w0];
       for (int g = w0; g < w1; g += 32) {
@@ -276,7 +289,7 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
   M->cols = cols;
   M->nnz = rowptr[rows];
   PackedMatrix pk;
-  pack_matrix(rows, rowptr, colidx, vals, &pk);
+  pack_matrix(rows, rowptr, colidx, vals, h->sm_count * kSpmvCtasPerSm * kSpmvWarps, &pk);
   const std::vector<Tile>& tiles = pk.tiles;
   const std::vector<int>& rowid = pk.rowid;
   const bool any_sorted = pk.any_sorted;
@@ -289,9 +302,13 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
   if ((rc = dev_alloc(h, &M->colidx, static_cast<size_t>(M->nnz) + pad))) return rc;
   if ((rc = dev_alloc(h, &M->vals, static_cast<size_t>(M->nnz) + pad))) return rc;
   if ((rc = dev_alloc(h, &M->tiles, tiles.size()))) return rc;
-  if (any_sorted) {
+  std::vector<int2> slot_row_len;
+  if (any_sorted) {  // (row, length) of every slot: one coalesced 8-byte load per lane of a sorted group
+    slot_row_len.resize(static_cast<size_t>(rows));
+    for (int q = 0; q < rows; ++q)
+      slot_row_len[q] = make_int2(rowid[q], rowptr[rowid[q] + 1] - rowptr[rowid[q]]);
     if ((rc = dev_alloc(h, &M->rowid, static_cast<size_t>(rows)))) return rc;
-    TRY(cudaMemcpyAsync(M->rowid, rowid.data(), static_cast<size_t>(rows) * sizeof(int),
+    TRY(cudaMemcpyAsync(M->rowid, slot_row_len.data(), static_cast<size_t>(rows) * sizeof(int2),
                         cudaMemcpyHostToDevice, h->stream));
   }
   if ((rc = dev_alloc(h, &M->long_partials, static_cast<size_t>(nchunks_total)))) return rc;
@@ -561,6 +578,8 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     return FOLP_UNSUPPORTED;
   }
   h->sm_count = prop.multiProcessorCount;
+  if (!(dist && dist->world_size > 1) && prop.cooperativeLaunch && getenv("FOLP_TR_MULTIKERNEL") == nullptr)
+    h->tr_grid = tr_solve_grid(h->sm_count);
   TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TRY(cudaEventCreate(&h->ev0));
   TRY(cudaEventCreate(&h->ev1));
@@ -1167,6 +1186,20 @@ static int tr_round(folp_handle* h, const TrProblem& P, int passes, bool init) {
 
 static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
   int rc;
+  if (h->tr_grid > 0) {  // single GPU: one cooperative kernel, one host read
+    TRY(static_cast<cudaError_t>(launch_tr_solve(h->B, P, h->d_trs, h->tr_grid, h->stream)));
+    h->launches += 1;
+    h->tr_solves += 1;
+    TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState), cudaMemcpyDeviceToHost, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+    if (h->h_trs->done != 1) {
+      h->err = "trust-region search did not converge";
+      return FOLP_CUDA_ERROR;
+    }
+    *out = *h->h_trs;
+    h->tr_passes += out->passes;
+    return FOLP_OK;
+  }
   if ((rc = tr_round(h, P, h->world == 1 ? 10 : 6, true))) return rc;
   h->tr_solves += 1;
   for (int round = 0;; ++round) {
@@ -1771,7 +1804,7 @@ extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, dou
 // machine without a GPU. y = A * x; stats = {tiles, sorted groups, narrow rounds, long rows}.
 extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr,
                                     const int64_t* colidx, const double* vals, const double* x,
-                                    double* y, int64_t* stats) {
+                                    double* y, int64_t warps_total, int64_t* stats) {
   if (rows < 0 || cols < 0 || !rowptr || !y || (rowptr[rows] > 0 && (!colidx || !vals || !x)))
     return FOLP_INVALID_ARGUMENT;
   const int64_t nnz = rowptr[rows];
@@ -1784,8 +1817,11 @@ extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* r
     ci[k] = static_cast<int>(colidx[k]);
   }
   PackedMatrix pk;
-  pack_matrix(static_cast<int>(rows), rp, ci, v, &pk);
+  pack_matrix(static_cast<int>(rows), rp, ci, v, warps_total > 0 ? static_cast<int>(warps_total) : 148 * kSpmvCtasPerSm * kSpmvWarps, &pk);
   int64_t n_sorted = 0, n_rounds = 0;
+  const int64_t W = warps_total > 0 ? warps_total : 148 * kSpmvCtasPerSm * kSpmvWarps;
+  std::vector<int64_t> warp_rounds(static_cast<size_t>(W), 0);
+  int64_t item = 0;
   std::vector<double> partial(static_cast<size_t>(std::max(pk.nchunks_total, 1)), 0.0);
   for (int64_t i = 0; i < rows; ++i) y[i] = 0.0;  // empty rows are covered by narrow groups too
   for (const Tile& t : pk.tiles) {
@@ -1817,8 +1853,10 @@ extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* r
       }
       if (off != t.nnz_end) return FOLP_INVALID_ARGUMENT;  // the group's range is exactly consumed
       n_rounds += (maxlen + 3) / 4;
+      warp_rounds[item % W] += (maxlen + 3) / 4;
       for (int lane = 0; lane < cnt; ++lane) y[row[lane]] = s[lane];
     } else {
+      warp_rounds[item % W] += (t.nnz_end - t.nnz_begin + 127) / 128;
       double lane_sum[32] = {0.0};
       for (int k = t.nnz_begin; k < t.nnz_end; ++k) lane_sum[(k - t.nnz_begin) & 31] += v[k] * x[ci[k]];
       auto tree = [](double* a) {  // warp_sum's xor-shuffle tree
@@ -1838,12 +1876,14 @@ extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* r
         }
       }
     }
+    item += 1;
   }
   if (stats) {
     stats[0] = static_cast<int64_t>(pk.tiles.size());
     stats[1] = n_sorted;
     stats[2] = n_rounds;
     stats[3] = pk.nlong;
+    stats[4] = *std::max_element(warp_rounds.begin(), warp_rounds.end());  // the busiest warp's rounds
   }
   return FOLP_OK;
 }

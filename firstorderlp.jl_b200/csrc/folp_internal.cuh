@@ -103,7 +103,7 @@ struct SpmvMat {
   int rows = 0, cols = 0;
   int64_t nnz = 0;
   int* rowptr = nullptr;     // rows+1 (device)
-  int* rowid = nullptr;      // rows: slot -> row inside length-sorted windows (nullptr: no sorted group)
+  int2* rowid = nullptr;     // rows: slot -> (row, its length) inside length-sorted windows (nullptr: none)
   int* colidx = nullptr;     // nnz + pad
   double* vals = nullptr;    // nnz + pad
   Tile* tiles = nullptr;

@@ -8,6 +8,7 @@
 //   k_spmv<EpiTrans>   A'*y+ (pdhg.jl:492), interaction dot (S7) and, in the last
 //                      CTA to finish, the scalar accept/reject + step-size rule (S8)
 // The evaluation block (pdhg.jl:892-1023) uses the kernels in the second half.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "folp_kernels.cuh"
@@ -625,32 +626,47 @@ void launch_make_avg(const Bufs& B, int use_current, cudaStream_t s) {
 }
 
 // Block-reduces NSUM sums followed by NMAX maxima, and lets the last block
-// produce the final values in red_out[0 .. NSUM+NMAX).
+// produce the final values in red_out[0 .. NSUM+NMAX). One barrier for all scalars: every warp
+// shuffle-reduces each of them, warp leaders park them in shared memory, thread k combines
+// scalar k over the warps in warp order; in the last block warp w finishes scalars w, w+8, ...
+// over the per-block partials (lanes stride the blocks, fixed order, then a shuffle tree).
 template <int NSUM, int NMAX>
 __device__ __forceinline__ void reduce_and_publish(const Bufs& B, double* sums, double* maxs,
-                                                   double* red_out, double* sh) {
+                                                   double* red_out, double* /*sh, unused*/) {
+  constexpr int K = NSUM + NMAX;
+  constexpr int kWarps = kVecThreads / 32;
+  __shared__ double sh_w[K * kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
 #pragma unroll
   for (int k = 0; k < NSUM; ++k) {
-    const double t = block_reduce<false>(sums[k], sh);
-    if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = t;
+    const double t = warp_sum(sums[k]);
+    if (lane == 0) sh_w[k * kWarps + warp] = t;
   }
 #pragma unroll
   for (int k = 0; k < NMAX; ++k) {
-    const double t = block_reduce<true>(maxs[k], sh);
-    if (threadIdx.x == 0)
-      part[static_cast<size_t>(NSUM + k) * kMaxPartialBlocks + blockIdx.x] = t;
+    const double t = warp_max(maxs[k]);
+    if (lane == 0) sh_w[(NSUM + k) * kWarps + warp] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const int k = threadIdx.x;
+    double t = sh_w[k * kWarps];
+    for (int w = 1; w < kWarps; ++w)
+      t = k < NSUM ? t + sh_w[k * kWarps + w] : fmax(t, sh_w[k * kWarps + w]);
+    part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = t;
   }
   if (!last_block_arrive(B.counters + kSlotEval)) return;
-  for (int k = 0; k < NSUM; ++k) {
-    const double t =
-        reduce_partials<false>(part + static_cast<size_t>(k) * kMaxPartialBlocks, gridDim.x, sh);
-    if (threadIdx.x == 0) red_out[k] = t;
-  }
-  for (int k = 0; k < NMAX; ++k) {
-    const double t = reduce_partials<true>(
-        part + static_cast<size_t>(NSUM + k) * kMaxPartialBlocks, gridDim.x, sh);
-    if (threadIdx.x == 0) red_out[NSUM + k] = t;
+  const int G = gridDim.x;
+  for (int k = warp; k < K; k += kWarps) {
+    const bool is_max = k >= NSUM;
+    double t = is_max ? -INFINITY : 0.0;
+    for (int j = lane; j < G; j += 32) {
+      const double q = __ldcg(part + static_cast<size_t>(k) * kMaxPartialBlocks + j);
+      t = is_max ? fmax(t, q) : t + q;
+    }
+    t = is_max ? warp_max(t) : warp_sum(t);
+    if (lane == 0) red_out[k] = t;
   }
 }
 
@@ -1104,6 +1120,172 @@ __global__ void k_tr_combine(Bufs B, TrProblem P, TrState* trs, int stage,
     trs->v_primal = r[0];
     trs->v_dual = r[1];
   }
+}
+
+// ---------------------------------------------------------------------------
+// The whole trust-region solve in ONE cooperative kernel (single GPU): init, Newton /
+// bisection passes until the partition stops changing, final value -- separated by grid-wide
+// barriers instead of kernel boundaries, so that a solve costs one launch and one host read
+// instead of ~12 launches (most of them early exits) and the passes stream tr_t / tr_d out of
+// L2. Every block reduces the same per-block partials in the same order, so all blocks hold
+// bit-identical copies of the TrState and take the same branches.
+// ---------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kTrThreads = 256;
+constexpr int kTrWarps = kTrThreads / 32;
+constexpr int kTrMaxK = 16;
+
+// totals of K per-thread values over the whole grid -> tot[0..K) (shared memory, valid in every
+// thread of every block after the call). Entry k is a maximum if bit k of max_mask is set, a sum
+// otherwise. part: two alternating buffers of kTrMaxK * gridDim.x doubles (parity flips per call).
+template <int K>
+__device__ __forceinline__ void grid_totals(cg::grid_group& grid, const double (&v)[K],
+                                            unsigned max_mask, double* part, int& parity,
+                                            double* sh /* K * kTrWarps */, double* tot /* K */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = gridDim.x;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double w = (max_mask >> k) & 1u ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) sh[k * kTrWarps + warp] = w;
+  }
+  __syncthreads();
+  double* buf = part + static_cast<size_t>(parity) * kTrMaxK * G;
+  if (threadIdx.x < K) {
+    const int k = threadIdx.x;
+    const bool is_max = (max_mask >> k) & 1u;
+    double t = sh[k * kTrWarps];
+    for (int w = 1; w < kTrWarps; ++w) t = is_max ? fmax(t, sh[k * kTrWarps + w]) : t + sh[k * kTrWarps + w];
+    buf[static_cast<size_t>(k) * G + blockIdx.x] = t;
+  }
+  grid.sync();
+  for (int k = warp; k < K; k += kTrWarps) {
+    const bool is_max = (max_mask >> k) & 1u;
+    double t = is_max ? -CUDART_INF : 0.0;
+    for (int j = lane; j < G; j += 32) {
+      const double q = __ldcg(buf + static_cast<size_t>(k) * G + j);
+      t = is_max ? fmax(t, q) : t + q;
+    }
+    t = is_max ? warp_max(t) : warp_sum(t);
+    if (lane == 0) tot[k] = t;
+  }
+  __syncthreads();
+  parity ^= 1;
+}
+
+__global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, TrState* trs,
+                                                         double* part) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[kTrMaxK * kTrWarps];
+  __shared__ double tot[kTrMaxK];
+  __shared__ TrState st;
+  int parity = 0;
+  const int stride = gridDim.x * blockDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = B.n + B.m;
+  // ---- init (k_tr_init) ----
+  {
+    double s[TI_TOTAL];
+#pragma unroll
+    for (int k = 0; k < TI_TOTAL; ++k) s[k] = 0.0;
+    for (int idx = tid; idx < total; idx += stride) {
+      const bool primal = idx < B.n;
+      const TrElem e = tr_elem(B, P, idx);
+      if (primal) {  // compute_lagrangian_value, sp.jl:1109-1120
+        s[TI_cx] += e.x0 * B.c[idx];
+        s[TI_xaty] += e.x0 * P.atp[idx];
+        if (P.qxp) s[TI_xqx] += e.x0 * P.qxp[idx];
+      } else {
+        s[TI_yb] += e.x0 * B.b[idx - B.n];
+      }
+      if (primal ? !P.use_primal : !P.use_dual) continue;
+      s[TI_g2] += e.g * e.g;
+      const bool skip = (e.x0 >= e.ub && e.g <= 0.0) || (e.x0 <= e.lb && e.g >= 0.0);  // tr.jl:96-103
+      const double d = skip ? 0.0 : -e.g / e.w;
+      B.tr_d[idx] = d;
+      if (P.approx) {  // tr.jl:194-224
+        s[TI_norm2] += e.w * d * d;
+        if (primal) s[TI_gdp] += e.g * d;
+        else s[TI_gdd] += e.g * d;
+        continue;
+      }
+      double t = 0.0;  // tr.jl:104-116
+      if (d > 0.0) t = (e.ub - e.x0) / d;
+      else if (d < 0.0) t = (e.lb - e.x0) / d;
+      B.tr_t[idx] = t;
+      const double h = e.w * d * d;
+      if (isinf(t)) {
+        s[TI_Hinf] += h;
+        s[TI_H0] += h;
+      } else {
+        if (t > 0.0) s[TI_H0] += h;
+        else s[TI_cnt0] += 1.0;
+        s[TI_Ltot] += h * t * t;
+        s[TI_max_t] = fmax(s[TI_max_t], t);
+      }
+    }
+    grid_totals<TI_TOTAL>(grid, s, 1u << TI_max_t, part, parity, sh, tot);
+    if (threadIdx.x == 0) tr_setup(&st, tot, P);
+    __syncthreads();
+  }
+  // ---- passes (k_tr_pass) ----
+  const int begin = P.use_primal ? 0 : B.n;
+  const int end = P.use_dual ? total : B.n;
+  while (!st.done) {
+    const double c0 = st.cand[0], c1 = st.cand[1];
+    double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // L0,H0,cnt0,L1,H1,cnt1
+#pragma unroll 4
+    for (int idx = begin + tid; idx < end; idx += stride) {
+      const double t = B.tr_t[idx], d = B.tr_d[idx];
+      const double h = (idx < B.n ? P.wp : P.wd) * d * d;
+      const double lt = h * t * t;
+      if (t <= c0) { s[0] += lt; s[2] += 1.0; } else { s[1] += h; }
+      if (t <= c1) { s[3] += lt; s[5] += 1.0; } else { s[4] += h; }
+    }
+    grid_totals<6>(grid, s, 0u, part, parity, sh, tot);
+    if (threadIdx.x == 0) {
+      tr_update(&st, tot);
+      // non-finite data (a diverged iterate) can keep the partition changing for ever
+      if (!st.done && st.passes >= 400) { st.done = 2; st.zero_value = 1; }
+    }
+    __syncthreads();
+  }
+  // ---- final value (k_tr_final) ----
+  if (!st.zero_value) {
+    const double tau = st.tau;
+    double s[2] = {0.0, 0.0};
+    for (int idx = begin + tid; idx < end; idx += stride) {
+      const TrElem e = tr_elem(B, P, idx);
+      const double sol = jl_clamp(e.x0 + tau * B.tr_d[idx], e.lb, e.ub);  // tr.jl:182-188
+      const double v = e.g * (sol - e.x0);
+      if (idx < B.n) s[0] += v;
+      else s[1] += v;
+    }
+    grid_totals<2>(grid, s, 0u, part, parity, sh, tot);
+    if (threadIdx.x == 0) {
+      st.v_primal = tot[0];
+      st.v_dual = tot[1];
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *trs = st;
+}
+
+int tr_solve_grid(int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tr_solve, kTrThreads, 0) != cudaSuccess ||
+      per_sm < 1)
+    return 0;
+  return sm_count * (per_sm < 2 ? per_sm : 2);
+}
+
+int launch_tr_solve(const Bufs& B, const TrProblem& P, TrState* d_trs, int grid, cudaStream_t s) {
+  // the scratch of the evaluation slot holds 2 * kTrMaxK * grid doubles
+  static_assert(2 * kTrMaxK <= kMaxScalars, "partials fit the evaluation slot");
+  double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
+  void* args[] = {const_cast<Bufs*>(&B), const_cast<TrProblem*>(&P), &d_trs, &part};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tr_solve), dim3(grid), dim3(kTrThreads),
+                                     args, 0, s);
 }
 
 void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bool init,

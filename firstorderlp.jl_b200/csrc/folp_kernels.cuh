@@ -88,7 +88,7 @@ struct TrState {
   double cand[2];
   double tau;        // final threshold
   double max_t;
-  int done;          // 1: tau is final
+  int done;          // 1: tau is final; 2: the search was abandoned (non-finite data)
   int zero_value;    // 1: solution == center (value 0)
   int approx;
   int passes;
@@ -130,6 +130,10 @@ void launch_dist(const Bufs& B, double* red_out, cudaStream_t s);
 void launch_apply_restart(const Bufs& B, int to_average, int have_ax_cur, cudaStream_t s);
 void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bool init,
                cudaStream_t s);
+// single GPU: the whole solve (init, passes to convergence, final value) as one cooperative
+// kernel on `grid` co-resident blocks; returns a cudaError_t
+int launch_tr_solve(const Bufs& B, const TrProblem& P, TrState* d_trs, int grid, cudaStream_t s);
+int tr_solve_grid(int sm_count);  // co-resident blocks for launch_tr_solve (0: unavailable)
 // row-partitioned mode: one kernel of the trust-region solve at a time; each leaves its
 // local sums in B.sc_send, and after the host's scalar exchange launch_tr_combine applies
 // the rank-ordered totals to the TrState.

@@ -74,11 +74,16 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
       // ---- up to 32 narrow rows, one per lane ----
       const bool valid = lane < t.rows();
       int r = t.row_begin + lane;
-      if (kind == kTileThreadPerRowSorted && valid) r = __ldg(A.rowid + r);
       int len = 0;
       double in0 = 0.0, in1 = 0.0, in2 = 0.0;
       if (valid) {
-        len = __ldg(A.rowptr + r + 1) - __ldg(A.rowptr + r);
+        if (kind == kTileThreadPerRowSorted) {  // (row, length) of this lane's slot
+          const int2 rl = __ldg(A.rowid + r);
+          r = rl.x;
+          len = rl.y;
+        } else {
+          len = __ldg(A.rowptr + r + 1) - __ldg(A.rowptr + r);
+        }
         // per-row operands are read once: stream them past L2 so that the gathered vector stays
         if (Epi::kNumIn > 0) in0 = ld_stream(epi.in_ptr(0) + r);
         if (Epi::kNumIn > 1) in1 = ld_stream(epi.in_ptr(1) + r);

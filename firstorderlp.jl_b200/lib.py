@@ -74,7 +74,7 @@ def lib() -> C.CDLL:
         L.folp_debug_spmv.argtypes = [C.c_void_p, C.c_int, _pd, _pd]
         L.folp_debug_profile_attempts.argtypes = [C.c_void_p, C.c_int64, _pd, C.POINTER(C.c_int64)]
         L.folp_debug_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, _pd]
-        L.folp_debug_host_spmv.argtypes = [C.c_int64, C.c_int64, _pi64, _pi64, _pd, _pd, _pd, _pi64]
+        L.folp_debug_host_spmv.argtypes = [C.c_int64, C.c_int64, _pi64, _pi64, _pd, _pd, _pd, C.c_int64, _pi64]
         L.folp_debug_stream.argtypes = [C.c_void_p]
         L.folp_debug_stream.restype = C.c_void_p
         L.folp_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), _pd, C.POINTER(C.c_int64)]
@@ -99,7 +99,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_pd)
 
 
-def host_packed_spmv(A_csr, x):
+def host_packed_spmv(A_csr, x, warps_total: int = 0):
     """y = A * x evaluated on the HOST through the library's packed work-item layout
     (folp_debug_host_spmv): checks the packing without a GPU. Returns (y, stats)."""
     import scipy.sparse as sp
@@ -111,13 +111,14 @@ def host_packed_spmv(A_csr, x):
     v = _d(A.data)
     xx = _d(x)
     y = np.empty(A.shape[0], dtype=np.float64)
-    stats = np.zeros(4, dtype=np.int64)
+    stats = np.zeros(5, dtype=np.int64)
     rc = lib().folp_debug_host_spmv(A.shape[0], A.shape[1], rp.ctypes.data_as(_pi64),
-                                    ci.ctypes.data_as(_pi64), _p(v), _p(xx), _p(y),
+                                    ci.ctypes.data_as(_pi64), _p(v), _p(xx), _p(y), warps_total,
                                     stats.ctypes.data_as(_pi64))
     if rc != 0:
         raise FolpError(rc, "folp_debug_host_spmv")
-    return y, dict(zip(("tiles", "sorted_groups", "narrow_rounds", "long_rows"), stats.tolist()))
+    return y, dict(zip(("tiles", "sorted_groups", "narrow_rounds", "long_rows", "busiest_warp_rounds"),
+                       stats.tolist()))
 
 
 def nccl_unique_id() -> bytes:

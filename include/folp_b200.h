@@ -345,11 +345,14 @@ int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, double* ms_out
  * work-item layout exactly as folp_create does and evaluates y = A * x on the
  * HOST by walking that layout with the kernel's own slot arithmetic, so that the
  * packing (position-major groups, length-sorted windows, wide rows, long-row
- * chunks) can be verified on a machine without a GPU. stats (may be NULL) =
- * {work items, length-sorted groups, narrow-group rounds, long rows}. It is not a
- * solver path: nothing in the library calls it. */
+ * chunks) can be verified on a machine without a GPU. warps_total = warps of
+ * the grid the kernel would run on (<= 0: a full B200). stats (5 entries, may be
+ * NULL) = {work items, length-sorted groups, narrow-group rounds, long rows,
+ * rounds of the busiest warp}. It is not a solver path: nothing in the library
+ * calls it. */
 int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr, const int64_t* colidx,
-                         const double* vals, const double* x, double* y, int64_t* stats);
+                         const double* vals, const double* x, double* y, int64_t warps_total,
+                         int64_t* stats);
 
 /* The CUDA stream (cudaStream_t) all kernels of this handle are launched on,
  * so a caller can bracket calls with its own events. */

@@ -65,9 +65,18 @@ def test_length_sorted_windows_save_rounds_on_poisson_columns(monkeypatch):
     y1, s1 = host_packed_spmv(At, x)
     monkeypatch.setenv("FOLP_NO_ROW_SORT", "1")
     y0, s0 = host_packed_spmv(At, x)
+    monkeypatch.delenv("FOLP_NO_ROW_SORT")
     assert np.array_equal(y0, y1)
     assert s0["sorted_groups"] == 0 and s1["sorted_groups"] > 0
     assert s1["narrow_rounds"] <= 0.8 * s0["narrow_rounds"]
+    # ... and the groups are dealt to the warps in rotation: the busiest warp gains as well
+    # (a grid of 64 warps here, so that every warp makes several trips)
+    _, r1 = host_packed_spmv(At, x, warps_total=64)
+    monkeypatch.setenv("FOLP_NO_ROW_SORT", "1")
+    _, r0 = host_packed_spmv(At, x, warps_total=64)
+    monkeypatch.delenv("FOLP_NO_ROW_SORT")
+    assert r1["busiest_warp_rounds"] <= 0.8 * r0["busiest_warp_rounds"]
+    assert r1["busiest_warp_rounds"] <= 1.2 * r1["narrow_rounds"] / 64
     # rows of (almost) equal length keep the identity order: no indirection for A itself
     A = random_sparse_lp(20000, 20000, 10, seed=7).constraint_matrix.tocsr()
     _, s = host_packed_spmv(A, np.ones(A.shape[1]))

@@ -2,7 +2,10 @@
 """Development probe: per-kernel device time of real take_step attempts for one or more
 builds of libfolp_b200.so on one synthetic workload.
 
-  python tools/probe_kernels.py [--workload c2] [--attempts 200] lib1.so [lib2.so ...]
+  python tools/probe_kernels.py [--workload c2] [--attempts 200] lib1.so [lib2.so:ENV=VALUE ...]
+
+A library may be followed by `:NAME=VALUE[,NAME=VALUE]`: environment variables set while that
+handle is created (e.g. FOLP_NO_ROW_SORT=1), so that set-up variants are compared in one process.
 """
 import argparse
 import json
@@ -37,10 +40,15 @@ def main():
     n, m, nnz = lp.num_variables, lp.num_constraints, lp.constraint_matrix.nnz
     b1, b2, b3 = bench.algorithmic_bytes(n, m, nnz)
     fparams.iteration_limit = 10_000_000
-    for path in (args.libs or [L.LIB_PATH]):
+    for spec in (args.libs or [L.LIB_PATH]):
+        path, _, envs = spec.partition(":")
+        env = dict(kv.split("=", 1) for kv in envs.split(",") if kv)
         L._LIB = None
         L.LIB_PATH = os.path.abspath(path)
+        os.environ.update(env)
         s = L.Solver(holder, fparams)
+        for k in env:
+            os.environ.pop(k, None)
         bench.run_until(s, 120)
         s.profile_attempts(20)
         kms, ran = s.profile_attempts(args.attempts)
@@ -51,7 +59,7 @@ def main():
             s.close()
             print(json.dumps(out), flush=True)
             continue
-        out = {"lib": os.path.basename(path), "info": L.build_info(), "k_primal_us": per[0] * 1e3,
+        out = {"lib": os.path.basename(path), "env": env, "info": L.build_info(), "k_primal_us": per[0] * 1e3,
                "k_dual_us": per[1] * 1e3, "k_trans_us": per[2] * 1e3,
                "gbs": [b1 / per[0] / 1e6, b2 / per[1] / 1e6, b3 / per[2] / 1e6],
                "iter_us": sum(per) * 1e3, "iter_gbs": (b1 + b2 + b3) / sum(per) / 1e6}
