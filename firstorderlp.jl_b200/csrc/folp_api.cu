@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/mman.h>
 #include <string.h>
 
 #include <algorithm>
@@ -29,13 +30,14 @@ double now_sec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Splits [begin, end) over up to 8 host threads (folp_create's O(nnz) loops: index conversion,
+constexpr unsigned kMaxHostThreadsU = 16;
+// Splits [begin, end) over up to kMaxHostThreadsU host threads (folp_create's O(nnz) loops: index conversion,
 // transposition, position-major packing). fn(lo, hi, thread_index).
 template <class F>
 void parallel_for(int64_t begin, int64_t end, int64_t min_chunk, F fn) {
   const int64_t len = end - begin;
   unsigned hw = std::thread::hardware_concurrency();
-  int T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), std::max<int64_t>(1, len / min_chunk)));
+  int T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, kMaxHostThreadsU), std::max<int64_t>(1, len / min_chunk)));
   if (T <= 1) {
     if (len > 0) fn(begin, end, 0);
     return;
@@ -48,7 +50,40 @@ void parallel_for(int64_t begin, int64_t end, int64_t min_chunk, F fn) {
   }
   for (auto& x : th) x.join();
 }
-constexpr int kMaxHostThreads = 8;
+
+// std::vector without the zero fill of resize() / the sizing constructor: folp_create's
+// O(nnz) scratch arrays are written exactly once, by several threads.
+// Large blocks are 2 MB aligned and advised as transparent huge pages: the arrays are touched
+// once, front to back, and with 4 KB pages the first-touch faults cost more than the work.
+template <class T>
+struct NoInit {
+  using value_type = T;
+  template <class U> struct rebind { using other = NoInit<U>; };
+  NoInit() = default;
+  template <class U> NoInit(const NoInit<U>&) {}
+  T* allocate(size_t count) {
+    const size_t bytes = count * sizeof(T);
+    void* q = nullptr;
+    constexpr size_t kHuge = size_t{2} << 20;
+    if (bytes >= 2 * kHuge) {
+      const size_t rounded = (bytes + kHuge - 1) / kHuge * kHuge;
+      q = aligned_alloc(kHuge, rounded);
+      static const bool thp = getenv("FOLP_NO_THP") == nullptr;
+      if (q && thp) madvise(q, rounded, MADV_HUGEPAGE);
+    } else {
+      q = malloc(bytes ? bytes : 1);
+    }
+    if (!q) throw std::bad_alloc();
+    return static_cast<T*>(q);
+  }
+  void deallocate(T* q, size_t) noexcept { free(q); }
+  template <class U> bool operator==(const NoInit<U>&) const { return true; }
+  template <class U> bool operator!=(const NoInit<U>&) const { return false; }
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using IVec = std::vector<int, NoInit<int>>;
+using DVec = std::vector<double, NoInit<double>>;
 }  // namespace
 
 struct folp_handle {
@@ -155,16 +190,13 @@ struct PackedMatrix {
 };
 // warps_total = warps of the grid k_spmv runs on: work item i goes to warp i % warps_total in
 // that warp's trip i / warps_total (static striding, see k_spmv).
-static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<int>& colidx,
-                        std::vector<double>& vals, int warps_total, PackedMatrix* out) {
+static void plan_tiles(int rows, const IVec& rowptr, int warps_total, PackedMatrix* out) {
   std::vector<Tile>& tiles = out->tiles;
   std::vector<int>& rowid = out->rowid;
   bool& any_sorted = out->any_sorted;
   int& nlong = out->nlong;
   int& nchunks_total = out->nchunks_total;
   tiles.reserve(static_cast<size_t>(rows) / 32 + 16);
-  struct Window { int first_tile, w0, w1, sorted; };
-  std::vector<Window> windows;
   rowid.resize(static_cast<size_t>(rows));
   for (int q = 0; q < rows; ++q) rowid[q] = q;
   const bool sort_rows = getenv("FOLP_NO_ROW_SORT") == nullptr;
@@ -203,7 +235,6 @@ static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<in
     while (r < rows && rowptr[r + 1] - rowptr[r] <= kNarrowMax) r += 1;
     for (int w0 = run0; w0 < r; w0 += kSortWindow) {
       const int w1 = std::min(r, w0 + kSortWindow);
-      windows.push_back(Window{static_cast<int>(tiles.size()), w0, w1, 0});
       // rounds of kGatherUnroll positions the warps spend on this window, identity vs sorted order
       auto rounds = [&](const int* ids) {
         int total = 0;
@@ -223,7 +254,6 @@ static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<in
       for (int b = 0; b <= kNarrowMax; ++b) start[b + 1] += start[b];
       for (int q = w0; q < w1; ++q) ids[start[kNarrowMax - (rowptr[q + 1] - rowptr[q])]++] = q;
       const bool sorted = sort_rows && 8 * rounds(ids) <= 7 * rounds(nullptr);
-      windows.back().sorted = sorted ? 1 : 0;
       if (sorted) {
         any_sorted = true;
         // The groups of a sorted window differ in length by design, and work item i always
@@ -251,45 +281,49 @@ static void pack_matrix(int rows, const std::vector<int>& rowptr, std::vector<in
       }
     }
   }
-  // position-major inside every narrow group (each row keeps its own order). A window's groups
-  // permute the window's own range [rowptr[w0], rowptr[w1]); windows are independent.
-  parallel_for(0, static_cast<int64_t>(windows.size()), 1 << 9, [&](int64_t lo, int64_t hi, int) {
-    std::vector<int> tc;
-    std::vector<double> tv;
-    for (int64_t wi = lo; wi < hi; ++wi) {
-      const Window& w = windows[wi];
-      const int kb = rowptr[w.w0], ke = rowptr[w.w1];
-      tc.assign(colidx.begin() + kb, colidx.begin() + ke);
-      tv.assign(vals.begin() + kb, vals.begin() + ke);
-      int out = kb;
-      for (int g = w.w0; g < w.w1; g += 32) {
-        const int g1 = std::min(w.w1, g + 32);
-        int left = 0;
-        for (int q = g; q < g1; ++q) left += rowptr[rowid[q] + 1] - rowptr[rowid[q]];
-        for (int pos = 0; left > 0; ++pos)
-          for (int q = g; q < g1; ++q) {
-            const int row = rowid[q];
-            if (rowptr[row + 1] - rowptr[row] > pos) {
-              colidx[out] = tc[rowptr[row] - kb + pos];
-              vals[out] = tv[rowptr[row] - kb + pos];
-              ++out;
-              --left;
-            }
-          }
+}
+
+// Writes the packed arrays: position-major inside every narrow group (each row keeps its own
+// ascending order), plain order for wide rows and long-row chunks. Out of place: entry k of the
+// CSR source is read through col(k) / val(k) -- the caller's own Int64 arrays, or scratch.
+template <class GetCol, class GetVal>
+static void fill_packed(const PackedMatrix& pk, const IVec& rowptr, GetCol col, GetVal val,
+                        int* dcol, double* dval) {
+  const std::vector<Tile>& tiles = pk.tiles;
+  const std::vector<int>& rowid = pk.rowid;
+  parallel_for(0, static_cast<int64_t>(tiles.size()), 1 << 11, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t ti = lo; ti < hi; ++ti) {
+      const Tile& t = tiles[ti];
+      const int kind = t.rows_kind >> 16;
+      if (kind != kTileThreadPerRow && kind != kTileThreadPerRowSorted) {
+        for (int k = t.nnz_begin; k < t.nnz_end; ++k) {
+          dcol[k] = col(k);
+          dval[k] = val(k);
+        }
+        continue;
       }
+      const int g = t.row_begin, g1 = g + (t.rows_kind & 0xffff);
+      int out = t.nnz_begin;
+      for (int pos = 0; out < t.nnz_end; ++pos)
+        for (int q = g; q < g1; ++q) {
+          const int row = rowid[q];
+          if (rowptr[row + 1] - rowptr[row] > pos) {
+            const int k = rowptr[row] + pos;
+            dcol[out] = col(k);
+            dval[out] = val(k);
+            ++out;
+          }
+        }
     }
   });
 }
 
 // Uploads a packed matrix.
-static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
-                        const std::vector<int>& rowptr, std::vector<int>& colidx,
-                        std::vector<double>& vals) {
+static int upload_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const IVec& rowptr,
+                         const PackedMatrix& pk, const IVec& colidx, const DVec& vals) {
   M->rows = rows;
   M->cols = cols;
   M->nnz = rowptr[rows];
-  PackedMatrix pk;
-  pack_matrix(rows, rowptr, colidx, vals, h->sm_count * kSpmvCtasPerSm * kSpmvWarps, &pk);
   const std::vector<Tile>& tiles = pk.tiles;
   const std::vector<int>& rowid = pk.rowid;
   const bool any_sorted = pk.any_sorted;
@@ -313,8 +347,8 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
   }
   if ((rc = dev_alloc(h, &M->long_partials, static_cast<size_t>(nchunks_total)))) return rc;
   if ((rc = dev_alloc(h, &M->long_tickets, static_cast<size_t>(nlong)))) return rc;
-  TRY(cudaMemsetAsync(M->colidx, 0, (static_cast<size_t>(M->nnz) + pad) * sizeof(int), h->stream));
-  TRY(cudaMemsetAsync(M->vals, 0, (static_cast<size_t>(M->nnz) + pad) * sizeof(double), h->stream));
+  TRY(cudaMemsetAsync(M->colidx + M->nnz, 0, pad * sizeof(int), h->stream));
+  TRY(cudaMemsetAsync(M->vals + M->nnz, 0, pad * sizeof(double), h->stream));
   TRY(cudaMemsetAsync(M->long_tickets, 0, std::max(nlong, 1) * sizeof(unsigned), h->stream));
   TRY(cudaMemcpyAsync(M->rowptr, rowptr.data(), (static_cast<size_t>(rows) + 1) * sizeof(int),
                       cudaMemcpyHostToDevice, h->stream));
@@ -329,6 +363,18 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols,
                         h->stream));
   TRY(cudaStreamSynchronize(h->stream));  // host vectors die with the caller's scope
   return FOLP_OK;
+}
+
+// plan + pack (from unpacked CSR scratch) + upload
+static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const IVec& rowptr,
+                        const IVec& colidx, const DVec& vals) {
+  PackedMatrix pk;
+  plan_tiles(rows, rowptr, h->sm_count * kSpmvCtasPerSm * kSpmvWarps, &pk);
+  IVec pc(colidx.size());
+  DVec pv(vals.size());
+  fill_packed(pk, rowptr, [&](int k) { return colidx[k]; }, [&](int k) { return vals[k]; }, pc.data(),
+              pv.data());
+  return upload_matrix(h, M, rows, cols, rowptr, pk, pc, pv);
 }
 
 static void free_handle(folp_handle* h) {
@@ -489,6 +535,179 @@ static int setup_peer_exchange(folp_handle* h) {
 // ---------------------------------------------------------------------------
 // folp_create
 // ---------------------------------------------------------------------------
+// CSC (n columns, row index row_of(k), value val_of(k)) -> CSR by a stable two-level counting
+// sort that keeps every write stream cache-friendly:
+//   1. column blocks (one per thread, balanced by nonzeros) are distributed into buckets by ROW
+//      BLOCK (2^S rows, ~1-2 MB of output each); bucket (row block b, thread t) sits at a fixed
+//      offset, so a row block's entries end up contiguous and in ascending column order;
+//   2. row blocks are finished independently: a counting sort by row inside a range that fits
+//      a core's cache.
+// The result does not depend on the thread count. Returns false if a row index is out of range
+// (nothing is written out of bounds).
+template <class RowOf, class ValOf>
+static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, RowOf row_of,
+                             ValOf val_of, IVec* rp2_out, IVec* ci2_out, DVec* v2_out) {
+  IVec& rp2 = *rp2_out;
+  IVec& ci2 = *ci2_out;
+  DVec& v2 = *v2_out;
+  rp2.resize(static_cast<size_t>(m) + 1);
+  ci2.resize(static_cast<size_t>(nnz));
+  v2.resize(static_cast<size_t>(nnz));
+  if (m == 0) { rp2[0] = 0; return nnz == 0; }
+  unsigned hw = std::thread::hardware_concurrency();
+  const int T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, kMaxHostThreadsU),
+                                                   std::max<int64_t>(1, nnz / (1 << 18))));
+  std::vector<int64_t> cut(static_cast<size_t>(T) + 1, n);
+  for (int t = 0; t <= T; ++t) {  // balance the column blocks by nonzeros
+    const int64_t target = nnz * t / T;
+    cut[t] = std::lower_bound(rp.begin(), rp.end(), static_cast<int>(target)) - rp.begin();
+  }
+  cut[0] = 0;
+  cut[T] = n;
+  // rows per block: ~128 K nonzeros of output per block, at most 4096 blocks
+  int S = 0;
+  {
+    const double avg = std::max(1.0, static_cast<double>(nnz) / static_cast<double>(m));
+    while ((int64_t{1} << S) * avg < 131072.0 && (int64_t{1} << S) < m) ++S;
+    while (((m - 1) >> S) + 1 > 4096) ++S;
+  }
+  const int64_t NB = ((m - 1) >> S) + 1;
+  struct Entry { int row, col; double val; };
+  std::vector<Entry, NoInit<Entry>> buf(static_cast<size_t>(nnz));
+  std::vector<int64_t> cnt(static_cast<size_t>(NB) * T, 0);  // [b * T + t]
+  std::atomic<int> bad{0};
+  std::vector<std::thread> th;
+  auto run = [&](auto fn) {
+    for (int t = 0; t < T; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+    th.clear();
+  };
+  run([&](int t) {
+    std::vector<int64_t> c(static_cast<size_t>(NB), 0);
+    for (int64_t k = rp[cut[t]]; k < rp[cut[t + 1]]; ++k) {
+      const int64_t r = row_of(k);
+      if (r < 0 || r >= m) { bad.store(1); return; }
+      c[r >> S] += 1;
+    }
+    for (int64_t b = 0; b < NB; ++b) cnt[b * T + t] = c[b];
+  });
+  if (bad.load()) return false;
+  std::vector<int64_t> block_start(static_cast<size_t>(NB) + 1, 0);
+  {
+    int64_t run_sum = 0;
+    for (int64_t b = 0; b < NB; ++b) {
+      block_start[b] = run_sum;
+      for (int t = 0; t < T; ++t) {
+        const int64_t c = cnt[b * T + t];
+        cnt[b * T + t] = run_sum;  // becomes the write cursor of bucket (b, t)
+        run_sum += c;
+      }
+    }
+    block_start[NB] = run_sum;
+  }
+  run([&](int t) {
+    std::vector<int64_t> cur(static_cast<size_t>(NB));
+    for (int64_t b = 0; b < NB; ++b) cur[b] = cnt[b * T + t];
+    for (int64_t j = cut[t]; j < cut[t + 1]; ++j)
+      for (int64_t k = rp[j]; k < rp[j + 1]; ++k) {
+        const int r = static_cast<int>(row_of(k));
+        buf[cur[r >> S]++] = Entry{r, static_cast<int>(j), val_of(k)};
+      }
+  });
+  std::atomic<int64_t> next_block{0};
+  run([&](int) {
+    IVec hist(static_cast<size_t>(1) << S);
+    for (;;) {
+      const int64_t b = next_block.fetch_add(1);
+      if (b >= NB) break;
+      const int64_t r0 = b << S, r1 = std::min<int64_t>(m, r0 + (int64_t{1} << S));
+      std::fill(hist.begin(), hist.begin() + (r1 - r0), 0);
+      const int64_t e0 = block_start[b], e1 = block_start[b + 1];
+      for (int64_t e = e0; e < e1; ++e) hist[buf[e].row - r0] += 1;
+      int64_t pos = e0;
+      for (int64_t i = r0; i < r1; ++i) {
+        rp2[i] = static_cast<int>(pos);
+        const int c = hist[i - r0];
+        hist[i - r0] = static_cast<int>(pos);
+        pos += c;
+      }
+      for (int64_t e = e0; e < e1; ++e) {
+        const Entry& q = buf[e];
+        const int at = hist[q.row - r0]++;
+        ci2[at] = q.col;
+        v2[at] = q.val;
+      }
+    }
+  });
+  rp2[m] = static_cast<int>(nnz);
+  return true;
+}
+
+// Host half of folp_create on one GPU: A' (= the caller's CSC, read as CSR) is planned and packed
+// straight from the caller's Int64 arrays on a second thread while this one transposes into the
+// CSR of A and packs that. No CUDA call. False if a row index is out of range.
+struct HostMatrices {
+  PackedMatrix pk_t, pk_a;
+  IVec atc, ac, rp2;
+  DVec atv, av;
+};
+static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, int warps_total,
+                                  HostMatrices* out) {
+  const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
+  const int base = p->index_base;
+  const int64_t* src_row = p->rowval;
+  const double* src_val = p->nzval;
+  auto row_of = [=](int64_t k) { return src_row[k] - base; };  // may be out of range until checked
+  auto val_of = [=](int64_t k) { return src_val[k]; };
+  out->atc.resize(static_cast<size_t>(nnz));
+  out->atv.resize(static_cast<size_t>(nnz));
+  out->ac.resize(static_cast<size_t>(nnz));
+  out->av.resize(static_cast<size_t>(nnz));
+  const bool timing = getenv("FOLP_TIMING") != nullptr;
+  const double t0 = now_sec();
+  double t_side_plan = 0, t_side = 0;
+  std::thread side([&] {
+    plan_tiles(static_cast<int>(n), rp, warps_total, &out->pk_t);
+    t_side_plan = now_sec();
+    fill_packed(out->pk_t, rp, [=](int k) { return static_cast<int>(row_of(k)); }, val_of,
+                out->atc.data(), out->atv.data());
+    t_side = now_sec();
+  });
+  IVec ci2;
+  DVec v2;
+  const bool ok = transpose_to_csr(n, m, nnz, rp, row_of, val_of, &out->rp2, &ci2, &v2);
+  const double t1 = now_sec();
+  double t2 = t1;
+  if (ok) {
+    plan_tiles(static_cast<int>(m), out->rp2, warps_total, &out->pk_a);
+    t2 = now_sec();
+    fill_packed(out->pk_a, out->rp2, [&](int k) { return ci2[k]; }, [&](int k) { return v2[k]; },
+                out->ac.data(), out->av.data());
+  }
+  const double t3 = now_sec();
+  side.join();
+  if (timing)
+    fprintf(stderr, "[folp host] main: transpose %.1f, plan A %.1f, pack A %.1f | side: plan A' %.1f, pack A' %.1f ms\n",
+            (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t_side_plan - t0) * 1e3,
+            (t_side - t_side_plan) * 1e3);
+  return ok;
+}
+
+// Test / measurement hook without any CUDA call: the host half of folp_create for one GPU
+// (index conversion, transposition, work-item planning and packing of both matrices);
+// *milliseconds receives its wall-clock time.
+extern "C" int folp_debug_host_prepare(const folp_problem* p, double* milliseconds) {
+  if (!p || !milliseconds) return FOLP_INVALID_ARGUMENT;
+  const int64_t n = p->num_variables, nnz = p->num_nonzeros;
+  const double t0 = now_sec();
+  IVec rp(static_cast<size_t>(n) + 1);
+  for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - p->index_base) : 0;
+  HostMatrices hm;
+  const bool ok = prepare_host_matrices(p, rp, 148 * kSpmvCtasPerSm * kSpmvWarps, &hm);
+  *milliseconds = (now_sec() - t0) * 1e3;
+  return ok ? FOLP_OK : FOLP_INVALID_ARGUMENT;
+}
+
 // FOLP_TIMING=1: wall-clock phases of folp_create on stderr (development aid)
 struct PhaseTimer {
   bool on = getenv("FOLP_TIMING") != nullptr;
@@ -604,88 +823,42 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   const int P = h->world;
   h->row_begin.assign(static_cast<size_t>(P) + 1, 0);
   {
-    std::vector<int> rp(static_cast<size_t>(n) + 1), ci(static_cast<size_t>(nnz));
-    std::vector<double> v(static_cast<size_t>(nnz));
+    IVec rp(static_cast<size_t>(n) + 1);
     for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - base) : 0;
-    std::atomic<int> bad_row{0};
-    parallel_for(0, nnz, 1 << 18, [&](int64_t lo, int64_t hi, int) {
-      for (int64_t k = lo; k < hi; ++k) {
-        const int64_t r = p->rowval[k] - base;
-        if (r < 0 || r >= m) { bad_row.store(1); return; }
-        ci[k] = static_cast<int>(r);
-        v[k] = p->nzval[k];
-      }
-    });
-    if (bad_row.load()) { h->err = "row index out of range"; return FOLP_INVALID_ARGUMENT; }
     for (int64_t j = 0; j < n; ++j)
       if (rp[j] > rp[j + 1] || rp[j] < 0 || rp[j + 1] > nnz) {
         h->err = "colptr is not monotone";
         return FOLP_INVALID_ARGUMENT;
       }
-    pt.mark("index conversion");
-    // transpose
-    std::vector<int> rp2(static_cast<size_t>(m) + 1, 0), ci2(static_cast<size_t>(nnz));
-    std::vector<double> v2(static_cast<size_t>(nnz));
-    {
-      // stable counting sort by row, parallel over column blocks: thread t counts the rows of its
-      // columns, the per-thread offsets are prefix sums over (row, thread), then every thread
-      // scatters its own columns -- ascending j inside each row, independent of the thread count
-      std::vector<int64_t> cut(kMaxHostThreads + 1, n);
-      int T = 0;
-      std::vector<std::vector<int>> hist;
-      {
-        unsigned hw = std::thread::hardware_concurrency();
-        T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u),
-                                               std::max<int64_t>(1, nnz / (1 << 20))));
-        // balance the blocks by nonzeros
-        for (int t = 0; t <= T; ++t) {
-          const int64_t target = nnz * t / T;
-          cut[t] = std::lower_bound(rp.begin(), rp.end(), static_cast<int>(target)) - rp.begin();
-        }
-        cut[0] = 0;
-        cut[T] = n;
-        hist.assign(static_cast<size_t>(T), std::vector<int>());
-      }
-      std::vector<std::thread> th;
-      for (int t = 0; t < T; ++t)
-        th.emplace_back([&, t] {
-          std::vector<int>& hh = hist[t];
-          hh.assign(static_cast<size_t>(m), 0);
-          for (int k = rp[cut[t]]; k < rp[cut[t + 1]]; ++k) hh[ci[k]] += 1;
-        });
-      for (auto& x : th) x.join();
-      th.clear();
-      int64_t run = 0;
-      for (int64_t i = 0; i < m; ++i) {
-        rp2[i] = static_cast<int>(run);
-        for (int t = 0; t < T; ++t) {
-          const int c = hist[t][i];
-          hist[t][i] = static_cast<int>(run);  // becomes thread t's write cursor for row i
-          run += c;
-        }
-      }
-      rp2[m] = static_cast<int>(run);
-      for (int t = 0; t < T; ++t)
-        th.emplace_back([&, t] {
-          std::vector<int>& cur = hist[t];
-          for (int64_t j = cut[t]; j < cut[t + 1]; ++j)
-            for (int k = rp[j]; k < rp[j + 1]; ++k) {
-              const int pos = cur[ci[k]]++;
-              ci2[pos] = static_cast<int>(j);
-              v2[pos] = v[k];
-            }
-        });
-      for (auto& x : th) x.join();
-    }
-    pt.mark("transpose");
+    const int64_t* src_row = p->rowval;
+    const double* src_val = p->nzval;
+    auto row_of = [=](int64_t k) { return src_row[k] - base; };  // may be out of range until checked
+    auto val_of = [=](int64_t k) { return src_val[k]; };
+    const int warps_total = h->sm_count * kSpmvCtasPerSm * kSpmvWarps;
+    IVec rp2, ci2;
+    DVec v2;
     int rc;
     if (P == 1) {
       h->row_begin[1] = m;
       h->n_pad = n; h->m_pad = m;
       h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
-      if ((rc = build_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp, ci, v))) return rc;
-      if ((rc = build_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, ci2, v2))) return rc;
+      HostMatrices hm;
+      if (!prepare_host_matrices(p, rp, warps_total, &hm)) {
+        h->err = "row index out of range";
+        return FOLP_INVALID_ARGUMENT;
+      }
+      pt.mark("transpose + pack (host)");
+      const PackedMatrix &pk_t = hm.pk_t, &pk_a = hm.pk_a;
+      const IVec &atc = hm.atc, &ac = hm.ac, &rp2 = hm.rp2;
+      const DVec &atv = hm.atv, &av = hm.av;
+      if ((rc = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp, pk_t, atc, atv))) return rc;
+      if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, pk_a, ac, av))) return rc;
     } else {
+      if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &v2)) {
+        h->err = "row index out of range";
+        return FOLP_INVALID_ARGUMENT;
+      }
+      pt.mark("transpose");
       std::vector<int64_t> prefix(static_cast<size_t>(m) + 1, 0);
       for (int64_t i = 0; i < m; ++i) prefix[i + 1] = prefix[i] + (rp2[i + 1] - rp2[i]) + 2;
       partition_rows(m, prefix, P, h->row_begin.data());
@@ -702,25 +875,25 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       // A_r: local rows, global columns
       const int k0 = rp2[h->row0], k1 = rp2[row1];
       h->nnz = k1 - k0;
-      std::vector<int> lrp(static_cast<size_t>(h->m) + 1);
+      IVec lrp(static_cast<size_t>(h->m) + 1);
       for (int64_t i = 0; i <= h->m; ++i) lrp[i] = rp2[h->row0 + i] - k0;
-      std::vector<int> lci(ci2.begin() + k0, ci2.begin() + k1);
-      std::vector<double> lv(v2.begin() + k0, v2.begin() + k1);
+      IVec lci(ci2.begin() + k0, ci2.begin() + k1);
+      DVec lv(v2.begin() + k0, v2.begin() + k1);
       if ((rc = build_matrix(h, &h->A, static_cast<int>(h->m), static_cast<int>(n), lrp, lci, lv))) return rc;
       // (A[:, slice])': the local columns of the caller's CSC, i.e. n_local rows of full length.
       // Their column indices (= global rows of A) are remapped into the padded rank-major
       // layout of y_full: row i of rank q -> q * m_pad + (i - row_begin[q]).
       const int64_t c1 = h->col0 + h->n;
       const int t0 = rp[h->col0], t1 = rp[c1];
-      std::vector<int> trp(static_cast<size_t>(h->n) + 1);
+      IVec trp(static_cast<size_t>(h->n) + 1);
       for (int64_t j = 0; j <= h->n; ++j) trp[j] = rp[h->col0 + j] - t0;
-      std::vector<int> owner_off(static_cast<size_t>(m) + 1, 0);  // global row -> padded index
+      IVec owner_off(static_cast<size_t>(m) + 1);  // global row -> padded index
       for (int q = 0; q < P; ++q)
         for (int64_t i = h->row_begin[q]; i < h->row_begin[q + 1]; ++i)
           owner_off[i] = static_cast<int>(q * h->m_pad + (i - h->row_begin[q]));
-      std::vector<int> tci(static_cast<size_t>(t1 - t0));
-      for (int k = t0; k < t1; ++k) tci[k - t0] = owner_off[ci[k]];
-      std::vector<double> tv(v.begin() + t0, v.begin() + t1);
+      IVec tci(static_cast<size_t>(t1 - t0));
+      for (int k = t0; k < t1; ++k) tci[k - t0] = owner_off[row_of(k)];  // rows were range-checked above
+      DVec tv(src_val + t0, src_val + t1);
       if ((rc = build_matrix(h, &h->At, static_cast<int>(h->n), static_cast<int>(P * h->m_pad), trp, tci, tv)))
         return rc;
       h->nnz = (k1 - k0) + (t1 - t0);
@@ -735,8 +908,8 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       h->err = "objective matrix exceeds 32-bit indexing";
       return FOLP_UNSUPPORTED;
     }
-    std::vector<int> qrp(static_cast<size_t>(n) + 1, 0), qci(static_cast<size_t>(qnnz));
-    std::vector<double> qv(static_cast<size_t>(qnnz));
+    IVec qrp(static_cast<size_t>(n) + 1, 0), qci(static_cast<size_t>(qnnz));
+    DVec qv(static_cast<size_t>(qnnz));
     for (int64_t j = 0; j < n; ++j)
       if (p->q_colptr[j] > p->q_colptr[j + 1] || p->q_colptr[j] - base < 0 ||
           p->q_colptr[j + 1] - base > qnnz) {
@@ -749,7 +922,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       qrp[r + 1] += 1;
     }
     for (int64_t i = 0; i < n; ++i) qrp[i + 1] += qrp[i];
-    std::vector<int> cursor(qrp.begin(), qrp.end() - 1);
+    IVec cursor(qrp.begin(), qrp.end() - 1);
     for (int64_t j = 0; j < n; ++j)
       for (int64_t k = p->q_colptr[j] - base; k < p->q_colptr[j + 1] - base; ++k) {
         const int pos = cursor[p->q_rowval[k] - base]++;
@@ -1798,26 +1971,10 @@ extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, dou
   return FOLP_OK;
 }
 
-// Host emulation of k_spmv's traversal of a packed matrix (test hook, no CUDA call): packs the
-// CSR matrix exactly as folp_create does and walks the work items lane by lane with the
-// kernel's slot arithmetic (ballot + popcounts), so that the packing can be checked on a
-// machine without a GPU. y = A * x; stats = {tiles, sorted groups, narrow rounds, long rows}.
-extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr,
-                                    const int64_t* colidx, const double* vals, const double* x,
-                                    double* y, int64_t warps_total, int64_t* stats) {
-  if (rows < 0 || cols < 0 || !rowptr || !y || (rowptr[rows] > 0 && (!colidx || !vals || !x)))
-    return FOLP_INVALID_ARGUMENT;
-  const int64_t nnz = rowptr[rows];
-  if (rows + cols >= (int64_t{1} << 31) - 64 || nnz >= (int64_t{1} << 31) - 64) return FOLP_UNSUPPORTED;
-  std::vector<int> rp(static_cast<size_t>(rows) + 1), ci(static_cast<size_t>(nnz));
-  std::vector<double> v(vals, vals + nnz);
-  for (int64_t i = 0; i <= rows; ++i) rp[i] = static_cast<int>(rowptr[i]);
-  for (int64_t k = 0; k < nnz; ++k) {
-    if (colidx[k] < 0 || colidx[k] >= cols) return FOLP_INVALID_ARGUMENT;
-    ci[k] = static_cast<int>(colidx[k]);
-  }
-  PackedMatrix pk;
-  pack_matrix(static_cast<int>(rows), rp, ci, v, warps_total > 0 ? static_cast<int>(warps_total) : 148 * kSpmvCtasPerSm * kSpmvWarps, &pk);
+// Walks a packed matrix lane by lane with k_spmv's slot arithmetic (host, test hooks only).
+static int emulate_packed_spmv(const PackedMatrix& pk, const IVec& rp, const IVec& ci, const DVec& v,
+                               int64_t rows, const double* x, double* y, int64_t warps_total,
+                               int64_t* stats) {
   int64_t n_sorted = 0, n_rounds = 0;
   const int64_t W = warps_total > 0 ? warps_total : 148 * kSpmvCtasPerSm * kSpmvWarps;
   std::vector<int64_t> warp_rounds(static_cast<size_t>(W), 0);
@@ -1886,6 +2043,45 @@ extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* r
     stats[4] = *std::max_element(warp_rounds.begin(), warp_rounds.end());  // the busiest warp's rounds
   }
   return FOLP_OK;
+}
+
+// Host emulation of k_spmv's traversal of a packed matrix (test hook, no CUDA call): packs the
+// CSR matrix exactly as folp_create does and walks the work items lane by lane with the
+// kernel's slot arithmetic (ballot + popcounts), so that the packing can be checked on a
+// machine without a GPU. y = A * x; stats = {tiles, sorted groups, narrow rounds, long rows}.
+extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr,
+                                    const int64_t* colidx, const double* vals, const double* x,
+                                    double* y, int64_t warps_total, int64_t* stats) {
+  if (rows < 0 || cols < 0 || !rowptr || !y || (rowptr[rows] > 0 && (!colidx || !vals || !x)))
+    return FOLP_INVALID_ARGUMENT;
+  const int64_t nnz = rowptr[rows];
+  if (rows + cols >= (int64_t{1} << 31) - 64 || nnz >= (int64_t{1} << 31) - 64) return FOLP_UNSUPPORTED;
+  IVec rp(static_cast<size_t>(rows) + 1), ci(static_cast<size_t>(nnz));
+  DVec v(static_cast<size_t>(nnz));
+  for (int64_t i = 0; i <= rows; ++i) rp[i] = static_cast<int>(rowptr[i]);
+  for (int64_t k = 0; k < nnz; ++k)
+    if (colidx[k] < 0 || colidx[k] >= cols) return FOLP_INVALID_ARGUMENT;
+  PackedMatrix pk;
+  plan_tiles(static_cast<int>(rows), rp, warps_total > 0 ? static_cast<int>(warps_total) : 148 * kSpmvCtasPerSm * kSpmvWarps, &pk);
+  // packed straight from the caller's Int64 arrays, as folp_create does for A'
+  fill_packed(pk, rp, [=](int k) { return static_cast<int>(colidx[k]); }, [=](int k) { return vals[k]; },
+              ci.data(), v.data());
+  return emulate_packed_spmv(pk, rp, ci, v, rows, x, y, warps_total, stats);
+}
+
+// Test hook without any CUDA call: runs the host half of folp_create on a folp_problem (transposition
+// included) and evaluates y = A * x (transpose == 0, x of length n) or y = A' * x (x of length m)
+// on the host through the packed layouts.
+extern "C" int folp_debug_host_problem_spmv(const folp_problem* p, int transpose, const double* x,
+                                            double* y) {
+  if (!p || !x || !y) return FOLP_INVALID_ARGUMENT;
+  const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
+  IVec rp(static_cast<size_t>(n) + 1);
+  for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - p->index_base) : 0;
+  HostMatrices hm;
+  if (!prepare_host_matrices(p, rp, 148 * kSpmvCtasPerSm * kSpmvWarps, &hm)) return FOLP_INVALID_ARGUMENT;
+  return transpose ? emulate_packed_spmv(hm.pk_t, rp, hm.atc, hm.atv, n, x, y, 0, nullptr)
+                   : emulate_packed_spmv(hm.pk_a, hm.rp2, hm.ac, hm.av, m, x, y, 0, nullptr);
 }
 
 extern "C" void* folp_debug_stream(folp_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }

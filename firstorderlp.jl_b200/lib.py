@@ -24,7 +24,7 @@ _LIB: Optional[C.CDLL] = None
 EXPORTS = [
     "folp_nccl_unique_id", "folp_partition", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
-    "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_host_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
+    "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_host_spmv", "folp_debug_host_prepare", "folp_debug_host_problem_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
 
 
@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.folp_debug_profile_attempts.argtypes = [C.c_void_p, C.c_int64, _pd, C.POINTER(C.c_int64)]
         L.folp_debug_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, _pd]
         L.folp_debug_host_spmv.argtypes = [C.c_int64, C.c_int64, _pi64, _pi64, _pd, _pd, _pd, C.c_int64, _pi64]
+        L.folp_debug_host_prepare.argtypes = [C.POINTER(FolpProblem), _pd]
+        L.folp_debug_host_problem_spmv.argtypes = [C.POINTER(FolpProblem), C.c_int, _pd, _pd]
         L.folp_debug_stream.argtypes = [C.c_void_p]
         L.folp_debug_stream.restype = C.c_void_p
         L.folp_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), _pd, C.POINTER(C.c_int64)]
@@ -119,6 +121,27 @@ def host_packed_spmv(A_csr, x, warps_total: int = 0):
         raise FolpError(rc, "folp_debug_host_spmv")
     return y, dict(zip(("tiles", "sorted_groups", "narrow_rounds", "long_rows", "busiest_warp_rounds"),
                        stats.tolist()))
+
+
+def host_problem_spmv(holder, x, transpose: bool = False) -> np.ndarray:
+    """A * x (or A' * x) on the HOST through folp_create's own host preparation (transposition,
+    planning, packing) of a marshalled problem: no CUDA call."""
+    pr = holder.struct
+    xx = _d(x)
+    y = np.empty(pr.num_variables if transpose else pr.num_constraints, dtype=np.float64)
+    rc = lib().folp_debug_host_problem_spmv(holder.byref(), 1 if transpose else 0, _p(xx), _p(y))
+    if rc != 0:
+        raise FolpError(rc, "folp_debug_host_problem_spmv")
+    return y
+
+
+def host_prepare_ms(holder) -> float:
+    """Wall-clock milliseconds of folp_create's host half (no CUDA call) on a marshalled problem."""
+    ms = C.c_double(0.0)
+    rc = lib().folp_debug_host_prepare(holder.byref(), C.byref(ms))
+    if rc != 0:
+        raise FolpError(rc, "folp_debug_host_prepare")
+    return ms.value
 
 
 def nccl_unique_id() -> bytes:

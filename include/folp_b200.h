@@ -354,6 +354,19 @@ int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr, cons
                          const double* vals, const double* x, double* y, int64_t warps_total,
                          int64_t* stats);
 
+/* Test / measurement hook without any CUDA call: the host half of folp_create on
+ * one GPU (transposition of the caller's CSC into the CSR of A, work-item planning
+ * and position-major packing of both matrices). *milliseconds = its wall-clock
+ * time. FOLP_INVALID_ARGUMENT if a row index is out of range. */
+int folp_debug_host_prepare(const folp_problem* problem, double* milliseconds);
+
+/* Test hook without any CUDA call: the host half of folp_create (transposition
+ * included) followed by y = A * x (transpose == 0; x has n entries, y has m) or
+ * y = A' * x evaluated on the HOST through the packed layouts, as
+ * folp_debug_host_spmv does. */
+int folp_debug_host_problem_spmv(const folp_problem* problem, int transpose, const double* x,
+                                 double* y);
+
 /* The CUDA stream (cudaStream_t) all kernels of this handle are launched on,
  * so a caller can bracket calls with its own events. */
 void* folp_debug_stream(folp_handle* h);

@@ -8,8 +8,10 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from folp_b200.lib import host_packed_spmv
-from folp_b200.synthetic import pagerank_lp, random_sparse_lp
+import folp_b200
+from folp_b200.lib import FolpError, host_packed_spmv, host_problem_spmv
+from folp_b200.synthetic import netlib_shaped_lp, pagerank_lp, random_sparse_lp
+from shared_problems import generate_pdhg_params
 
 
 def _serial(A, x):
@@ -81,3 +83,38 @@ def test_length_sorted_windows_save_rounds_on_poisson_columns(monkeypatch):
     A = random_sparse_lp(20000, 20000, 10, seed=7).constraint_matrix.tocsr()
     _, s = host_packed_spmv(A, np.ones(A.shape[1]))
     assert s["sorted_groups"] == 0
+
+
+@pytest.mark.parametrize("make", [lambda: random_sparse_lp(30000, 20000, 10, seed=9),
+                                  lambda: pagerank_lp(5000), lambda: netlib_shaped_lp(seed=3),
+                                  lambda: random_sparse_lp(300000, 150000, 4, seed=10)])
+def test_host_preparation_of_a_problem(make):
+    """folp_create's host half end to end (parallel two-level transposition of the caller's CSC,
+    planning, packing of A and A') against the serial row sums."""
+    lp = make()
+    params = generate_pdhg_params(l_inf_ruiz_iterations=2)
+    holder, _, scaled = folp_b200.host_setup(params, lp)
+    A = scaled.scaled_qp.constraint_matrix
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(A.shape[1]), rng.standard_normal(A.shape[0])
+    ax = host_problem_spmv(holder, x)
+    aty = host_problem_spmv(holder, y, transpose=True)
+    Ar, Atr = A.tocsr(), A.T.tocsr()
+    if Ar.shape[0] * 10 < 400000:
+        ref_ax, ref_aty = _serial(Ar, x), _serial(Atr, y)
+        narrow_r, narrow_c = np.diff(Ar.indptr) <= 32, np.diff(Atr.indptr) <= 32
+        assert np.array_equal(ax[narrow_r], ref_ax[narrow_r])
+        assert np.array_equal(aty[narrow_c], ref_aty[narrow_c])
+    else:
+        ref_ax, ref_aty = Ar @ x, Atr @ y
+    assert np.max(np.abs(ax - ref_ax)) <= 1e-12 * max(1.0, np.max(np.abs(ref_ax)))
+    assert np.max(np.abs(aty - ref_aty)) <= 1e-12 * max(1.0, np.max(np.abs(ref_aty)))
+
+
+def test_host_preparation_rejects_bad_row_index():
+    lp = random_sparse_lp(50, 40, 3, seed=2)
+    holder, _, _ = folp_b200.host_setup(generate_pdhg_params(), lp)
+    rowval = next(a for a in holder._keep if a.dtype == np.int64 and a.size == lp.constraint_matrix.nnz)
+    rowval[5] = 40  # == m: out of range
+    with pytest.raises(FolpError):
+        host_problem_spmv(holder, np.ones(50))
