@@ -100,6 +100,8 @@ struct folp_handle {
   SpmvMat Q;  // CSR of the scaled objective matrix (QP only; B.has_q)
   Bufs B;
   std::vector<void*> allocs;
+  char* arena = nullptr;  // see arena_reserve
+  size_t arena_cap = 0, arena_used = 0;
   // pinned host mirrors
   DevState* hs = nullptr;
   double* h_red = nullptr;   // 4 * kMaxScalars
@@ -151,14 +153,33 @@ struct folp_handle {
 // ---------------------------------------------------------------------------
 // setup helpers
 // ---------------------------------------------------------------------------
+// One cudaMalloc for (nearly) everything a handle owns: ~60 separate allocations cost tens of
+// milliseconds of folp_create and as many cudaFree calls in folp_destroy. dev_alloc carves
+// 256-byte aligned blocks out of the arena and falls back to cudaMalloc when it is absent or full.
+static int arena_reserve(folp_handle* h, size_t bytes) {
+  if (h->arena || bytes == 0) return FOLP_OK;
+  void* q = nullptr;
+  TRY(cudaMalloc(&q, bytes));
+  h->allocs.push_back(q);
+  h->arena = static_cast<char*>(q);
+  h->arena_cap = bytes;
+  h->arena_used = 0;
+  return FOLP_OK;
+}
 template <class T>
 static int dev_alloc(folp_handle* h, T** p, size_t count) {
   void* q = nullptr;
-  // 16 elements of slack: the staged bulk copies of k_spmv round their extents up
-  // to 16-byte multiples and may read (never use) a few elements past the end
-  TRY(cudaMalloc(&q, (count + 16) * sizeof(T)));
+  // 16 elements of slack: vectorised kernels round their extents up and may read (never use)
+  // a few elements past the end
+  const size_t bytes = ((count + 16) * sizeof(T) + 255) / 256 * 256;
+  if (h->arena && h->arena_used + bytes <= h->arena_cap) {
+    q = h->arena + h->arena_used;
+    h->arena_used += bytes;
+  } else {
+    TRY(cudaMalloc(&q, bytes));
+    h->allocs.push_back(q);
+  }
   TRY(cudaMemsetAsync(static_cast<char*>(q) + count * sizeof(T), 0, 16 * sizeof(T), h->stream));
-  h->allocs.push_back(q);
   *p = static_cast<T*>(q);
   return FOLP_OK;
 }
@@ -848,6 +869,21 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         return FOLP_INVALID_ARGUMENT;
       }
       pt.mark("transpose + pack (host)");
+      {  // device memory of the whole handle in one allocation (sizes: upload_matrix + the vectors below)
+        auto mat_bytes = [](int64_t rows, int64_t nz, const PackedMatrix& pk) {
+          return static_cast<size_t>(4 * (rows + 17) + 12 * (nz + 32) + 32 * (pk.tiles.size() + 16) +
+                                     (pk.any_sorted ? 8 * (rows + 16) : 0) + 8 * (pk.nchunks_total + 16) +
+                                     4 * (pk.nlong + 16) + 8 * 256);
+        };
+        const int64_t qnnz = has_q ? p->q_num_nonzeros : 0;
+        const size_t q_bytes = has_q ? static_cast<size_t>(4 * (n + 17) + 12 * (qnnz + 32) + 32 * (n / 8 + qnnz / kChunkNnz + 64) +
+                                                           8 * (n + 16) + 8 * 256 + 5 * 8 * (n + 48))
+                                     : 0;
+        const size_t vec_bytes = static_cast<size_t>(8) * (19 * (n + 48) + 13 * (m + 48)) +
+                                 sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 16);
+        if ((rc = arena_reserve(h, mat_bytes(n, nnz, hm.pk_t) + mat_bytes(m, nnz, hm.pk_a) + q_bytes + vec_bytes)))
+          return rc;
+      }
       const PackedMatrix &pk_t = hm.pk_t, &pk_a = hm.pk_a;
       const IVec &atc = hm.atc, &ac = hm.ac, &rp2 = hm.rp2;
       const DVec &atv = hm.atv, &av = hm.av;

@@ -380,18 +380,37 @@ struct EpiTransT {
     dp2 += dat * dat;   // pdhg.jl:615 (Malitsky-Pock)
   }
   __device__ void finish(double* sh) {
-    const double a = block_reduce<false>(inter, sh);
-    const double b = block_reduce<false>(dp2, sh);
-    if (threadIdx.x == 0) {
-      part_ptr(B, kSlotTrans, 0)[blockIdx.x] = a;
-      part_ptr(B, kSlotTrans, 1)[blockIdx.x] = b;
+    // sh: 32 doubles. One barrier for both sums: warp leaders park them, threads 0/1 combine.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double wa = warp_sum(inter), wb = warp_sum(dp2);
+    if (lane == 0) {
+      sh[warp] = wa;
+      sh[kSpmvWarps + warp] = wb;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = sh[threadIdx.x * kSpmvWarps];
+      for (int w = 1; w < kSpmvWarps; ++w) t += sh[threadIdx.x * kSpmvWarps + w];
+      part_ptr(B, kSlotTrans, threadIdx.x)[blockIdx.x] = t;
     }
     if (!last_block_arrive(B.counters + kSlotTrans)) return;
-    const double dx2 = reduce_partials<false>(part_ptr(B, kSlotPrimal, 0), g_primal, sh);
-    const double dy2 = reduce_partials<false>(part_ptr(B, kSlotDual, 0), g_dual, sh);
-    const double it = reduce_partials<false>(part_ptr(B, kSlotTrans, 0), gridDim.x, sh);
-    const double dp = reduce_partials<false>(part_ptr(B, kSlotTrans, 1), gridDim.x, sh);
-    const double qd = g_q ? reduce_partials<false>(part_ptr(B, kSlotPrimal, 1), g_q, sh) : 0.0;
+    // The last CTA closes the attempt; this tail is serial time of every iteration, so the five
+    // totals are formed side by side: warp w sums total w over the per-block partials (lanes
+    // stride the blocks in a fixed order, then a shuffle tree).
+    if (warp < 5) {
+      const double* src = warp == 0 ? part_ptr(B, kSlotPrimal, 0)
+                        : warp == 1 ? part_ptr(B, kSlotDual, 0)
+                        : warp == 2 ? part_ptr(B, kSlotTrans, 0)
+                        : warp == 3 ? part_ptr(B, kSlotTrans, 1) : part_ptr(B, kSlotPrimal, 1);
+      const int count = warp == 0 ? g_primal : warp == 1 ? g_dual : warp == 4 ? g_q
+                                                                              : static_cast<int>(gridDim.x);
+      double t = 0.0;
+      for (int j = lane; j < count; j += 32) t += __ldcg(src + j);
+      t = warp_sum(t);
+      if (lane == 0) sh[16 + warp] = t;
+    }
+    __syncthreads();
+    const double dx2 = sh[16], dy2 = sh[17], it = sh[18], dp = sh[19], qd = sh[20];
     if (threadIdx.x != 0) return;
     if (!DIST) {
       finalize_attempt(B.st, dx2, dy2, it, dp, qd);
