@@ -17,3 +17,16 @@ FOLP_TIMING=1 timeout 500 python bench.py > gpurun_out/bench_c2.json 2> gpurun_o
 echo "bench rc=$?"
 cut -c1-1500 gpurun_out/bench_c2.json
 grep -E 'folp_create\]|folp_destroy' gpurun_out/bench_c2.err | tail -24
+if [ -n "$NCU" ]; then
+  # launch list of the default bench workload (cold-cache, serialised per-launch times: shares only)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 700 --csv \
+    --log-file gpurun_out/launches_c2.csv python bench.py --steps 1 --warmup 3 --skip-e2e --skip-cpu \
+    > gpurun_out/ncu_launches.log 2>&1
+  echo "ncu launch list rc=$?"
+  # full capture of the three per-attempt kernels, two launches each
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_spmv|k_primal" -s 3000 -c 6 \
+    -f -o gpurun_out/full_c2 python bench.py --steps 1 --warmup 3 --skip-e2e --skip-cpu \
+    > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full rc=$?"
+  ls -la gpurun_out/
+fi
