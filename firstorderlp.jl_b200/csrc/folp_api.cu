@@ -221,7 +221,7 @@ static void plan_tiles(int rows, const IVec& rowptr, int warps_total, PackedMatr
   rowid.resize(static_cast<size_t>(rows));
   for (int q = 0; q < rows; ++q) rowid[q] = q;
   const bool sort_rows = getenv("FOLP_NO_ROW_SORT") == nullptr;
-  constexpr int kGatherUnrollHost = 4;  // = FOLP_GATHER_UNROLL of folp_spmv.cuh
+  constexpr int kGatherUnrollHost = FOLP_GATHER_UNROLL;  // positions per round of k_spmv
   int r = 0;
   while (r < rows) {
     const int len = rowptr[r + 1] - rowptr[r];
@@ -1131,7 +1131,8 @@ extern "C" const char* folp_build_info(void) {
 #define FOLP_STR2(x) #x
 #define FOLP_STR(x) FOLP_STR2(x)
   return "libfolp_b200;sm_100a;cuda 12.9;fp64;fmad=false;spmv=one row per lane on position-major "
-         "32-row groups, coalesced direct loads, " FOLP_STR(FOLP_SPMV_CTAS_PER_SM) " CTAs of 256 per SM;"
+         "32-row groups (length-sorted windows), coalesced direct loads, " FOLP_STR(FOLP_GATHER_UNROLL)
+         " gathers per lane and round, " FOLP_STR(FOLP_SPMV_CTAS_PER_SM) " CTAs of 256 per SM;"
          "chunk_nnz=" FOLP_STR(FOLP_CHUNK_NNZ);
 }
 
@@ -2045,8 +2046,8 @@ static int emulate_packed_spmv(const PackedMatrix& pk, const IVec& rp, const IVe
         off += __builtin_popcount(m);
       }
       if (off != t.nnz_end) return FOLP_INVALID_ARGUMENT;  // the group's range is exactly consumed
-      n_rounds += (maxlen + 3) / 4;
-      warp_rounds[item % W] += (maxlen + 3) / 4;
+      n_rounds += (maxlen + FOLP_GATHER_UNROLL - 1) / FOLP_GATHER_UNROLL;
+      warp_rounds[item % W] += (maxlen + FOLP_GATHER_UNROLL - 1) / FOLP_GATHER_UNROLL;
       for (int lane = 0; lane < cnt; ++lane) y[row[lane]] = s[lane];
     } else {
       warp_rounds[item % W] += (t.nnz_end - t.nnz_begin + 127) / 128;

@@ -73,6 +73,9 @@ struct DevState {
 #ifndef FOLP_CHUNK_NNZ
 #define FOLP_CHUNK_NNZ 4096
 #endif
+#ifndef FOLP_GATHER_UNROLL
+#define FOLP_GATHER_UNROLL 3
+#endif
 #ifndef FOLP_SPMV_CTAS_PER_SM
 #define FOLP_SPMV_CTAS_PER_SM 4
 #endif

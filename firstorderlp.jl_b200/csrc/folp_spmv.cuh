@@ -22,8 +22,11 @@
 //     for the row sums and measured 15-40 % slower;
 //   * each lane gathers, multiplies and adds in ascending column order in a
 //     register and runs the fused epilogue on its row: no products written back;
-//   * latency is hidden by occupancy (1024 threads per SM, four independent
-//     gathers per lane and round), not by a software pipeline.
+//   * latency is hidden by occupancy (1024 threads per SM, kGatherUnroll independent
+//     gathers per lane and round), not by a software pipeline. Measured on the
+//     1e6 x 1e6 x 1e7 workload (K2 / K3 microseconds): unroll 1: 57.6 / 69.7, 2: 55.7 / 68.2,
+//     3: 55.4 / 65.3, 4: 58.9 / 71.5, 5: 54.5 / 67.4, 6: 55.6 / 65.9; pipelined variants
+//     (FOLP_PIPELINE) 2: 55.9 / 64.7, 3: 57.6 / 66.7, 5: 61.8 / 68.5; 5 CTAs per SM lose.
 // Rows of up to 32 nonzeros are summed by one lane in ascending column order --
 // the summation order of the reference's stdlib kernels -- so such rows are
 // bit-identical to the CPU oracle; longer rows use a warp, rows longer than
@@ -33,9 +36,6 @@
 
 namespace folp {
 
-#ifndef FOLP_GATHER_UNROLL
-#define FOLP_GATHER_UNROLL 4
-#endif
 #ifndef FOLP_PIPELINE
 #define FOLP_PIPELINE 0
 #endif

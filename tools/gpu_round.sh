@@ -28,5 +28,9 @@ if [ -n "$NCU" ]; then
     -f -o gpurun_out/full_c2 python bench.py --steps 1 --warmup 3 --skip-e2e --skip-cpu \
     > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"EpiPlain" -s 10 -c 2 \
+    -f -o gpurun_out/full_plain_c2 python bench.py --steps 1 --warmup 3 --skip-e2e --skip-cpu \
+    > gpurun_out/ncu_full_plain.log 2>&1
+  echo "ncu plain rc=$?"
   ls -la gpurun_out/
 fi
