@@ -664,6 +664,32 @@ static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, 
   return true;
 }
 
+namespace folp {
+void set_create_error(const std::string& msg) { g_create_error = msg; }
+
+// The CSR view of a CSC matrix as a permutation (used by folp_rescale.cu): rowptr (m+1) and, for
+// the k-th entry of the CSR order (rows ascending, columns ascending inside a row), its CSC
+// position perm[k]. False if a row index is out of range.
+bool csr_permutation(int64_t n, int64_t m, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
+                     int base, std::vector<int>* rowptr, std::vector<int>* perm) {
+  IVec rp(static_cast<size_t>(n) + 1);
+  for (int64_t j = 0; j <= n; ++j) rp[j] = static_cast<int>(colptr[j] - base);
+  for (int64_t j = 0; j < n; ++j)
+    if (rp[j] > rp[j + 1] || rp[j] < 0 || rp[j + 1] > nnz) return false;
+  IVec rp2, ci2;
+  DVec pos;
+  auto row_of = [=](int64_t k) { return rowval[k] - base; };
+  auto val_of = [](int64_t k) { return static_cast<double>(k); };  // exact: k < 2^31
+  if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &pos)) return false;
+  rowptr->assign(rp2.begin(), rp2.end());
+  perm->resize(static_cast<size_t>(nnz));
+  parallel_for(0, nnz, 1 << 18, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t k = lo; k < hi; ++k) (*perm)[k] = static_cast<int>(pos[k]);
+  });
+  return true;
+}
+}  // namespace folp
+
 // Host half of folp_create on one GPU: A' (= the caller's CSC, read as CSR) is planned and packed
 // straight from the caller's Int64 arrays on a second thread while this one transposes into the
 // CSR of A and packs that. No CUDA call. False if a row index is out of range.

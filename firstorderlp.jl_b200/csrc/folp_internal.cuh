@@ -185,6 +185,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch (PDL): the three kernels of an attempt are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that the CTAs of the next kernel are
+// placed on SMs as the previous kernel's CTAs retire instead of after its last one has: the launch
+// latency and the ramp of ~600 CTAs leave the critical path. pdl_wait() returns when the
+// previous kernel has completed and its writes are visible -- nothing it produced (DevState
+// included) may be read before; pdl_release() lets the next kernel start being placed. Both are
+// no-ops for a kernel launched without the attribute.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // deterministic block reductions (fixed shape: shuffle tree, then warp 0)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

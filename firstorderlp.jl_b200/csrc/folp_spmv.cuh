@@ -61,6 +61,8 @@ __device__ __forceinline__ TileHot load_hot(const Tile* tiles, int idx) {
 template <class Epi>
 __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A, Epi epi) {
   __shared__ double s_red[32];
+  pdl_wait();
+  pdl_release();
   if (!epi.begin()) return;
   const double* __restrict__ xin = epi.input();
   const int lane = threadIdx.x & 31;

@@ -22,7 +22,7 @@ _pd = C.POINTER(C.c_double)
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
-    "folp_nccl_unique_id", "folp_partition", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
+    "folp_nccl_unique_id", "folp_partition", "folp_rescale_problem", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
     "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_host_spmv", "folp_debug_host_prepare", "folp_debug_host_problem_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
@@ -75,6 +75,9 @@ def lib() -> C.CDLL:
         L.folp_debug_profile_attempts.argtypes = [C.c_void_p, C.c_int64, _pd, C.POINTER(C.c_int64)]
         L.folp_debug_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, _pd]
         L.folp_debug_host_spmv.argtypes = [C.c_int64, C.c_int64, _pi64, _pi64, _pd, _pd, _pd, C.c_int64, _pi64]
+        L.folp_rescale_problem.argtypes = [C.c_int64, C.c_int64, C.c_int32, _pi64, _pi64, _pd, _pi64, _pi64, _pd,
+                                           _pd, _pd, _pd, _pd, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                           _pd, _pd]
         L.folp_debug_host_prepare.argtypes = [C.POINTER(FolpProblem), _pd]
         L.folp_debug_host_problem_spmv.argtypes = [C.POINTER(FolpProblem), C.c_int, _pd, _pd]
         L.folp_debug_stream.argtypes = [C.c_void_p]
@@ -121,6 +124,42 @@ def host_packed_spmv(A_csr, x, warps_total: int = 0):
         raise FolpError(rc, "folp_debug_host_spmv")
     return y, dict(zip(("tiles", "sorted_groups", "narrow_rounds", "long_rows", "busiest_warp_rounds"),
                        stats.tolist()))
+
+
+def rescale_problem(l_inf_ruiz_iterations, l2_norm_rescaling, pock_chambolle_alpha, original_problem,
+                    ruiz_p: int = 0):
+    """rescale_problem (src/preprocess.jl:631-687) on the GPU through folp_rescale_problem.
+    `original_problem` is untouched; returns a ScaledQpProblem like preprocess.rescale_problem."""
+    from .problem import ScaledQpProblem
+    P = original_problem.copy()
+    A, Q = P.constraint_matrix, P.objective_matrix
+    m, n = A.shape
+    _pi64 = C.POINTER(C.c_int64)
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    ix = np.ascontiguousarray(A.indices, dtype=np.int64)
+    data = _d(A.data).copy()
+    if Q.nnz:
+        qip = np.ascontiguousarray(Q.indptr, dtype=np.int64)
+        qix = np.ascontiguousarray(Q.indices, dtype=np.int64)
+        qdata = _d(Q.data).copy()
+        qargs = (qip.ctypes.data_as(_pi64), qix.ctypes.data_as(_pi64), _p(qdata))
+    else:
+        qdata = None
+        qargs = (None, None, None)
+    c, l, u, b = (_d(v).copy() for v in (P.objective_vector, P.variable_lower_bound,
+                                         P.variable_upper_bound, P.right_hand_side))
+    con, var = np.zeros(m), np.zeros(n)
+    alpha = -1.0 if pock_chambolle_alpha is None else float(pock_chambolle_alpha)
+    rc = lib().folp_rescale_problem(m, n, 0, ip.ctypes.data_as(_pi64), ix.ctypes.data_as(_pi64), _p(data),
+                                    *qargs, _p(c), _p(l), _p(u), _p(b), int(l_inf_ruiz_iterations),
+                                    int(ruiz_p), int(bool(l2_norm_rescaling)), alpha, _p(con), _p(var))
+    if rc != 0:
+        raise FolpError(rc, lib().folp_last_error(None).decode())
+    A.data[:] = data
+    if qdata is not None:
+        Q.data[:] = qdata
+    P.objective_vector, P.variable_lower_bound, P.variable_upper_bound, P.right_hand_side = c, l, u, b
+    return ScaledQpProblem(original_problem, P, con, var)
 
 
 def host_problem_spmv(holder, x, transpose: bool = False) -> np.ndarray:

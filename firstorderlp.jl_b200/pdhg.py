@@ -57,10 +57,17 @@ def estimate_maximum_singular_value(matrix, probability_of_failure=0.001,
 
 
 def host_setup(params: PdhgParameters, original_problem: QuadraticProgrammingProblem,
-               scaled: Optional[ScaledQpProblem] = None):
-    """pdhg.jl:786-859 -> (ProblemHolder, FolpParams, ScaledQpProblem)."""
+               scaled: Optional[ScaledQpProblem] = None, device_rescaling: bool = False):
+    """pdhg.jl:786-859 -> (ProblemHolder, FolpParams, ScaledQpProblem).
+
+    device_rescaling: rescale_problem (preprocess.jl:631-687) runs on the GPU through
+    folp_rescale_problem instead of the host mirror (same arithmetic)."""
     validate(original_problem)
     cache = cached_quadratic_program_info(original_problem)
+    if scaled is None and device_rescaling:
+        from .lib import rescale_problem as device_rescale_problem
+        scaled = device_rescale_problem(params.l_inf_ruiz_iterations, params.l2_norm_rescaling,
+                                        params.pock_chambolle_alpha, original_problem)
     if scaled is None:
         scaled = rescale_problem(params.l_inf_ruiz_iterations, params.l2_norm_rescaling,
                                  params.pock_chambolle_alpha, params.verbosity, original_problem)
@@ -84,8 +91,9 @@ def host_setup(params: PdhgParameters, original_problem: QuadraticProgrammingPro
     return holder, fparams, scaled
 
 
-def optimize(params: PdhgParameters, original_problem: QuadraticProgrammingProblem) -> SaddlePointOutput:
-    holder, fparams, _ = host_setup(params, original_problem)
+def optimize(params: PdhgParameters, original_problem: QuadraticProgrammingProblem,
+             device_rescaling: bool = False) -> SaddlePointOutput:
+    holder, fparams, _ = host_setup(params, original_problem, device_rescaling=device_rescaling)
     with Solver(holder, fparams) as solver:
         x, y, reason, iters, evals = solver.solve()
     stats = [iteration_stats_from_eval(e) for e in evals]

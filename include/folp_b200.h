@@ -354,6 +354,27 @@ int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* rowptr, cons
                          const double* vals, const double* x, double* y, int64_t warps_total,
                          int64_t* stats);
 
+/* rescale_problem (src/preprocess.jl:631-687) computed on the current CUDA device
+ * (SURVEY.md section 8f-1): Ruiz rescaling in the infinity norm (ruiz_p = 0) or
+ * the 2-norm (ruiz_p = 2) (:412-477), l2-norm rescaling (:358-372) and
+ * Pock-Chambolle rescaling (:508-539; pock_chambolle_alpha < 0 = nothing), applied
+ * in that order. Same contract as the reference function on a copied problem: the
+ * CSC values of A (and Q, q_colptr may be NULL for an LP) and the vectors c, l, u, b
+ * are rescaled IN PLACE (scale_problem, :555-573), and the cumulative
+ * constraint_rescaling (m) / variable_rescaling (n) come back, from which the
+ * host forms ScaledQpProblem(original, scaled, constraint_rescaling,
+ * variable_rescaling). Indices are Int64 with index_base 0 or 1. Bit-identical to
+ * the reference arithmetic for rows and columns of up to 2048 entries and
+ * pock_chambolle_alpha = 1 (other exponents go through pow); see folp_rescale.cu. */
+int folp_rescale_problem(int64_t num_constraints, int64_t num_variables, int32_t index_base,
+                         const int64_t* colptr, const int64_t* rowval, double* nzval,
+                         const int64_t* q_colptr, const int64_t* q_rowval, double* q_nzval,
+                         double* objective_vector, double* variable_lower_bound,
+                         double* variable_upper_bound, double* right_hand_side,
+                         int32_t l_inf_ruiz_iterations, int32_t ruiz_p, int32_t l2_norm_rescaling,
+                         double pock_chambolle_alpha, double* constraint_rescaling,
+                         double* variable_rescaling);
+
 /* Test / measurement hook without any CUDA call: the host half of folp_create on
  * one GPU (transposition of the caller's CSC into the CSR of A, work-item planning
  * and position-major packing of both matrices). *milliseconds = its wall-clock

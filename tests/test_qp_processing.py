@@ -86,6 +86,11 @@ def test_recover_original_solution_and_presolve():  # :162-209
     assert qp.constraint_matrix.shape == (3, 3)
 
 
+# further rescale_problem implementations that must agree bit for bit with the two above:
+# tests/test_gpu_rescale.py runs every test of this file with folp_rescale_problem in the list
+EXTRA_RESCALERS = []
+
+
 def _both(problem, ruiz, l2, alpha, ruiz_p=np.inf):
     """(scaled problem, con, var) from the host mirror and from the oracle; asserts they agree
     bit for bit."""
@@ -104,6 +109,11 @@ def _both(problem, ruiz, l2, alpha, ruiz_p=np.inf):
     assert np.array_equal(o.constraint_rescaling, con)
     assert np.array_equal(o.variable_rescaling, var)
     _assert_problem(o.scaled_qp, p, approx=False)
+    for fn in EXTRA_RESCALERS:
+        g = fn(ruiz, l2, alpha, problem, ruiz_p=0 if ruiz_p == np.inf else 2)
+        assert np.array_equal(g.constraint_rescaling, con)
+        assert np.array_equal(g.variable_rescaling, var)
+        _assert_problem(g.scaled_qp, p, approx=False)
     return p, con, var
 
 
