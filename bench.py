@@ -254,8 +254,10 @@ def bench_gpu(args):
 
     # ---- cpu baseline: the oracle on a bounded sample of the same workload (rank 0, N = 1 only) ----
     cpu = None
+    rescale = None
     if not args.skip_cpu and world == 1:
         cpu = cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
+        rescale = rescale_timing(params, lp)
 
     line = {
         "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
@@ -278,7 +280,7 @@ def bench_gpu(args):
                    "final_relative_l2_primal_residual": e.relative_l2_primal_residual,
                    "final_l2_primal_residual": e.l2_primal_residual,
                    "final_l2_dual_residual": e.l2_dual_residual,
-                   "folp_create_seconds": t_create, "build": build_info()},
+                   "folp_create_seconds": t_create, "rescale_problem": rescale, "build": build_info()},
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -305,6 +307,29 @@ def cpu_baseline(params, lp, scaled, sample_iters):
             "sample": f"iterations 40..{40 + sample_iters} of the same problem and parameters "
                       f"({sample_iters // 40} evaluation/restart blocks included), {dt:.1f}s",
             "host_cores_available": os.cpu_count()}
+
+
+def rescale_timing(params, lp):
+    """rescale_problem (src/preprocess.jl:631-687), the step before the loop: the
+    device path (folp_rescale_problem, host arrays in and out) next to the oracle's C restatement
+    (one thread, as the reference). Outside every timed region of the headline metric."""
+    from folp_b200.lib import rescale_problem as device_rescale
+    from oracle import oracle
+
+    args_ = (params.l_inf_ruiz_iterations, params.l2_norm_rescaling, params.pock_chambolle_alpha, lp)
+    device_rescale(*args_)  # warm-up (module load)
+    t0 = time.perf_counter()
+    g = device_rescale(*args_)
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o = oracle.rescale_problem(*args_)
+    t_cpu = time.perf_counter() - t0
+    same = bool(np.array_equal(g.scaled_qp.constraint_matrix.data, o.scaled_qp.constraint_matrix.data)
+                and np.array_equal(g.variable_rescaling, o.variable_rescaling)
+                and np.array_equal(g.constraint_rescaling, o.constraint_rescaling))
+    return {"device_seconds": t_dev, "oracle_seconds_1_thread": t_cpu, "bit_identical": same,
+            "what": "ruiz %d + l2 %s + pock-chambolle %s, host arrays in / out" % (
+                params.l_inf_ruiz_iterations, params.l2_norm_rescaling, params.pock_chambolle_alpha)}
 
 
 def bench_reference(args):
