@@ -63,9 +63,9 @@ struct DevState {
 //   sorted group  the same, but its rows were picked from a window of kSortWindow consecutive
 //                 narrow rows in order of decreasing length (rowid[slot] names the row of
 //                 a slot), so that the 32 lanes of a warp run out of nonzeros together.
-//                 Only windows where that saves rounds are sorted (columns of a random
-//                 matrix, power-law degrees); the others keep the identity order and never
-//                 read rowid. A row's own nonzeros keep their ascending column order.
+//                 Only windows whose rounds at least halve are sorted (a few long rows among
+//                 many short ones); the others keep the identity order and never read
+//                 rowid. A row's own nonzeros keep their ascending column order.
 //   wide row      one row of 33 .. kChunkNnz nonzeros, plain CSR order, one warp.
 //   long chunk    kChunkNnz nonzeros of a longer row; the partial sums are combined in
 //                 chunk order by the last chunk to finish (deterministic).

@@ -45,7 +45,7 @@ def _ragged(seed, rows=3000, n=5000):
     lambda: random_sparse_lp(4000, 3000, 10, seed=5).constraint_matrix.T.tocsr(),     # Poisson columns: sorted
     lambda: pagerank_lp(3000).constraint_matrix.T.tocsr(),                            # power-law + dense row
     lambda: pagerank_lp(3000).constraint_matrix.tocsr(),
-    lambda: _ragged(1), lambda: _ragged(2, rows=257), lambda: sp.csr_matrix((5, 7)),
+    lambda: _ragged(1), lambda: _ragged(2, rows=257), lambda: sp.csr_matrix((5, 7)), lambda: _heavy_tailed(3, 3000, 4000),
     lambda: sp.csr_matrix(np.ones((1, 40))),
 ])
 def test_packed_layout_reproduces_serial_row_sums(make):
@@ -61,28 +61,39 @@ def test_packed_layout_reproduces_serial_row_sums(make):
     assert stats["long_rows"] == int((row_len > 4096).sum())
 
 
-def test_length_sorted_windows_save_rounds_on_poisson_columns(monkeypatch):
-    At = random_sparse_lp(20000, 20000, 10, seed=7).constraint_matrix.T.tocsr()
-    x = np.ones(At.shape[1])
-    y1, s1 = host_packed_spmv(At, x)
+def _heavy_tailed(seed=7, rows=20000, n=20000):  # noqa: E302
+    """Most rows have 2 entries, one in ten has 30: in place every group of 32 runs 30 positions."""
+    rng = np.random.default_rng(seed)
+    lens = np.where(rng.random(rows) < 0.1, 30, 2)
+    ind = np.concatenate([np.sort(rng.choice(n, size=int(k), replace=False)) for k in lens])
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    return sp.csr_matrix((rng.standard_normal(ind.size), ind, ptr), shape=(rows, n))
+
+
+def test_length_sorted_windows_on_heavy_tailed_rows(monkeypatch):
+    M = _heavy_tailed()
+    x = np.random.default_rng(1).standard_normal(M.shape[1])
+    y1, s1 = host_packed_spmv(M, x)
     monkeypatch.setenv("FOLP_NO_ROW_SORT", "1")
-    y0, s0 = host_packed_spmv(At, x)
+    y0, s0 = host_packed_spmv(M, x)
     monkeypatch.delenv("FOLP_NO_ROW_SORT")
-    assert np.array_equal(y0, y1)
+    assert np.array_equal(y0, y1) and np.array_equal(y1, _serial(M, x))
     assert s0["sorted_groups"] == 0 and s1["sorted_groups"] > 0
-    assert s1["narrow_rounds"] <= 0.8 * s0["narrow_rounds"]
+    assert s1["narrow_rounds"] <= 0.5 * s0["narrow_rounds"]
     # ... and the groups are dealt to the warps in rotation: the busiest warp gains as well
     # (a grid of 64 warps here, so that every warp makes several trips)
-    _, r1 = host_packed_spmv(At, x, warps_total=64)
+    _, r1 = host_packed_spmv(M, x, warps_total=64)
     monkeypatch.setenv("FOLP_NO_ROW_SORT", "1")
-    _, r0 = host_packed_spmv(At, x, warps_total=64)
+    _, r0 = host_packed_spmv(M, x, warps_total=64)
     monkeypatch.delenv("FOLP_NO_ROW_SORT")
-    assert r1["busiest_warp_rounds"] <= 0.8 * r0["busiest_warp_rounds"]
-    assert r1["busiest_warp_rounds"] <= 1.2 * r1["narrow_rounds"] / 64
-    # rows of (almost) equal length keep the identity order: no indirection for A itself
-    A = random_sparse_lp(20000, 20000, 10, seed=7).constraint_matrix.tocsr()
-    _, s = host_packed_spmv(A, np.ones(A.shape[1]))
-    assert s["sorted_groups"] == 0
+    assert r1["busiest_warp_rounds"] <= 0.6 * r0["busiest_warp_rounds"]
+    assert r1["busiest_warp_rounds"] <= 2.0 * r1["narrow_rounds"] / 64
+    # mild imbalance (Poisson(10) columns of a random matrix, rows of ~10) stays in place: measured
+    # on the B200 the scattered epilogue costs more than the saved rounds
+    lp = random_sparse_lp(20000, 20000, 10, seed=7)
+    for Mx in (lp.constraint_matrix.tocsr(), lp.constraint_matrix.T.tocsr()):
+        _, s = host_packed_spmv(Mx, np.ones(Mx.shape[1]))
+        assert s["sorted_groups"] == 0
 
 
 @pytest.mark.parametrize("make", [lambda: random_sparse_lp(30000, 20000, 10, seed=9),
