@@ -174,7 +174,11 @@ def test_row_partitioned_attempt_gloo_world2():
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    world, port = 2, 29631
+    import socket
+    with socket.socket() as sock:  # a free port: a fixed one may still be in TIME_WAIT from the last run
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    world = 2
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
