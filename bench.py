@@ -37,8 +37,9 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the two k_spmv launches of an
-# iteration, from the committed `ncu --set full` capture (profiles/r01_ncu_full_c2_summary.csv)
-TRAFFIC_NCU = {"c2": 162.2e6 + 164.0e6}
+# iteration, from the committed `ncu --set full` capture (profiles/r01b_ncu_full_c2_summary.csv:
+# K2 157.0 + 7.6 MB, K3 157.1 + 4.9 MB; algorithmic 172.0 + 164.0 MB)
+TRAFFIC_NCU = {"c2": 164.6e6 + 162.0e6}
 
 
 def log(*a):
