@@ -174,7 +174,34 @@ def case_artificial_restart_cadence(optimize):
 
 
 # (id, function, kwargs, needs a quadratic objective)
+def case_config1_trivial_mps(optimize):
+    """BASELINE.json configs[0]: the two-variable MPS model read from disk and solved with the CLI
+    defaults (scripts/solve_qp.jl:193-472, --iteration_limit 5000 as in README.md:54-57), the summary
+    written the way scripts/solve_qp.jl:115-141 writes it. min 2x - y, x + y <= 3, 0 <= x <= 1,
+    1 <= y <= 2  ->  (x, y) = (0, 2), objective -2, the constraint is slack."""
+    import json
+    import os
+    import tempfile
+
+    import folp_b200
+    from folp_b200 import io as fio
+    here = os.path.dirname(os.path.abspath(__file__))
+    lp = fio.qps_reader_to_standard_form(os.path.join(here, "golden", "trivial_lp_model.mps"))
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.iteration_limit = 5000
+    out = optimize(params, lp)
+    assert out.termination_reason == TerminationReason.TERMINATION_REASON_OPTIMAL
+    _close(out.primal_solution, [0.0, 2.0], 1e-5)
+    _close(out.dual_solution, [0.0], 1e-5)
+    with tempfile.TemporaryDirectory() as d:
+        summary, _ = fio.write_solve_log_json(d, "trivial_lp_model", out, 0.0)
+        log = json.load(open(summary))
+    assert log["termination_reason"] == "TERMINATION_REASON_OPTIMAL" and log["termination_string"] == "OPTIMAL"
+    assert abs(log["solution_stats"]["convergence_information"][0]["primal_objective"] + 2.0) <= 1e-5
+
+
 CASES = [
+    ("config1_trivial_mps", case_config1_trivial_mps, {}, False),
     ("low_precision", case_low_precision, {}, False),
     ("terminate_with_optimal_solution", case_terminate_with_optimal_solution, {}, False),
     ("fixed_frequency_restart", case_fixed_frequency_restart, {}, False),
