@@ -1424,21 +1424,33 @@ static int tr_round(folp_handle* h, const TrProblem& P, int passes, bool init) {
   return FOLP_OK;
 }
 
+// The search was abandoned on non-finite data (a diverged iterate: e.g. the constant step size of
+// pdhg.jl:826-836 ignores Q). The reference's median search returns NaN bounds there and the solve
+// carries on to its limits; so does this one.
+static void tr_abandoned(TrState* t) {
+  t->tau = NAN;
+  t->v_primal = NAN;
+  t->v_dual = NAN;
+}
+
 static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
   int rc;
   if (h->tr_grid > 0) {  // single GPU: one cooperative kernel, one host read
-    TRY(static_cast<cudaError_t>(launch_tr_solve(h->B, P, h->d_trs, h->tr_grid, h->stream)));
-    h->launches += 1;
-    h->tr_solves += 1;
-    TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState), cudaMemcpyDeviceToHost, h->stream));
-    TRY(cudaStreamSynchronize(h->stream));
-    if (h->h_trs->done != 1) {
-      h->err = "trust-region search did not converge";
-      return FOLP_CUDA_ERROR;
+    const cudaError_t le = static_cast<cudaError_t>(launch_tr_solve(h->B, P, h->d_trs, h->tr_grid, h->stream));
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
+      cudaGetLastError();  // the device is shared (MPS partition, ...): kernel-per-pass form from now on
+      h->tr_grid = 0;
+    } else {
+      TRY(le);
+      h->launches += 1;
+      h->tr_solves += 1;
+      TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState), cudaMemcpyDeviceToHost, h->stream));
+      TRY(cudaStreamSynchronize(h->stream));
+      *out = *h->h_trs;
+      h->tr_passes += out->passes;
+      if (out->done != 1) tr_abandoned(out);
+      return FOLP_OK;
     }
-    *out = *h->h_trs;
-    h->tr_passes += out->passes;
-    return FOLP_OK;
   }
   if ((rc = tr_round(h, P, h->world == 1 ? 10 : 6, true))) return rc;
   h->tr_solves += 1;
@@ -1447,8 +1459,9 @@ static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
     TRY(cudaStreamSynchronize(h->stream));
     if (h->h_trs->done) break;
     if (round > 40) {
-      h->err = "trust-region search did not converge";
-      return FOLP_CUDA_ERROR;
+      *out = *h->h_trs;
+      tr_abandoned(out);
+      return FOLP_OK;
     }
     if ((rc = tr_round(h, P, h->world == 1 ? 16 : 6, false))) return rc;
   }

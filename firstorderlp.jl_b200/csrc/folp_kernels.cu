@@ -1290,7 +1290,7 @@ __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, Tr
     if (threadIdx.x == 0) {
       tr_update(&st, tot);
       // non-finite data (a diverged iterate) can keep the partition changing for ever
-      if (!st.done && st.passes >= 400) { st.done = 2; st.zero_value = 1; }
+      if (!st.done && st.passes >= 120) { st.done = 2; st.zero_value = 1; }
     }
     __syncthreads();
   }

@@ -275,6 +275,23 @@ def test_eval_records_match_oracle_qp(scheme, policy):
     assert records == 10 + 14
 
 
+def test_diverging_iterates_run_to_the_limit_like_the_reference():
+    """The constant step 0.8 / sigma_max(A) ignores Q: with |Q| ~ |A| the reference's own iteration
+    blows up (1e240 after 120 iterations, NaN bounds) and simply runs into its iteration limit.
+    The library must do the same -- no error, no hang."""
+    problem = random_sparse_qp(1200, 900, 6, seed=33, upper_fraction=0.1)
+    params = generate_pdhg_params(iteration_limit=120, l_inf_ruiz_iterations=10, pock_chambolle_alpha=1.0,
+                                  restart_scheme=RestartScheme.ADAPTIVE_LOCALIZED, step_size_policy="constant")
+    params.termination_evaluation_frequency = 8
+    out_o = oracle.optimize(params, problem)
+    out_g = folp_b200.optimize(params, problem)
+    assert out_g.termination_reason == out_o.termination_reason == \
+        TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
+    assert out_g.iteration_count == out_o.iteration_count == 120
+    fin = out_g.iteration_stats[-1].convergence_information[0]
+    assert not np.isfinite(fin.primal_objective) or abs(fin.primal_objective) > 1e100
+
+
 def test_qp_full_solve_matches_oracle():
     """A QP solved to 1e-6 with the CLI defaults: same reason, and the GPU-reported KKT record
     equals the oracle's evaluation of the GPU's returned point."""
