@@ -31,6 +31,7 @@ WORKLOADS = {
     # name: (n, m, nnz_per_row)
     "c2": (1_000_000, 1_000_000, 10),      # BASELINE.json configs[1]
     "target": (10_000_000, 10_000_000, 10),  # north_star target size
+    "mid": (4_000_000, 4_000_000, 10),      # between the two: where the 1-D partition starts to pay
     "small": (100_000, 100_000, 10),
     "half": (1_000_000, 500_000, 10),       # one rank's row block of c2 at 2 GPUs
 }
