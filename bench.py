@@ -47,6 +47,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout. Libraries print there too (NCCL's "NCCL version ..."
+# banner at the first communicator, for one): file descriptor 1 is pointed at stderr for the whole
+# run and the line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def make_problem(workload):
     import folp_b200
     from folp_b200.synthetic import random_sparse_lp
@@ -285,7 +305,7 @@ def bench_gpu(args):
                    "folp_create_seconds": t_create, "rescale_problem": rescale, "build": build_info()},
     }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as td
         td.barrier()
@@ -372,7 +392,7 @@ def bench_reference(args):
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -387,6 +407,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only (ncu)")
     args = ap.parse_args()
+    _capture_stdout()
     if args.warmup < 3 and args.impl != "reference":
         log("[bench] warning: fewer than 3 warm-up steps")
     if args.impl == "reference":
