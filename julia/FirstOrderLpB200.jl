@@ -172,24 +172,69 @@ function to_iteration_stats(e::FolpEval)
 end
 
 """
+Drop-in for `FirstOrderLp.rescale_problem` (src/preprocess.jl:631-687) computed on the
+device by `folp_rescale_problem`: the copied problem's arrays are rescaled in place, the
+cumulative rescaling vectors come back. Same arithmetic and summation order as the
+reference (bit-identical for rows / columns of up to 2048 entries and alpha = 1).
+"""
+function rescale_problem_b200(
+  l_inf_ruiz_iterations::Int64,
+  l2_norm_rescaling::Bool,
+  pock_chambolle_alpha::Union{Float64,Nothing},
+  original_problem::FirstOrderLp.QuadraticProgrammingProblem,
+)
+  p = deepcopy(original_problem)
+  A, Q = p.constraint_matrix, p.objective_matrix
+  m, n = size(A)
+  con = Vector{Float64}(undef, m)
+  var = Vector{Float64}(undef, n)
+  GC.@preserve p con var begin
+    rc = ccall(
+      (:folp_rescale_problem, LIB),
+      Cint,
+      (
+        Int64, Int64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+        Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Float64,
+        Ptr{Float64}, Ptr{Float64},
+      ),
+      m, n, Int32(1), A.colptr, A.rowval, A.nzval, Q.colptr, Q.rowval, Q.nzval,
+      p.objective_vector, p.variable_lower_bound, p.variable_upper_bound, p.right_hand_side,
+      Int32(l_inf_ruiz_iterations), Int32(0), Int32(l2_norm_rescaling),
+      pock_chambolle_alpha === nothing ? -1.0 : pock_chambolle_alpha, con, var,
+    )
+  end
+  rc == 0 || error(unsafe_string(ccall((:folp_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+  return FirstOrderLp.ScaledQpProblem(original_problem, p, con, var)
+end
+
+"""
 Drop-in for `FirstOrderLp.optimize(params::PdhgParameters, qp)`
 (src/primal_dual_hybrid_gradient.jl:782): same arguments, same
 `SaddlePointOutput`.
 """
 function optimize_b200(
   params::FirstOrderLp.PdhgParameters,
-  original_problem::FirstOrderLp.QuadraticProgrammingProblem,
+  original_problem::FirstOrderLp.QuadraticProgrammingProblem;
+  device_rescaling::Bool = false,
 )
   # ---- host half, unchanged (pdhg.jl:786-859) ----
   FirstOrderLp.validate(original_problem)
   qp_cache = FirstOrderLp.cached_quadratic_program_info(original_problem)
-  scaled_problem = FirstOrderLp.rescale_problem(
-    params.l_inf_ruiz_iterations,
-    params.l2_norm_rescaling,
-    params.pock_chambolle_alpha,
-    params.verbosity,
-    original_problem,
-  )
+  scaled_problem =
+    device_rescaling ?
+    rescale_problem_b200(
+      params.l_inf_ruiz_iterations,
+      params.l2_norm_rescaling,
+      params.pock_chambolle_alpha,
+      original_problem,
+    ) :
+    FirstOrderLp.rescale_problem(
+      params.l_inf_ruiz_iterations,
+      params.l2_norm_rescaling,
+      params.pock_chambolle_alpha,
+      params.verbosity,
+      original_problem,
+    )
   problem = scaled_problem.scaled_qp
   if params.primal_importance <= 0 || !isfinite(params.primal_importance)
     error("primal_importance must be positive and finite")
