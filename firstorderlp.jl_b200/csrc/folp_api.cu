@@ -848,8 +848,10 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     return FOLP_UNSUPPORTED;
   }
   h->sm_count = prop.multiProcessorCount;
-  if (!(dist && dist->world_size > 1) && prop.cooperativeLaunch && getenv("FOLP_TR_MULTIKERNEL") == nullptr)
-    h->tr_grid = tr_solve_grid(h->sm_count);
+  // one cooperative kernel per trust-region solve: single GPU, and the partitioned mode once the
+  // peer-memory exchange is up (decided after setup_peer_exchange below)
+  const bool tr_coop = prop.cooperativeLaunch && getenv("FOLP_TR_MULTIKERNEL") == nullptr;
+  if (tr_coop) h->tr_grid = tr_solve_grid(h->sm_count);
   TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TRY(cudaEventCreate(&h->ev0));
   TRY(cudaEventCreate(&h->ev1));
@@ -1040,6 +1042,8 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     if ((rc = dev_zeros(h, &h->d_rows, fy))) return rc;
     if ((rc = dev_zeros(h, &h->d_cols, fx))) return rc;
     if ((rc = setup_peer_exchange(h))) return rc;
+    // the cooperative trust-region kernel exchanges its scalars through peer memory
+    if (!B.p2p || getenv("FOLP_DIST_TR_MULTIKERNEL") != nullptr) h->tr_grid = 0;
   }
   if ((rc = dev_upload(h, &B.c, at(p->objective_vector, c0), nl, 0.0))) return rc;
   if ((rc = dev_upload(h, &B.l, at(p->variable_lower_bound, c0), nl, 0.0))) return rc;
@@ -1436,7 +1440,8 @@ static void tr_abandoned(TrState* t) {
 static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
   int rc;
   if (h->tr_grid > 0) {  // single GPU: one cooperative kernel, one host read
-    const cudaError_t le = static_cast<cudaError_t>(launch_tr_solve(h->B, P, h->d_trs, h->tr_grid, h->stream));
+    const cudaError_t le = static_cast<cudaError_t>(
+        launch_tr_solve(h->B, P, h->d_trs, h->tr_grid, h->xchg_seq + 1, h->stream));
     if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
       cudaGetLastError();  // the device is shared (MPS partition, ...): kernel-per-pass form from now on
       h->tr_grid = 0;
@@ -1448,6 +1453,15 @@ static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
       TRY(cudaStreamSynchronize(h->stream));
       *out = *h->h_trs;
       h->tr_passes += out->passes;
+      h->xchg_seq += static_cast<unsigned long long>(out->exchanges);  // same count on every rank
+      if (h->world > 1) {
+        unsigned timed_out = 0;
+        TRY(cudaMemcpy(&timed_out, h->B.counters + 6, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (timed_out) {
+          h->err = "peer exchange timed out: a rank of the row partition stopped responding";
+          return FOLP_CUDA_ERROR;
+        }
+      }
       if (out->done != 1) tr_abandoned(out);
       return FOLP_OK;
     }

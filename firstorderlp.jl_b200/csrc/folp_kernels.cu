@@ -1179,13 +1179,25 @@ constexpr int kTrThreads = 256;
 constexpr int kTrWarps = kTrThreads / 32;
 constexpr int kTrMaxK = 16;
 
+// Cross-rank part of grid_totals (partitioned mode over peer memory): block 0 pushes this rank's
+// totals into slot `rank` of every rank's receive buffer (parity = seq & 1, the convention of
+// k_exchange), raises flag kind 3 to seq and waits for every rank's; after a second grid barrier
+// every block of every rank combines the same world x K numbers in rank order -- identical bits
+// everywhere. Two receive buffers suffice: a rank cannot start exchange e+2 before every rank has
+// consumed exchange e (it needs their flags of e+1, raised after that).
+struct TrXchg {
+  unsigned long long seq;  // number of the next exchange (host: folp_handle::xchg_seq + 1)
+  int count;               // exchanges done by this kernel
+};
+
 // totals of K per-thread values over the whole grid -> tot[0..K) (shared memory, valid in every
 // thread of every block after the call). Entry k is a maximum if bit k of max_mask is set, a sum
 // otherwise. part: two alternating buffers of kTrMaxK * gridDim.x doubles (parity flips per call).
 template <int K>
-__device__ __forceinline__ void grid_totals(cg::grid_group& grid, const double (&v)[K],
+__device__ __forceinline__ void grid_totals(cg::grid_group& grid, const Bufs& B, const double (&v)[K],
                                             unsigned max_mask, double* part, int& parity,
-                                            double* sh /* K * kTrWarps */, double* tot /* K */) {
+                                            double* sh /* K * kTrWarps */, double* tot /* K */,
+                                            TrXchg& xc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = gridDim.x;
 #pragma unroll
@@ -1215,11 +1227,45 @@ __device__ __forceinline__ void grid_totals(cg::grid_group& grid, const double (
   }
   __syncthreads();
   parity ^= 1;
+  if (B.world > 1) {
+    const int xpar = static_cast<int>(xc.seq & 1ull);
+    const size_t base = static_cast<size_t>(xpar) * B.world * kScBlock;
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < K) {
+        const double mine = tot[threadIdx.x];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+          if (r < B.world) B.scx_peer[r][base + B.rank * kScBlock + threadIdx.x] = mine;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        p2p_signal(B, 3, xc.seq);
+        p2p_wait(B, 3, xc.seq);
+      }
+    }
+    grid.sync();
+    if (threadIdx.x < K) {
+      const int k = threadIdx.x;
+      const bool is_max = (max_mask >> k) & 1u;
+      double t = is_max ? -CUDART_INF : 0.0;
+      for (int r = 0; r < B.world; ++r) {
+        double q;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(q) : "l"(B.scx + base + r * kScBlock + k) : "memory");
+        t = is_max ? fmax(t, q) : t + q;
+      }
+      tot[k] = t;
+    }
+    __syncthreads();
+    xc.seq += 1;
+    xc.count += 1;
+  }
 }
 
 __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, TrState* trs,
-                                                         double* part) {
+                                                         double* part, unsigned long long seq_first) {
   cg::grid_group grid = cg::this_grid();
+  TrXchg xc{seq_first, 0};
   __shared__ double sh[kTrMaxK * kTrWarps];
   __shared__ double tot[kTrMaxK];
   __shared__ TrState st;
@@ -1268,7 +1314,7 @@ __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, Tr
         s[TI_max_t] = fmax(s[TI_max_t], t);
       }
     }
-    grid_totals<TI_TOTAL>(grid, s, 1u << TI_max_t, part, parity, sh, tot);
+    grid_totals<TI_TOTAL>(grid, B, s, 1u << TI_max_t, part, parity, sh, tot, xc);
     if (threadIdx.x == 0) tr_setup(&st, tot, P);
     __syncthreads();
   }
@@ -1286,11 +1332,15 @@ __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, Tr
       if (t <= c0) { s[0] += lt; s[2] += 1.0; } else { s[1] += h; }
       if (t <= c1) { s[3] += lt; s[5] += 1.0; } else { s[4] += h; }
     }
-    grid_totals<6>(grid, s, 0u, part, parity, sh, tot);
+    grid_totals<6>(grid, B, s, 0u, part, parity, sh, tot, xc);
     if (threadIdx.x == 0) {
       tr_update(&st, tot);
-      // non-finite data (a diverged iterate) can keep the partition changing for ever
-      if (!st.done && st.passes >= 120) { st.done = 2; st.zero_value = 1; }
+      // non-finite data (a diverged iterate) can keep the partition changing for ever; a lost peer
+      // (sticky time-out flag, identical on this rank's blocks after the barrier) ends the search too
+      if (!st.done && (st.passes >= 120 || (B.world > 1 && __ldcg(B.counters + 6)))) {
+        st.done = 2;
+        st.zero_value = 1;
+      }
     }
     __syncthreads();
   }
@@ -1305,14 +1355,17 @@ __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, Tr
       if (idx < B.n) s[0] += v;
       else s[1] += v;
     }
-    grid_totals<2>(grid, s, 0u, part, parity, sh, tot);
+    grid_totals<2>(grid, B, s, 0u, part, parity, sh, tot, xc);
     if (threadIdx.x == 0) {
       st.v_primal = tot[0];
       st.v_dual = tot[1];
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *trs = st;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st.exchanges = xc.count;
+    *trs = st;
+  }
 }
 
 int tr_solve_grid(int sm_count) {
@@ -1323,11 +1376,12 @@ int tr_solve_grid(int sm_count) {
   return sm_count * (per_sm < 2 ? per_sm : 2);
 }
 
-int launch_tr_solve(const Bufs& B, const TrProblem& P, TrState* d_trs, int grid, cudaStream_t s) {
+int launch_tr_solve(const Bufs& B, const TrProblem& P, TrState* d_trs, int grid,
+                    unsigned long long seq_first, cudaStream_t s) {
   // the scratch of the evaluation slot holds 2 * kTrMaxK * grid doubles
   static_assert(2 * kTrMaxK <= kMaxScalars, "partials fit the evaluation slot");
   double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
-  void* args[] = {const_cast<Bufs*>(&B), const_cast<TrProblem*>(&P), &d_trs, &part};
+  void* args[] = {const_cast<Bufs*>(&B), const_cast<TrProblem*>(&P), &d_trs, &part, &seq_first};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tr_solve), dim3(grid), dim3(kTrThreads),
                                      args, 0, s);
 }

@@ -97,6 +97,8 @@ struct TrState {
   double cx, x_aty, y_b;
   double v_primal, v_dual;  // objective_vector . (solution - center), per segment
   double xqx;               // center' * Q * center (0 for an LP)
+  int exchanges;            // cross-rank scalar exchanges made by k_tr_solve (partitioned mode)
+  int reserved0;
 };
 
 struct TrProblem {
@@ -132,7 +134,10 @@ void launch_tr(const Bufs& B, const TrProblem& P, TrState* d_trs, int passes, bo
                cudaStream_t s);
 // single GPU: the whole solve (init, passes to convergence, final value) as one cooperative
 // kernel on `grid` co-resident blocks; returns a cudaError_t
-int launch_tr_solve(const Bufs& B, const TrProblem& P, TrState* d_trs, int grid, cudaStream_t s);
+// (partitioned mode over peer memory: every rank launches it; seq_first = number of the first
+// scalar exchange it will make, TrState::exchanges = how many it made)
+int launch_tr_solve(const Bufs& B, const TrProblem& P, TrState* d_trs, int grid,
+                    unsigned long long seq_first, cudaStream_t s);
 int tr_solve_grid(int sm_count);  // co-resident blocks for launch_tr_solve (0: unavailable)
 // row-partitioned mode: one kernel of the trust-region solve at a time; each leaves its
 // local sums in B.sc_send, and after the host's scalar exchange launch_tr_combine applies
