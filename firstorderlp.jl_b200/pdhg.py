@@ -93,9 +93,46 @@ def host_setup(params: PdhgParameters, original_problem: QuadraticProgrammingPro
 
 def optimize(params: PdhgParameters, original_problem: QuadraticProgrammingProblem,
              device_rescaling: bool = False) -> SaddlePointOutput:
-    holder, fparams, _ = host_setup(params, original_problem, device_rescaling=device_rescaling)
+    holder, fparams, scaled = host_setup(params, original_problem, device_rescaling=device_rescaling)
+    if params.verbosity <= 0:  # nothing to print: the whole loop in one C call
+        with Solver(holder, fparams) as solver:
+            x, y, reason, iters, evals = solver.solve()
+        stats = [iteration_stats_from_eval(e) for e in evals]
+        reason = _abi.TerminationReason(reason)
+        return SaddlePointOutput(x, y, reason, termination_reason_to_string(reason), iters, stats)
+    return _optimize_with_log(params, holder, fparams, scaled)
+
+
+def _optimize_with_log(params: PdhgParameters, holder, fparams, scaled) -> SaddlePointOutput:
+    """The loop of pdhg.jl:886-1048 driven evaluation by evaluation (folp_run), so that the
+    verbosity-gated table of isu.jl:459-619 and the final logs are printed where the reference
+    prints them."""
+    from . import display
+    verbosity = params.verbosity
+    freq = params.termination_evaluation_frequency
+    stats = []
+    display.display_iteration_stats_heading(verbosity)  # pdhg.jl:883
     with Solver(holder, fparams) as solver:
-        x, y, reason, iters, evals = solver.solve()
-    stats = [iteration_stats_from_eval(e) for e in evals]
-    reason = _abi.TerminationReason(reason)
-    return SaddlePointOutput(x, y, reason, termination_reason_to_string(reason), iters, stats)
+        while True:
+            e = solver.run()
+            iteration = e.iteration_number + 1  # the reference's loop counter at the evaluation
+            st = iteration_stats_from_eval(e)
+            terminated = e.termination_reason != 0
+            if params.record_iteration_stats or terminated:  # :958-960
+                stats.append(st)
+            if display.print_to_screen_this_iteration(terminated, iteration, verbosity, freq):
+                display.display_iteration_stats(st, verbosity)
+            if terminated:
+                reason = _abi.TerminationReason(e.termination_reason)
+                x, y = solver.get_solution(which=0, unscaled=True)
+                if verbosity >= 2:  # the reference logs the SCALED average on the scaled problem
+                    xs, ys = solver.get_solution(which=0, unscaled=False)
+                else:
+                    xs, ys = x, y
+                display.pdhg_final_log(scaled.scaled_qp, xs, ys, verbosity, iteration, reason, st)
+                return SaddlePointOutput(x, y, reason, termination_reason_to_string(reason),
+                                         int(e.iteration_number), stats)
+            if verbosity >= 6 and display.print_to_screen_this_iteration(False, iteration, verbosity, freq):
+                xc, yc = solver.get_solution(which=1, unscaled=False)  # :1027-1041
+                display.pdhg_specific_log(scaled.scaled_qp, iteration, xc, yc, e.step_size, None,
+                                          e.primal_weight)

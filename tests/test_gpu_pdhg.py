@@ -25,3 +25,26 @@ def test_malitsky_pock_rejects_qp():
     with pytest.raises(FolpError) as err:
         folp_b200.optimize(params, example_qp())
     assert err.value.status == folp_b200.Status.UNSUPPORTED
+
+
+def test_verbosity_table_and_final_log(capsys):
+    """Row E37: with verbosity >= 2 optimize() drives the loop evaluation by evaluation and prints
+    the reference's table (isu.jl:499-619) and final logs (pdhg.jl:324-370, sp.jl:947-1013); the
+    result is the one of the silent single-call path, bit for bit."""
+    import numpy as np
+    from folp_b200 import display
+    from shared_problems import example_lp, generate_pdhg_params
+    quiet = folp_b200.optimize(generate_pdhg_params(iteration_limit=300, verbosity=0), example_lp())
+    capsys.readouterr()
+    loud = folp_b200.optimize(generate_pdhg_params(iteration_limit=300, verbosity=9), example_lp())
+    text = capsys.readouterr().out.splitlines()
+    assert np.array_equal(quiet.primal_solution, loud.primal_solution)
+    assert np.array_equal(quiet.dual_solution, loud.dual_solution)
+    assert quiet.iteration_count == loud.iteration_count == 300
+    assert len(quiet.iteration_stats) == len(loud.iteration_stats)
+    assert text[:2] == display.iteration_stats_heading(True).split("\n")
+    rows = [t for t in text if t[:1].isdigit()]
+    assert len(rows) == len(loud.iteration_stats)          # verbosity 9: every evaluation
+    assert rows[-1] == display.iteration_stats_row(loud.iteration_stats[-1], True)
+    assert "Avg solution:" in text and "Terminated after 301 iterations: ITERATION_LIMIT" in text
+    assert any(t.lstrip().startswith("41 norms=(") for t in text)   # pdhg_specific_log, verbosity >= 6
