@@ -44,7 +44,10 @@ def test_verbosity_table_and_final_log(capsys):
     assert len(quiet.iteration_stats) == len(loud.iteration_stats)
     assert text[:2] == display.iteration_stats_heading(True).split("\n")
     rows = [t for t in text if t[:1].isdigit()]
-    assert len(rows) == len(loud.iteration_stats)          # verbosity 9: every evaluation
+    shown = [s_ for k, s_ in enumerate(loud.iteration_stats)
+             if display.print_to_screen_this_iteration(k == len(loud.iteration_stats) - 1,
+                                                       s_.iteration_number + 1, 9, 5)]
+    assert len(rows) == len(shown) and len(shown) >= 60    # verbosity 9: every fifth iteration here
     assert rows[-1] == display.iteration_stats_row(loud.iteration_stats[-1], True)
     assert "Avg solution:" in text and "Terminated after 301 iterations: ITERATION_LIMIT" in text
     assert any(t.lstrip().startswith("41 norms=(") for t in text)   # pdhg_specific_log, verbosity >= 6
