@@ -34,8 +34,13 @@ WORKLOADS = {
     "mid": (4_000_000, 4_000_000, 10),      # between the two: where the 1-D partition starts to pay
     "small": (100_000, 100_000, 10),
     "half": (1_000_000, 500_000, 10),       # one rank's row block of c2 at 2 GPUs
+    # BASELINE.json configs[2] / [3] shapes (the real files / LightGraphs' RNG are not available offline)
+    "netlib": "netlib",      # block-angular, 9 902 x 230 000, ~1.4e6 nonzeros, 12 dense-ish linking rows (osa-60 class)
+    "pagerank": "pagerank",  # generate_pagerank_lp.jl at 1e6 nodes: one dense row + power-law degrees, ~8e6 nonzeros
 }
 
+
+WORKLOAD_LABEL = {"netlib": "synthetic Netlib-shaped block-angular LP", "pagerank": "PageRank LP (Barabasi-Albert graph)"}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the two k_spmv launches of an
 # iteration, from the committed `ncu --set full` capture (profiles/r01b_ncu_full_c2_summary.csv:
@@ -71,9 +76,17 @@ def make_problem(workload):
     import folp_b200
     from folp_b200.synthetic import random_sparse_lp
 
-    n, m, k = WORKLOADS[workload]
     t0 = time.time()
-    lp = random_sparse_lp(n, m, k)
+    if workload == "netlib":
+        from folp_b200.synthetic import netlib_shaped_lp
+        lp = netlib_shaped_lp(num_blocks=230, block_rows=43, block_cols=1000, linking_rows=12, density=0.06)
+    elif workload == "pagerank":
+        from folp_b200.synthetic import pagerank_lp
+        lp = pagerank_lp(1_000_000)
+    else:
+        n, m, k = WORKLOADS[workload]
+        lp = random_sparse_lp(n, m, k)
+    n, m = lp.num_variables, lp.num_constraints
     params = folp_b200.PdhgParameters(verbosity=0)  # scripts/solve_qp.jl defaults
     # fixed amount of work per step: never stop on a tolerance
     params.termination_criteria.eps_optimal_absolute = 0.0
@@ -286,15 +299,18 @@ def bench_gpu(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"synthetic random sparse LP n={n} m={m} nnz={nnz} fp64 ({args.workload})",
+        "config": {"workload": f"{WORKLOAD_LABEL.get(args.workload, 'synthetic random sparse LP')} n={n} m={m} "
+                               f"nnz={nnz} fp64 ({args.workload})",
                    "iterations_per_step": ITERS_PER_STEP, "parameters": "scripts/solve_qp.jl defaults "
                    "(ruiz 10, pock-chambolle 1.0, adaptive step 0.3/0.6, adaptive_normalized restarts, "
                    "evaluation every 40 iterations), tolerances 0 so every step does the same work",
                    "parallelism": "single GPU" if world == 1 else
                    f"1-D row partition over {world} GPUs (nnz-balanced row blocks + primal slices), per-attempt "
                    f"exchange: {exchange}",
-                   "l2_flush": "working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush"
-                               % ((24 * nnz + 8 * (20 * n + 12 * m)) / 1e6)},
+                   "l2_flush": ("working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush"
+                                if 24 * nnz + 8 * (20 * n + 12 * m) > 126e6 else
+                                "working set 24*nnz + vectors = %.0f MB fits the 126 MB L2 (an L2-resident "
+                                "instance class by design); no flush") % ((24 * nnz + 8 * (20 * n + 12 * m)) / 1e6)},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "clocks": clocks.summary(),
         "detail": {"iterations_timed": int(iters), "take_step_seconds": basic_s,
