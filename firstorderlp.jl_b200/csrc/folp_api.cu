@@ -2108,8 +2108,20 @@ static int emulate_packed_spmv(const PackedMatrix& pk, const IVec& rp, const IVe
       for (int lane = 0; lane < cnt; ++lane) y[row[lane]] = s[lane];
     } else {
       warp_rounds[item % W] += (t.nnz_end - t.nnz_begin + 127) / 128;
-      double lane_sum[32] = {0.0};
-      for (int k = t.nnz_begin; k < t.nnz_end; ++k) lane_sum[(k - t.nnz_begin) & 31] += v[k] * x[ci[k]];
+      // four partial sums per lane, as the kernel: trips of 128 entries feed s0..s3, the rest s0
+      double lane_sum[32];
+      for (int lane = 0; lane < 32; ++lane) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = t.nnz_begin + lane;
+        for (; k + 96 < t.nnz_end; k += 128) {
+          s0 += v[k] * x[ci[k]];
+          s1 += v[k + 32] * x[ci[k + 32]];
+          s2 += v[k + 64] * x[ci[k + 64]];
+          s3 += v[k + 96] * x[ci[k + 96]];
+        }
+        for (; k < t.nnz_end; k += 32) s0 += v[k] * x[ci[k]];
+        lane_sum[lane] = (s0 + s1) + (s2 + s3);
+      }
       auto tree = [](double* a) {  // warp_sum's xor-shuffle tree
         for (int o = 16; o > 0; o >>= 1)
           for (int l = 0; l < o; ++l) a[l] += a[l + o];  // lane l of the next level; same pairing as xor

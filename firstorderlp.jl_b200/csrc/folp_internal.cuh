@@ -71,7 +71,7 @@ struct DevState {
 //                 chunk order by the last chunk to finish (deterministic).
 // ---------------------------------------------------------------------------
 #ifndef FOLP_CHUNK_NNZ
-#define FOLP_CHUNK_NNZ 4096
+#define FOLP_CHUNK_NNZ 1024
 #endif
 #ifndef FOLP_GATHER_UNROLL
 #define FOLP_GATHER_UNROLL 3

@@ -14,6 +14,11 @@ from folp_b200.synthetic import netlib_shaped_lp, pagerank_lp, random_sparse_lp
 from shared_problems import generate_pdhg_params
 
 
+def _chunk_nnz():
+    from folp_b200.lib import build_info
+    return int(build_info().split("chunk_nnz=")[1].split(";")[0])
+
+
 def _serial(A, x):
     A = sp.csr_matrix(A)
     A.sort_indices()
@@ -29,7 +34,7 @@ def _serial(A, x):
 def _ragged(seed, rows=3000, n=5000):
     rng = np.random.default_rng(seed)
     lens = np.concatenate([np.zeros(9, int), rng.poisson(10, rows), np.full(5, 100),
-                           np.array([9000, 4097, 4096, 33, 32, 31])])
+                           np.array([9000, 4097, 4096, 1025, 1024, 200, 129, 128, 127, 33, 32, 31])])
     lens = np.minimum(lens, n)
     rng.shuffle(lens)
     ind, ptr, val = [], [0], []
@@ -58,7 +63,7 @@ def test_packed_layout_reproduces_serial_row_sums(make):
     assert np.array_equal(y[narrow], ref[narrow])          # bit-identical: same summation order
     scale = max(1.0, np.max(np.abs(ref)) if ref.size else 1.0)
     assert np.max(np.abs(y - ref), initial=0.0) <= 1e-13 * scale
-    assert stats["long_rows"] == int((row_len > 4096).sum())
+    assert stats["long_rows"] == int((row_len > _chunk_nnz()).sum())
 
 
 def _heavy_tailed(seed=7, rows=20000, n=20000):  # noqa: E302
