@@ -53,8 +53,8 @@ void parallel_for(int64_t begin, int64_t end, int64_t min_chunk, F fn) {
 
 // std::vector without the zero fill of resize() / the sizing constructor: folp_create's
 // O(nnz) scratch arrays are written exactly once, by several threads.
-// Large blocks are 2 MB aligned and advised as transparent huge pages: the arrays are touched
-// once, front to back, and with 4 KB pages the first-touch faults cost more than the work.
+// Large blocks are 2 MB aligned and can be advised as transparent huge pages (FOLP_THP=1): the
+// arrays are touched once, front to back, and 4 KB first-touch faults are a fifth of the work.
 template <class T>
 struct NoInit {
   using value_type = T;
@@ -68,7 +68,9 @@ struct NoInit {
     if (bytes >= 2 * kHuge) {
       const size_t rounded = (bytes + kHuge - 1) / kHuge * kHuge;
       q = aligned_alloc(kHuge, rounded);
-      static const bool thp = getenv("FOLP_NO_THP") == nullptr;
+      // opt-in: 38 vs 46 ms of host preparation on the GPU box when huge pages are at hand, but a
+      // first-touch compaction stall of several hundred ms when they are not (seen on a long-running host)
+      static const bool thp = getenv("FOLP_THP") != nullptr;
       if (q && thp) madvise(q, rounded, MADV_HUGEPAGE);
     } else {
       q = malloc(bytes ? bytes : 1);

@@ -12,7 +12,7 @@ FOLP_TIMING=1 timeout 400 python tools/probe_kernels.py --workload c2 --iters 20
   $(ls scratch/*.so 2>/dev/null) > gpurun_out/probe_c2.log 2>&1
 grep -E '^\{|folp_create\] (TOTAL|pack|transpose|index|vectors)|folp_destroy' gpurun_out/probe_c2.log | cut -c1-600
 python tools/host_prepare_probe.py 2>/dev/null | tee gpurun_out/host_prepare.log
-FOLP_NO_THP=1 python tools/host_prepare_probe.py 2>/dev/null | tee -a gpurun_out/host_prepare.log
+FOLP_THP=1 python tools/host_prepare_probe.py 2>/dev/null | tee -a gpurun_out/host_prepare.log
 FOLP_TIMING=1 timeout 500 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
 echo "bench rc=$?"
 cut -c1-1500 gpurun_out/bench_c2.json
