@@ -1074,7 +1074,6 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_pass(Bufs B, TrProblem P, Tr
   if (trs->done) return;
   const double c0 = trs->cand[0], c1 = trs->cand[1];
   double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // L0,H0,cnt0,L1,H1,cnt1
-  double mx[1] = {0.0};
   const int begin = P.use_primal ? 0 : B.n;
   const int end = P.use_dual ? B.n + B.m : B.n;
   const int stride = gridDim.x * blockDim.x;
@@ -1091,7 +1090,6 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_pass(Bufs B, TrProblem P, Tr
     const double v = block_reduce<false>(s[k], sh);
     if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = v;
   }
-  (void)mx;
   if (!last_block_arrive(B.counters + kSlotEval)) return;
   double r[6];
   for (int k = 0; k < 6; ++k)
@@ -1109,7 +1107,6 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_final(Bufs B, TrProblem P, T
   if (!trs->done || trs->zero_value) return;
   const double tau = trs->tau;
   double s[2] = {0.0, 0.0};
-  double mx[1] = {0.0};
   const int begin = P.use_primal ? 0 : B.n;
   const int end = P.use_dual ? B.n + B.m : B.n;
   const int stride = gridDim.x * blockDim.x;
@@ -1126,7 +1123,6 @@ __global__ void __launch_bounds__(kVecThreads) k_tr_final(Bufs B, TrProblem P, T
     const double v = block_reduce<false>(s[k], sh);
     if (threadIdx.x == 0) part[static_cast<size_t>(k) * kMaxPartialBlocks + blockIdx.x] = v;
   }
-  (void)mx;
   if (!last_block_arrive(B.counters + kSlotEval)) return;
   const double vp = reduce_partials<false>(part, gridDim.x, sh);
   const double vd = reduce_partials<false>(part + kMaxPartialBlocks, gridDim.x, sh);
