@@ -30,6 +30,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import scipy.sparse as sp
 
+from .preprocess import row_permute_in_place
 from .problem import QuadraticProgrammingProblem
 from .solve_log import IterationStats, SolveLog
 
@@ -96,8 +97,9 @@ def transform_to_standard_form(qp: TwoSidedQpProblem) -> QuadraticProgrammingPro
     A.data[flip] *= -1
     new_row_to_old = np.concatenate([np.flatnonzero(is_eq), np.flatnonzero(~is_eq)])
     if not np.array_equal(new_row_to_old, np.arange(lo.size)):
-        A = sp.csc_matrix(A.tocsr()[new_row_to_old, :])
-        A.sort_indices()
+        old_row_to_new = np.empty_like(new_row_to_old)       # invperm, :73
+        old_row_to_new[new_row_to_old] = np.arange(lo.size)
+        row_permute_in_place(A, old_row_to_new)
     rhs = lo.copy()
     rhs[is_leq] = -up[is_leq]
     rhs = rhs[new_row_to_old]

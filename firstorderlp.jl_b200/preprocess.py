@@ -162,6 +162,18 @@ def pock_chambolle_rescaling(
     return constraint_rescaling, variable_rescaling
 
 
+def row_permute_in_place(matrix: sp.csc_matrix, old_row_to_new) -> None:
+    """src/preprocess.jl:590-623: permutes the rows of a CSC matrix in place according to the map
+    `old_row_to_new` (0-based here), keeping the row indices sorted inside every column."""
+    old_row_to_new = np.asarray(old_row_to_new, dtype=np.int64)
+    new_rows = old_row_to_new[matrix.indices]
+    # stable sort by (column, new row): columns are contiguous, so one lexsort does every column
+    order = np.lexsort((new_rows, _col_index(matrix)))
+    matrix.indices[:] = new_rows[order].astype(matrix.indices.dtype)
+    matrix.data[:] = matrix.data[order]
+    matrix.has_sorted_indices = True
+
+
 def rescale_problem(
     l_inf_ruiz_iterations: int,
     l2_norm_rescaling_flag: bool,

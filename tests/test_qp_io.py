@@ -65,6 +65,17 @@ def test_two_sided_rows_to_slacks():  # :66-94
     assert np.array_equal(qp.objective_matrix.toarray(), np.diag([1.0, 3.0, 0.0]))
 
 
+def test_row_permute_in_place():  # test/test_sparse_linalg.jl:15-35 (1-based maps there)
+    from folp_b200.preprocess import row_permute_in_place
+    mat = sp.csc_matrix(np.array([[1.0, 0.0], [0.0, 1.0]]))
+    row_permute_in_place(mat, [1, 0])
+    assert np.array_equal(mat.toarray(), [[0.0, 1.0], [1.0, 0.0]])
+    mat = sp.csc_matrix(np.array([[1.0, 0.0], [0.0, 1.0], [2.0, 3.0]]))
+    row_permute_in_place(mat, [2, 0, 1])
+    assert np.array_equal(mat.toarray(), [[0.0, 1.0], [2.0, 3.0], [1.0, 0.0]])
+    assert mat.has_sorted_indices and np.all(np.diff(mat.indices[mat.indptr[0]:mat.indptr[1]]) > 0)
+
+
 def test_fixed_format_every_row_and_bound_type():
     path = os.path.join(GOLDEN, "ranged_fixed_format.mps")
     mps = fio.read_mps(path, fixed_format=True)
