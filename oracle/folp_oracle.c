@@ -114,10 +114,60 @@ typedef struct {
   int64_t* rowval; /* nnz */
   double* nzval;   /* nnz */
   int owns_pattern;
+  /* CSR view (row pointers, column of every entry, its CSC position), built on first use by the
+   * threaded A * x below; NULL otherwise */
+  int64_t* t_rowptr;
+  int64_t* t_col;
+  int64_t* t_pos;
 } csc_t;
+
+/* Optional "all cores" timing mode (oracle_set_threads > 1; bench.py's stronger CPU baseline,
+ * SURVEY.md section 8d). The reference's kernels are serial and so is the default. The threaded
+ * products are bit-identical to the serial ones: A' * y is one independent dot product per
+ * column, and A * x is evaluated row by row through a CSR view in ascending column order -- the
+ * order in which the serial column scatter adds into each out[i]. */
+static int g_threads = 1;
+void oracle_set_threads(int threads) { g_threads = threads > 1 ? threads : 1; }
+int oracle_get_threads(void) { return g_threads; }
+int oracle_openmp_enabled(void) {
+#ifdef _OPENMP
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+static void csc_build_csr_view(csc_t* A) {
+  int64_t* rp = (int64_t*)calloc((size_t)A->m + 1, sizeof(int64_t));
+  int64_t* col = (int64_t*)malloc(sizeof(int64_t) * (size_t)(A->nnz > 0 ? A->nnz : 1));
+  int64_t* pos = (int64_t*)malloc(sizeof(int64_t) * (size_t)(A->nnz > 0 ? A->nnz : 1));
+  for (int64_t k = 0; k < A->nnz; ++k) rp[A->rowval[k] + 1] += 1;
+  for (int64_t i = 0; i < A->m; ++i) rp[i + 1] += rp[i];
+  int64_t* cur = (int64_t*)malloc(sizeof(int64_t) * (size_t)(A->m > 0 ? A->m : 1));
+  for (int64_t i = 0; i < A->m; ++i) cur[i] = rp[i];
+  for (int64_t j = 0; j < A->n; ++j)
+    for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; ++k) {
+      int64_t at = cur[A->rowval[k]]++;
+      col[at] = j;
+      pos[at] = k;
+    }
+  free(cur);
+  A->t_rowptr = rp; A->t_col = col; A->t_pos = pos;
+}
 
 /* SparseArrays: mul!(C, A, B) column scatter */
 static void csc_mul(const csc_t* A, const double* x, double* out) {
+  if (g_threads > 1 && A->nnz > 0) {
+    if (!A->t_rowptr) csc_build_csr_view((csc_t*)A); /* cache; the handle is used by one thread */
+    const int64_t* rp = A->t_rowptr;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int64_t i = 0; i < A->m; ++i) {
+      double tmp = 0.0;
+      for (int64_t k = rp[i]; k < rp[i + 1]; ++k) tmp += A->nzval[A->t_pos[k]] * x[A->t_col[k]];
+      out[i] = tmp;
+    }
+    return;
+  }
   for (int64_t i = 0; i < A->m; ++i) out[i] = 0.0;
   for (int64_t j = 0; j < A->n; ++j) {
     double xj = x[j];
@@ -127,6 +177,7 @@ static void csc_mul(const csc_t* A, const double* x, double* out) {
 }
 /* SparseArrays: mul!(C, adjoint(A), B) per-column gather */
 static void csc_tmul(const csc_t* A, const double* y, double* out) {
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1)
   for (int64_t j = 0; j < A->n; ++j) {
     double tmp = 0.0;
     for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; ++k)
@@ -137,6 +188,8 @@ static void csc_tmul(const csc_t* A, const double* y, double* out) {
 
 static void csc_free(csc_t* A) {
   if (A->owns_pattern) { free(A->colptr); free(A->rowval); }
+  free(A->t_rowptr); free(A->t_col); free(A->t_pos);
+  A->t_rowptr = A->t_col = A->t_pos = NULL;
   free(A->nzval);
   memset(A, 0, sizeof(*A));
 }
@@ -601,6 +654,10 @@ static void infeasibility_information(const qp_t* p, const double* primal_ray_in
   double inf_norm = norminf(xr, n);
   if (inf_norm != 0.0)
     for (int64_t j = 0; j < n; ++j) xr[j] /= inf_norm;
+  if (g_threads > 1) { /* the copies below must share the CSR views, not build (and leak) their own */
+    if (!p->A.t_rowptr && p->A.nnz > 0) csc_build_csr_view((csc_t*)&p->A);
+    if (!p->Q.t_rowptr && p->Q.nnz > 0) csc_build_csr_view((csc_t*)&p->Q);
+  }
   /* homogeneous primal :301-309 */
   qp_t hp = *p;
   hp.l = dalloc(n); hp.u = dalloc(n); hp.b = dzeros(m);
@@ -622,6 +679,7 @@ static void infeasibility_information(const qp_t* p, const double* primal_ray_in
   hd.Q.nnz = 0;
   int64_t* zero_colptr = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
   hd.Q.colptr = zero_colptr;
+  hd.Q.t_rowptr = hd.Q.t_col = hd.Q.t_pos = NULL; /* the copy has another pattern than p->Q */
   double* dres = dalloc(nin + n);
   double* rc = dalloc(n);
   double dobj = dual_stats(&hd, xr, dual_ray, dres, rc);

@@ -125,6 +125,13 @@ int oracle_l2_norm(int64_t m, int64_t n, const int64_t* colptr,
                    const int64_t* rowval, const double* nzval, int dimension,
                    double* out);
 
+/* Timing mode for bench.py's "all cores" CPU baseline: the two sparse
+ * products run on `threads` OpenMP threads, bit-identical to the serial kernels (see
+ * folp_oracle.c). Process-wide; 1 (the default) is the reference's serial behaviour. */
+void oracle_set_threads(int threads);
+int oracle_get_threads(void);
+int oracle_openmp_enabled(void); /* 0: built without OpenMP, the timing mode runs serially */
+
 #ifdef __cplusplus
 }
 #endif

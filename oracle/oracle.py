@@ -104,6 +104,20 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+def set_threads(threads: int) -> None:
+    """All-cores timing mode of the two sparse products (bit-identical results); 1 = serial, the
+    reference's behaviour and the default."""
+    lib().oracle_set_threads(int(threads))
+
+
+def get_threads() -> int:
+    return int(lib().oracle_get_threads())
+
+
+def openmp_enabled() -> bool:
+    return bool(lib().oracle_openmp_enabled())
+
+
 def _d(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
