@@ -308,6 +308,59 @@ static void plan_tiles(int rows, const IVec& rowptr, int warps_total, PackedMatr
       }
     }
   }
+  // Opt-in (FOLP_BALANCE_TILES=1; DESIGN.md section 10, lead 1): a cost-balanced STATIC order of
+  // the work items. k_spmv hands item i to warp i % warps_total; in row order the busiest warp of
+  // A' on the 1e6 x 1e6 x 1e7 workload carries 56 cost units against a mean of 46.4, a
+  // longest-processing-time assignment 49. Items are dealt to the least loaded warp in order of
+  // decreasing cost (rounds of a group, 128-entry trips of a warp-per-row item, + 1), then laid out
+  // so that warp w's k-th item sits at index k * warps_total + w, short lists padded with empty
+  // groups. Deterministic (a function of the matrix and the grid), no atomics; the per-thread
+  // partial sums of the reductions are simply formed over other rows. Not measured yet.
+  if (getenv("FOLP_BALANCE_TILES") != nullptr && warps_total > 0 &&
+      tiles.size() > static_cast<size_t>(warps_total)) {
+    const size_t T = tiles.size();
+    std::vector<int> cost(T);
+    for (size_t i = 0; i < T; ++i) {
+      const Tile& t = tiles[i];
+      const int kind = t.rows_kind >> 16;
+      if (kind == kTileThreadPerRow || kind == kTileThreadPerRowSorted) {
+        int mx = 0;
+        for (int q = t.row_begin; q < t.row_begin + (t.rows_kind & 0xffff); ++q)
+          mx = std::max(mx, rowptr[rowid[q] + 1] - rowptr[rowid[q]]);
+        cost[i] = (mx + kGatherUnrollHost - 1) / kGatherUnrollHost + 1;
+      } else {
+        cost[i] = (t.nnz_end - t.nnz_begin + 127) / 128 + 1;
+      }
+    }
+    std::vector<int> order(T);
+    for (size_t i = 0; i < T; ++i) order[i] = static_cast<int>(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    // least-loaded-first with a deterministic tie break (load, then warp index)
+    std::vector<std::vector<int>> mine(static_cast<size_t>(warps_total));
+    std::vector<std::pair<int64_t, int>> heap;  // (-load, -warp) as a max-heap == min load, min warp
+    heap.reserve(static_cast<size_t>(warps_total));
+    for (int w = 0; w < warps_total; ++w) heap.emplace_back(0, -w);
+    std::make_heap(heap.begin(), heap.end());
+    for (int idx : order) {
+      std::pop_heap(heap.begin(), heap.end());
+      auto& top = heap.back();
+      mine[static_cast<size_t>(-top.second)].push_back(idx);
+      top.first -= cost[idx];
+      std::push_heap(heap.begin(), heap.end());
+    }
+    size_t depth = 0;
+    for (const auto& v : mine) depth = std::max(depth, v.size());
+    Tile empty{};
+    empty.rows_kind = kTileThreadPerRow << 16;  // a group of zero rows: every lane idles through it
+    std::vector<Tile> balanced(depth * static_cast<size_t>(warps_total), empty);
+    for (int w = 0; w < warps_total; ++w) {
+      // within a warp keep the matrix order: its streams then move forward through memory
+      std::sort(mine[w].begin(), mine[w].end());
+      for (size_t k = 0; k < mine[w].size(); ++k)
+        balanced[k * static_cast<size_t>(warps_total) + w] = tiles[mine[w][k]];
+    }
+    tiles.swap(balanced);
+  }
 }
 
 // Writes the packed arrays: position-major inside every narrow group (each row keeps its own
