@@ -149,4 +149,5 @@ def test_cost_balanced_static_order_is_a_pure_reordering(monkeypatch):
         monkeypatch.delenv("FOLP_BALANCE_TILES")
         assert np.array_equal(y0, y1)
         assert s1["busiest_warp_rounds"] <= s0["busiest_warp_rounds"]
-        assert s1["narrow_rounds"] == s0["narrow_rounds"] and s1["tiles"] % 256 == 0
+        assert s1["narrow_rounds"] == s0["narrow_rounds"]
+        assert s1["tiles"] % 256 == 0 if s0["tiles"] > 256 else s1["tiles"] == s0["tiles"]
