@@ -260,11 +260,12 @@ def bench_gpu(args):
     else:
         # the per-rank kernels are the same; at N > 1 the whole-iteration figure is what can be stated
         roofline = {
-            "bound": "hbm", "kernel": "whole iteration over all ranks (k_primal, k_spmv x2, k_interaction + NCCL "
-                                      "allgather / reduce-scatter / scalar exchange)",
+            "bound": "hbm", "kernel": "whole iteration over all ranks (k_primal, k_spmv x2, k_finalize_dist; xbar and "
+                                      "y+ pushed to every rank from the producing kernels over peer memory, or "
+                                      "NCCL allgathers; four scalars per attempt)",
             "achieved": iteration["gbs_at_value"], "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": iteration["frac_at_value"], "traffic": None, "iteration": iteration,
-            "nvlink_bytes_per_iteration_per_gpu": 2 * 8 * n * (world - 1) // world,
+            "nvlink_bytes_per_iteration_per_gpu": 8 * (n + m) * (world - 1) // world,
         }
     solver.close()
 
