@@ -37,10 +37,13 @@ WORKLOADS = {
     # BASELINE.json configs[2] / [3] shapes (the real files / LightGraphs' RNG are not available offline)
     "netlib": "netlib",      # block-angular, 9 902 x 230 000, ~1.4e6 nonzeros, 12 dense-ish linking rows (osa-60 class)
     "pagerank": "pagerank",  # generate_pagerank_lp.jl at 1e6 nodes: one dense row + power-law degrees, ~8e6 nonzeros
+    # the median Netlib instance class (~1e3 x 2e3, ~1.5e4 nonzeros): the launch-/latency-bound regime
+    "netlib_small": "netlib_small",
 }
 
 
-WORKLOAD_LABEL = {"netlib": "synthetic Netlib-shaped block-angular LP", "pagerank": "PageRank LP (Barabasi-Albert graph)"}
+WORKLOAD_LABEL = {"netlib": "synthetic Netlib-shaped block-angular LP", "pagerank": "PageRank LP (Barabasi-Albert graph)",
+                  "netlib_small": "synthetic Netlib-shaped block-angular LP, median Netlib size"}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the two k_spmv launches of an
 # iteration, from the committed `ncu --set full` capture (profiles/r01b_ncu_full_c2_summary.csv:
@@ -80,6 +83,9 @@ def make_problem(workload):
     if workload == "netlib":
         from folp_b200.synthetic import netlib_shaped_lp
         lp = netlib_shaped_lp(num_blocks=230, block_rows=43, block_cols=1000, linking_rows=12, density=0.06)
+    elif workload == "netlib_small":
+        from folp_b200.synthetic import netlib_shaped_lp
+        lp = netlib_shaped_lp(num_blocks=24, block_rows=40, block_cols=90, linking_rows=12, density=0.08)
     elif workload == "pagerank":
         from folp_b200.synthetic import pagerank_lp
         lp = pagerank_lp(1_000_000)
@@ -142,6 +148,23 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def config_dict(args, n, m, nnz):
+    """The `config` object of the JSON line: identical for both arms of one (workload, --gpus)."""
+    ws = 24 * nnz + 8 * (20 * n + 12 * m)
+    return {"workload": f"{WORKLOAD_LABEL.get(args.workload, 'synthetic random sparse LP')} n={n} m={m} "
+                        f"nnz={nnz} fp64 ({args.workload})",
+            "iterations_per_step": ITERS_PER_STEP,
+            "parameters": "scripts/solve_qp.jl defaults (ruiz 10, pock-chambolle 1.0, adaptive step 0.3/0.6, "
+                          "adaptive_normalized restarts, evaluation every 40 iterations), tolerances 0 so every "
+                          "step does the same work",
+            "parallelism": "single GPU" if args.gpus == 1 else
+                           f"1-D partition over {args.gpus} GPUs (nnz-balanced row blocks + primal slices), one "
+                           "process per GPU",
+            "l2_flush": ("working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush" if ws > 126e6 else
+                         "working set 24*nnz + vectors = %.0f MB fits the 126 MB L2 (an L2-resident instance "
+                         "class by design); no flush") % (ws / 1e6)}
 
 
 def algorithmic_bytes(n, m, nnz):
@@ -288,30 +311,34 @@ def bench_gpu(args):
                "what": "folp_create(host CSC arrays%s) + folp_solve + folp_get_solution, wall clock, max over ranks"
                        % (", NCCL communicator" if world > 1 else "")}
 
-    # ---- cpu baseline: the oracle on a bounded sample of the same workload (rank 0, N = 1 only) ----
+    # ---- cpu baseline + parity at bench scale: the oracle on a bounded sample of the same workload ----
     cpu = None
+    parity = None
     rescale = None
-    if not args.skip_cpu and world == 1:
-        cpu = cpu_baseline(params, lp, scaled, sample_iters=args.cpu_iters)
-        rescale = rescale_timing(params, lp)
+    if not args.skip_cpu:
+        def make_gpu_solver(step0, weight0):
+            import copy
+            gp = copy.copy(fparams)
+            gp.iteration_limit = 1_000_000
+            gp.initial_step_size = step0
+            gp.initial_primal_weight = weight0
+            return Solver(holder, gp)
+
+        # N > 1: a shorter oracle run on rank 0 (the other ranks wait for it)
+        sample = args.cpu_iters if world == 1 else min(args.cpu_iters, 40)
+        cpu, parity = cpu_baseline(params, lp, scaled, sample_iters=sample, world=world, rank=rank,
+                                   make_gpu_solver=make_gpu_solver)
+        if world == 1:
+            rescale = rescale_timing(params, lp)
+        else:
+            cpu = None  # the contract wants the CPU baseline at N = 1 only; parity is kept at every N
 
     line = {
         "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD_LABEL.get(args.workload, 'synthetic random sparse LP')} n={n} m={m} "
-                               f"nnz={nnz} fp64 ({args.workload})",
-                   "iterations_per_step": ITERS_PER_STEP, "parameters": "scripts/solve_qp.jl defaults "
-                   "(ruiz 10, pock-chambolle 1.0, adaptive step 0.3/0.6, adaptive_normalized restarts, "
-                   "evaluation every 40 iterations), tolerances 0 so every step does the same work",
-                   "parallelism": "single GPU" if world == 1 else
-                   f"1-D row partition over {world} GPUs (nnz-balanced row blocks + primal slices), per-attempt "
-                   f"exchange: {exchange}",
-                   "l2_flush": ("working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush"
-                                if 24 * nnz + 8 * (20 * n + 12 * m) > 126e6 else
-                                "working set 24*nnz + vectors = %.0f MB fits the 126 MB L2 (an L2-resident "
-                                "instance class by design); no flush") % ((24 * nnz + 8 * (20 * n + 12 * m)) / 1e6)},
+        "config": config_dict(args, n, m, nnz),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "clocks": clocks.summary(),
         "detail": {"iterations_timed": int(iters), "take_step_seconds": basic_s,
@@ -319,7 +346,8 @@ def bench_gpu(args):
                    "final_relative_l2_primal_residual": e.relative_l2_primal_residual,
                    "final_l2_primal_residual": e.l2_primal_residual,
                    "final_l2_dual_residual": e.l2_dual_residual,
-                   "folp_create_seconds": t_create, "rescale_problem": rescale, "build": build_info()},
+                   "folp_create_seconds": t_create, "rescale_problem": rescale, "build": build_info(),
+                   "exchange": exchange, "parity": parity},
     }
     if rank == 0:
         emit(line)
@@ -327,42 +355,105 @@ def bench_gpu(args):
         import torch.distributed as td
         td.barrier()
         td.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        log("[bench] PARITY FAILED against the CPU oracle:", parity["problems"])
+        sys.exit(3)
 
 
-def cpu_baseline(params, lp, scaled, sample_iters):
-    """The oracle (kind "port": the Julia reference cannot run here), one thread,
-    timed from iteration 40 (after the ten per-iteration evaluations of the start)."""
+def _collect(solver, until, records):
+    """folp_run / oracle_run up to iteration `until`, keeping every record."""
+    while True:
+        e = solver.run()
+        records.append(e)
+        if e.iteration_number >= until or e.termination_reason != 0:
+            return e
+
+
+def cpu_baseline(params, lp, scaled, sample_iters, world=1, rank=0, make_gpu_solver=None):
+    """The CPU leg: the oracle (kind "port": the Julia reference cannot run here), one thread as the
+    reference's serial loop, timed from iteration 40 (after the ten per-iteration evaluations of the
+    start) -- and, with the records it produced on the way, the PARITY check of the CUDA path at
+    bench scale: a fresh GPU solve of the same problem from the same initial scalars is stepped
+    through the same evaluations and every folp_eval record is compared by the rule of
+    oracle/parity.py (1e-9 relative, widened only by the oracle's own one-ulp sensitivity, which the
+    all-cores run below measures). Under torchrun rank 0 runs the oracle while the other ranks wait;
+    all ranks then step the partitioned GPU solver together. Returns (cpu_baseline, parity)."""
     from oracle import oracle
+    from oracle.parity import compare_eval
 
-    holder, fparams, _ = oracle.host_setup(params, lp, scaled)
-    fparams.iteration_limit = 1_000_000
-    o = oracle.OracleSolver(holder, fparams)
-    run_until(o, 40)
-    t0 = time.perf_counter()
-    e = run_until(o, 40 + sample_iters)
-    dt = time.perf_counter() - t0
-    o.close()
-    out = {"value": sample_iters / dt, "unit": "iterations/s", "cores": 1, "kind": "port",
-           "sample": f"iterations 40..{40 + sample_iters} of the same problem and parameters "
-                     f"({sample_iters // 40} evaluation/restart blocks included), {dt:.1f}s",
-           "host_cores_available": os.cpu_count()}
-    # SURVEY 8d: a STRONGER baseline than the (serial) reference, labelled as such: the oracle with its two
-    # sparse products on every host core (bit-identical results; vector passes and reductions stay serial)
-    if oracle.openmp_enabled() and (os.cpu_count() or 1) > 1:
-        oracle.set_threads(os.cpu_count())
+    horizon = 40 + sample_iters
+    out, rec_o, rec_p = None, [], []
+    o_params = None
+    if rank == 0:
+        holder, o_params, _ = oracle.host_setup(params, lp, scaled)
+        o_params.iteration_limit = 1_000_000
+        o = oracle.OracleSolver(holder, o_params)
+        _collect(o, 40, rec_o)
+        t0 = time.perf_counter()
+        _collect(o, horizon, rec_o)
+        dt = time.perf_counter() - t0
+        o.close()
+        out = {"value": sample_iters / dt, "unit": "iterations/s", "cores": 1, "kind": "port",
+               "sample": f"iterations 40..{horizon} of the same problem and parameters "
+                         f"({sample_iters // 40} evaluation/restart blocks included), {dt:.1f}s",
+               "host_cores_available": os.cpu_count()}
+        # SURVEY 8d: a STRONGER baseline than the (serial) reference, labelled as such: the oracle with its two
+        # sparse products on every host core (bit-identical results; vector passes and reductions stay serial).
+        # Its initial step size is moved by ONE ulp: the timing does not care, and its records measure how far
+        # rounding noise alone moves each field (the sensitivity the parity rule allows for).
+        h2, p2, _ = oracle.host_setup(params, lp, scaled)
+        p2.iteration_limit = 1_000_000
+        p2.initial_step_size = float(np.nextafter(o_params.initial_step_size, np.inf))
+        threads = os.cpu_count() or 1
+        if oracle.openmp_enabled() and threads > 1:
+            oracle.set_threads(threads)
         try:
-            o = oracle.OracleSolver(holder, fparams)
-            run_until(o, 40)
+            o2 = oracle.OracleSolver(h2, p2)
+            _collect(o2, 40, rec_p)
             t0 = time.perf_counter()
-            run_until(o, 40 + sample_iters)
+            _collect(o2, horizon, rec_p)
             dt2 = time.perf_counter() - t0
-            o.close()
+            o2.close()
         finally:
             oracle.set_threads(1)
-        out["all_cores_variant"] = {"value": sample_iters / dt2, "unit": "iterations/s", "cores": os.cpu_count(),
-                                    "what": "oracle with A*x and A'*y on OpenMP threads (same bits), not the "
-                                            "reference's behaviour: a stronger baseline"}
-    return out
+        if oracle.openmp_enabled() and threads > 1:
+            out["all_cores_variant"] = {"value": sample_iters / dt2, "unit": "iterations/s", "cores": threads,
+                                        "what": "oracle with A*x and A'*y on OpenMP threads (same bits), not the "
+                                                "reference's behaviour: a stronger baseline"}
+    parity = None
+    if make_gpu_solver is not None:
+        # identical scalar inputs on both sides (rank 0's, broadcast)
+        init = [o_params.initial_step_size, o_params.initial_primal_weight] if rank == 0 else [0.0, 0.0]
+        if world > 1:
+            import torch
+            import torch.distributed as td
+            t = torch.tensor(init, dtype=torch.float64, device="cuda")
+            td.broadcast(t, src=0)
+            init = [float(v) for v in t.cpu()]
+        g = make_gpu_solver(init[0], init[1])
+        rec_g = []
+        _collect(g, horizon, rec_g)
+        g.close()
+        if rank == 0:
+            problems, worst, last_restart, restarts, equal = [], 0.0, 0, 0, True
+            if len(rec_g) != len(rec_o):
+                problems.append(f"{len(rec_g)} GPU records against {len(rec_o)} oracle records")
+            for eg, eo, ep in zip(rec_g, rec_o, rec_p):
+                pr, w = compare_eval(eg, eo, 1e-9, ep, eo.iteration_number - last_restart)
+                problems += pr
+                worst = max(worst, w)
+                equal = equal and eg.restart_used == eo.restart_used
+                if eo.restart_used >= 2:
+                    restarts += 1
+                    last_restart = eo.iteration_number
+            parity = {"ok": not problems, "records": len(rec_o), "iterations": int(rec_o[-1].iteration_number),
+                      "max_rel_err": worst, "tolerance": 1e-9, "restart_choices_equal": equal,
+                      "restarts": restarts, "n_gpus": world, "problems": problems[:6],
+                      "rule": "every floating-point field of every folp_eval record within 1e-9 relative of the "
+                              "CPU oracle (objective-like fields against max(|objective|, 1)), widened only by 20x "
+                              "the oracle's own sensitivity to a one-ulp change of its initial step size; identical "
+                              "restart choices and termination reasons (oracle/parity.py)"}
+    return out, parity
 
 
 def rescale_timing(params, lp):
@@ -421,11 +512,12 @@ def bench_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"synthetic random sparse LP n={n} m={m} nnz={nnz} fp64 ({args.workload})",
-                       "iterations_per_step": per},
+            "config": config_dict(args, n, m, nnz),
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "detail": {"sample_iterations_per_step": per,
+                       "note": "a step of this arm is a bounded sample (one evaluation period) of the config's step"}}
     emit(line)
 
 

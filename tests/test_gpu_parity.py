@@ -177,44 +177,14 @@ def test_trajectory_parity_no_restarts():
 # ---------------------------------------------------------------------------
 # evaluation records
 # ---------------------------------------------------------------------------
-_EVAL_FIELDS = [
-    "primal_objective", "dual_objective", "l_inf_primal_residual", "l2_primal_residual",
-    "l_inf_dual_residual", "l2_dual_residual", "relative_l_inf_primal_residual",
-    "relative_l2_primal_residual", "relative_l_inf_dual_residual", "relative_l2_dual_residual",
-    "relative_optimality_gap", "l_inf_primal_variable", "l2_primal_variable",
-    "l_inf_dual_variable", "l2_dual_variable", "max_primal_ray_infeasibility",
-    "primal_ray_linear_objective", "primal_ray_quadratic_norm", "max_dual_ray_infeasibility",
-    "dual_ray_objective",
-    "cumulative_kkt_matrix_passes", "step_size", "primal_weight", "lagrangian_value",
-    "estimated_lower_bound", "estimated_upper_bound",
-]
+from oracle.parity import EVAL_FIELDS as _EVAL_FIELDS, compare_eval  # noqa: E402
 
 
 def _assert_eval_close(eg, eo, tol, e_pert=None, restart_length=None):
-    """eg (GPU) against eo (oracle); e_pert = the oracle's record when its initial
-    step size is one ulp larger (the inherent sensitivity at this iteration)."""
-    assert eg.iteration_number == eo.iteration_number
-    if eg.restart_used != eo.restart_used:
-        # With a single iterate in the average, average == current up to one
-        # rounding, and should_reset_to_average (sp.jl:530-547, a `>=` between two
-        # equal quantities) is decided by that rounding: either restart is the
-        # reference's behaviour.
-        assert restart_length == 1 and {eg.restart_used, eo.restart_used} == {2, 3}
-    assert eg.termination_reason == eo.termination_reason
-    ref = max(abs(eo.primal_objective), abs(eo.dual_objective), 1.0)
-    for f in _EVAL_FIELDS:
-        a, b = getattr(eg, f), getattr(eo, f)
-        if np.isnan(b):
-            assert np.isnan(a), f
-            continue
-        if np.isinf(b):
-            assert a == b, f
-            continue
-        scale = max(abs(b), ref if "objective" in f or "bound" in f or "lagr" in f else 0.0, 1e-12)
-        bound = tol * scale
-        if e_pert is not None and np.isfinite(getattr(e_pert, f)):
-            bound = max(bound, 20 * abs(getattr(e_pert, f) - b))
-        assert abs(a - b) <= bound, (f, a, b, eo.iteration_number)
+    """eg (GPU) against eo (oracle) by the rule of oracle/parity.py; e_pert = the oracle's record
+    when its initial step size is one ulp larger (the inherent sensitivity at this iteration)."""
+    problems, _ = compare_eval(eg, eo, tol, e_pert, restart_length)
+    assert not problems, problems
 
 
 def _run_lockstep(problem, params, tol=1e-9):
