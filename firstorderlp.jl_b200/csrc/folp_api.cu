@@ -122,6 +122,14 @@ struct folp_handle {
   int64_t launches = 0;
   int64_t tr_passes = 0, tr_solves = 0;
   int tr_grid = 0;  // > 0: trust-region solves run as one cooperative kernel on this many blocks
+  // results of the evaluation block's device work when it was enqueued blind (evaluate_enqueue_blind):
+  // bit k of pre_mask = trust-region slot k is in pre[k]; pre_dist / pre_ax_cur = the distance sums are in
+  // h_red / A * x_cur is in B.ax_cur already
+  TrState pre[kTrSlots];
+  unsigned pre_mask = 0;
+  bool pre_dist = false, pre_ax_cur = false;
+  int take_grid = 0;  // > 0: batches of take_step attempts run as one cooperative kernel (k_take_steps) on this many blocks
+  unsigned long long* d_timers = nullptr;  // phase timers of k_take_steps (folp_debug_profile_attempts)
   std::map<int, cudaGraphExec_t> step_graphs;
   bool use_graphs = true;
   // ---- row-partitioned mode (folp_dist.world_size > 1) ----
@@ -913,7 +921,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   TRY(static_cast<cudaError_t>(spmv_configure()));
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->hs), sizeof(DevState)));
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_red), sizeof(double) * 4 * kMaxScalars));
-  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_trs), sizeof(TrState)));
+  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_trs), sizeof(TrState) * kTrSlots));
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_sc), sizeof(double) * h->world * kScBlock));
 
   if (h->world > 1) {
@@ -967,7 +975,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
                                                            8 * (n + 16) + 8 * 256 + 5 * 8 * (n + 48))
                                      : 0;
         const size_t vec_bytes = static_cast<size_t>(8) * (19 * (n + 48) + 13 * (m + 48)) +
-                                 sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 16);
+                                 sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 17);
         if ((rc = arena_reserve(h, mat_bytes(n, nnz, hm.pk_t) + mat_bytes(m, nnz, hm.pk_a) + q_bytes + vec_bytes)))
           return rc;
       }
@@ -1147,7 +1155,38 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   if ((rc = dev_zeros(h, &B.red, static_cast<size_t>(4) * kMaxScalars))) return rc;
   if ((rc = dev_alloc(h, &B.counters, 8))) return rc;
   TRY(cudaMemsetAsync(B.counters, 0, 8 * sizeof(unsigned), h->stream));
-  if ((rc = dev_alloc(h, &h->d_trs, 1))) return rc;
+  if ((rc = dev_alloc(h, &h->d_trs, kTrSlots))) return rc;
+  // ---- persistent take_step kernel: barrier words, phase timers, co-resident grid ----
+  if ((rc = dev_alloc(h, &B.bar_top, kBarL1Stride))) return rc;
+  if ((rc = dev_alloc(h, &B.bar_gen, static_cast<size_t>(kBarMaxGroups + 1) * kBarGenStride))) return rc;
+  if ((rc = dev_alloc(h, &h->d_timers, 16))) return rc;
+  TRY(cudaMemsetAsync(B.bar_top, 0, sizeof(unsigned) * kBarL1Stride, h->stream));
+  TRY(cudaMemsetAsync(B.bar_gen, 0, sizeof(unsigned long long) * (kBarMaxGroups + 1) * kBarGenStride, h->stream));
+  TRY(cudaMemsetAsync(h->d_timers, 0, sizeof(unsigned long long) * 16, h->stream));
+  if (const char* t = getenv("FOLP_P2P_TIMEOUT_MS")) {
+    const double ms = atof(t);
+    if (ms > 0.0) B.p2p_timeout_ns = static_cast<unsigned long long>(ms * 1e6);
+  }
+  // k_take_steps (one cooperative launch per batch of attempts) is the form of the partitioned mode,
+  // where the peer exchanges ride on its grid barriers. On one GPU the CUDA graph of three kernels per
+  // attempt is faster (measured, 1e6 x 1e6 x 1e7: 8 250 against 7 690 take_step iterations/s; a software
+  // grid barrier costs ~3 us of fences and atomic round trips against ~1.5 us for a kernel boundary
+  // inside a graph) and stays the default; FOLP_PERSISTENT=1 / 0 force either form.
+  {
+    const char* pe = getenv("FOLP_PERSISTENT");
+    const bool want = pe ? atoi(pe) != 0 : (P > 1);
+    if (want && prop.cooperativeLaunch && getenv("FOLP_NO_PERSISTENT") == nullptr && (P == 1 || B.p2p)) {
+      const int cap = take_steps_grid(h->sm_count, P > 1);
+      // no more CTAs than there is work: fewer CTAs make a cheaper barrier on small instances
+      int64_t need = std::max<int64_t>((h->A.ntiles + kSpmvWarps - 1) / kSpmvWarps,
+                                       (h->At.ntiles + kSpmvWarps - 1) / kSpmvWarps);
+      need = std::max<int64_t>(need, (nl / 2 + kSpmvThreads - 1) / kSpmvThreads);
+      if (has_q) need = std::max<int64_t>(need, (h->Q.ntiles + kSpmvWarps - 1) / kSpmvWarps);
+      if (const char* g = getenv("FOLP_TAKE_GRID")) need = atoi(g);
+      h->take_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(cap, need)));
+      if (cap <= 0) h->take_grid = 0;
+    }
+  }
 
   pt.mark("vectors");
   // ---- PdhgSolverState scalars, pdhg.jl:805-819 ----
@@ -1391,6 +1430,22 @@ static int launch_attempts_any(folp_handle* h, int attempts) {
 static int enqueue_attempts(folp_handle* h, int attempts) {
   if (attempts <= 0) return FOLP_OK;
   int rc;
+  if (h->take_grid > 0) {  // the whole batch as one cooperative launch
+    const cudaError_t le = static_cast<cudaError_t>(
+        launch_take_steps(h->B, h->A, h->At, h->Q, attempts, h->take_grid, h->stream));
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
+      cudaGetLastError();  // the device is shared (MPS partition, ...): kernel-per-phase form from now on
+      if (h->world > 1) {  // the ranks must agree on the form: an error rather than a silent divergence
+        h->err = "cooperative launch of k_take_steps refused on this rank";
+        return FOLP_CUDA_ERROR;
+      }
+      h->take_grid = 0;
+    } else {
+      TRY(le);
+      h->launches += 1;
+      return FOLP_OK;
+    }
+  }
   if (!h->use_graphs || attempts < 2) {
     if ((rc = launch_attempts_any(h, attempts))) return rc;
     CHECK_LAUNCH();
@@ -1492,8 +1547,17 @@ static void tr_abandoned(TrState* t) {
   t->v_dual = NAN;
 }
 
-static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
+// slot: which result of the evaluation block this is (0..kTrSlots-1); when the block was enqueued
+// blind the solve has already run and its state was fetched with the block's single read-back.
+static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out, int slot) {
   int rc;
+  if (h->pre_mask & (1u << slot)) {
+    *out = h->pre[slot];
+    h->tr_solves += 1;
+    h->tr_passes += out->passes;
+    if (out->done != 1) tr_abandoned(out);
+    return FOLP_OK;
+  }
   if (h->tr_grid > 0) {  // single GPU: one cooperative kernel, one host read
     const cudaError_t le = static_cast<cudaError_t>(
         launch_tr_solve(h->B, P, h->d_trs, h->tr_grid, h->xchg_seq + 1, h->stream));
@@ -1543,11 +1607,11 @@ static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out) {
 // products A*x and A'*y are already in HBM.
 static int euclidean_gap(folp_handle* h, const double* px, const double* atp, const double* py,
                          const double* axp, const double* qxp, double wp, double wd, double radius,
-                         BoundResult* out) {
+                         BoundResult* out, int slot) {
   TrProblem P{px, atp, py, axp, wp, wd, radius, 1, 1,
               h->prm.use_approximate_localized_duality_gap, h->B.has_q ? qxp : nullptr};
   TrState t;
-  int rc = tr_solve(h, P, &t);
+  int rc = tr_solve(h, P, &t, slot);
   if (rc) return rc;
   out->lagrangian_value = ((0.5 * t.xqx + t.cx) - t.x_aty) + t.y_b + h->objective_constant;
   out->lower_bound_value = out->lagrangian_value + t.v_primal;
@@ -1603,11 +1667,13 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
       rp->artificial_restart_threshold * static_cast<double>(iterations_completed))
     do_restart = 1;
   // distances to the last restart point (needed by every branch that restarts)
-  double* red = B.red + 2 * kMaxScalars;
-  launch_dist(B, red, h->stream);
-  CHECK_LAUNCH();
-  h->launches += 1;
-  if ((rc = pull_red(h, 2 * kMaxScalars, SD_TOTAL, SD_TOTAL))) return rc;
+  if (!h->pre_dist) {
+    double* red = B.red + 2 * kMaxScalars;
+    launch_dist(B, red, h->stream);
+    CHECK_LAUNCH();
+    h->launches += 1;
+    if ((rc = pull_red(h, 2 * kMaxScalars, SD_TOTAL, SD_TOTAL))) return rc;
+  }
   const double* dist = h->h_red + 2 * kMaxScalars;
   const double avg_px = sqrt(wp * dist[SD_avg_x]), avg_dy = sqrt(wd * dist[SD_avg_y]);
   const double cur_px = sqrt(wp * dist[SD_cur_x]), cur_dy = sqrt(wd * dist[SD_cur_y]);
@@ -1624,12 +1690,12 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
     const double d_cur = sqrt(cur_px * cur_px + cur_dy * cur_dy);
     BoundResult g_avg, g_cur;
     if ((rc = euclidean_gap(h, B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, B.qx_avg, wp, wd, d_avg,
-                            &g_avg)))
+                            &g_avg, 2)))
       return rc;
-    if ((rc = spmv_A(h, B.x[s->cur], B.ax_cur))) return rc;
+    if (!h->pre_ax_cur && (rc = spmv_A(h, B.x[s->cur], B.ax_cur))) return rc;
     have_ax_cur = 1;
     if ((rc = euclidean_gap(h, B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, B.qx[s->cur], wp,
-                            wd, d_cur, &g_cur)))
+                            wd, d_cur, &g_cur, 3)))
       return rc;
     // should_reset_to_average, sp.jl:530-547
     const double cur_ng = get_gap(g_cur) / d_cur, avg_ng = get_gap(g_avg) / d_avg;
@@ -1649,7 +1715,7 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
       const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);
       BoundResult g_last;
       if ((rc = euclidean_gap(h, B.last_x, B.last_aty, B.last_y, B.last_ax, B.last_qx, wp, wd,
-                              d_last, &g_last)))
+                              d_last, &g_last, 4)))
         return rc;
       const double ncg = get_gap(candidate_gap) / candidate_distance;
       const double nlg = get_gap(g_last) / d_last;
@@ -1696,6 +1762,63 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
   return FOLP_OK;
 }
 
+// One GPU, cooperative trust-region kernel available: enqueues everything the evaluation block may
+// need after the statistics kernels, in the order (and with the operands) evaluate() and
+// run_restart_scheme() would launch it, with the weights / radii taken from the device-resident sums.
+// Sets pre_mask / pre_dist / pre_ax_cur for what was enqueued; on a refused cooperative launch it
+// stops early and the remaining pieces are computed by the synchronous path.
+static int evaluate_enqueue_blind(folp_handle* h) {
+  if (h->tr_grid <= 0 || getenv("FOLP_EVAL_SYNC") != nullptr) return FOLP_OK;
+  DevState* s = h->hs;
+  const folp_params* rp = &h->prm;
+  Bufs& B = h->B;
+  const double wp = 1 / s->step_size * s->primal_weight;  // define_norms, pdhg.jl:265-276
+  const double wd = 1 / s->step_size / s->primal_weight;
+  auto solve = [&](TrProblem P, int slot) -> bool {
+    const cudaError_t le = static_cast<cudaError_t>(
+        launch_tr_solve(B, P, h->d_trs + slot, h->tr_grid, h->xchg_seq + 1, h->stream));
+    if (le != cudaSuccess) {
+      cudaGetLastError();
+      if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) h->tr_grid = 0;
+      return false;
+    }
+    h->launches += 1;
+    h->pre_mask |= 1u << slot;
+    return true;
+  };
+  // update_objective_bound_estimates, sp.jl:1015-1047 (never approximate)
+  TrProblem Pp{B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, 1.0, 1, 0, 0, B.has_q ? B.qx_avg : nullptr};
+  Pp.param_src = kTrParamBounds;
+  TrProblem Pd = Pp;
+  Pd.use_primal = 0;
+  Pd.use_dual = 1;
+  if (!solve(Pp, 0) || !solve(Pd, 1)) return FOLP_OK;
+  if (!(s->count_x > 0 && s->count_y > 0)) return FOLP_OK;  // run_restart_scheme returns at once
+  launch_dist(B, B.red + 2 * kMaxScalars, h->stream);
+  h->launches += 1;
+  h->pre_dist = true;
+  if (rp->restart_scheme == FOLP_NO_RESTARTS) return FOLP_OK;
+  const int approx = rp->use_approximate_localized_duality_gap;
+  TrProblem Pa{B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, 0.0, 1, 1, approx, B.has_q ? B.qx_avg : nullptr};
+  Pa.param_src = kTrParamDistAvg;
+  if (!solve(Pa, 2)) return FOLP_OK;
+  launch_spmv_plain(h->A, B.x[s->cur], B.ax_cur, B.grid_spmv, h->stream);
+  h->launches += 1;
+  h->pre_ax_cur = true;
+  TrProblem Pc{B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, 0.0, 1, 1, approx,
+               B.has_q ? B.qx[s->cur] : nullptr};
+  Pc.param_src = kTrParamDistCur;
+  if (!solve(Pc, 3)) return FOLP_OK;
+  if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) {  // sp.jl:549-593 (needed unless the restart is forced)
+    const double pw = s->primal_weight;
+    const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);
+    TrProblem Pl{B.last_x, B.last_aty, B.last_y, B.last_ax, wp, wd, d_last, 1, 1, approx,
+                 B.has_q ? B.last_qx : nullptr};
+    solve(Pl, 4);
+  }
+  return FOLP_OK;
+}
+
 // The evaluation block, pdhg.jl:892-1023. hs holds the current device state.
 static int evaluate(folp_handle* h, folp_eval* out) {
   DevState* s = h->hs;
@@ -1721,10 +1844,23 @@ static int evaluate(folp_handle* h, folp_eval* out) {
   launch_stats_m(B, B.red + kMaxScalars, h->stream);
   CHECK_LAUNCH();
   h->launches += 3;
+  h->pre_mask = 0;
+  h->pre_dist = h->pre_ax_cur = false;
   if (h->world == 1) {
-    TRY(cudaMemcpyAsync(h->h_red, B.red, sizeof(double) * 2 * kMaxScalars, cudaMemcpyDeviceToHost,
+    // One GPU: the REST of the block's device work -- both bound-estimate solves, the distances to the
+    // last restart point, A * x_cur and the localized-gap solves -- is enqueued behind the statistics
+    // without a host round trip (their weights / radii are formed on the device from the sums in
+    // B.red, see TrParamSrc), and everything comes back with ONE copy and ONE synchronisation. The
+    // scalar decisions below then consume the fetched results instead of launching and waiting seven
+    // times per evaluation. (A terminating evaluation has computed restart candidates it does not use.)
+    if ((rc = evaluate_enqueue_blind(h))) return rc;
+    TRY(cudaMemcpyAsync(h->h_red, B.red, sizeof(double) * 3 * kMaxScalars, cudaMemcpyDeviceToHost,
                         h->stream));
+    if (h->pre_mask)
+      TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState) * kTrSlots, cudaMemcpyDeviceToHost, h->stream));
     TRY(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < kTrSlots; ++k)
+      if (h->pre_mask & (1u << k)) h->pre[k] = h->h_trs[k];
   } else {
     static_assert(2 * kMaxScalars <= kScBlock, "both statistics blocks travel in one exchange");
     if ((rc = pull_red(h, 0, SN_TOTAL, SN_NSUM))) return rc;  // gathers all 64 scalars once
@@ -1802,8 +1938,8 @@ static int evaluate(folp_handle* h, folp_eval* out) {
     TrProblem Pd = Pp;
     Pd.use_primal = 0; Pd.use_dual = 1;
     TrState tp, td;
-    if ((rc = tr_solve(h, Pp, &tp))) return rc;
-    if ((rc = tr_solve(h, Pd, &td))) return rc;
+    if ((rc = tr_solve(h, Pp, &tp, 0))) return rc;
+    if ((rc = tr_solve(h, Pd, &td, 1))) return rc;
     e.lagrangian_value = L;
     e.estimated_lower_bound = L + tp.v_primal;
     e.estimated_upper_bound = L - td.v_dual;
@@ -2054,6 +2190,24 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
   s->target_iterations = INT64_MAX / 4;
   s->active = s->numerical_error ? 0 : 1;
   if ((rc = push_state(h))) return rc;
+  if (h->take_grid > 0) {  // persistent kernel: per-phase device time from its own phase timers
+    TRY(cudaMemsetAsync(h->d_timers, 0, sizeof(unsigned long long) * 16, h->stream));
+    Bufs Bt = h->B;
+    Bt.timers = h->d_timers;
+    for (int64_t left = attempts; left > 0; left -= 256) {
+      const cudaError_t le = static_cast<cudaError_t>(launch_take_steps(
+          Bt, h->A, h->At, h->Q, static_cast<int>(std::min<int64_t>(left, 256)), h->take_grid, h->stream));
+      TRY(le);
+      h->launches += 1;
+    }
+    if ((rc = pull_state(h))) return rc;
+    unsigned long long t[8] = {0};
+    TRY(cudaMemcpy(t, h->d_timers, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) ms_out[k] = 0.0;
+    for (int k = 0; k < 3; ++k) ms_out[k] = 1e-6 * static_cast<double>(t[1 + k]);
+    if (attempts_run) *attempts_run = s->numerical_error ? -1 : static_cast<int64_t>(t[4]);
+    return FOLP_OK;
+  }
   const int nk = h->world == 1 ? 3 : 4;  // kernels (and, without peer memory, NCCL calls) per attempt
   std::vector<cudaEvent_t> ev(static_cast<size_t>((nk + 1) * attempts));
   for (auto& e : ev) TRY(cudaEventCreate(&e));

@@ -40,23 +40,36 @@ __device__ __forceinline__ void p2p_signal(const Bufs& B, int kind, unsigned lon
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
     }
 }
-// One thread: wait until every rank's flag of `kind` has reached v. Gives up after ~2 s so
-// that a lost peer surfaces as an error instead of a hung device.
-__device__ __forceinline__ void p2p_wait(const Bufs& B, int kind, unsigned long long v) {
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// One thread: wait until every rank's flag of `kind` has reached v. Gives up after
+// Bufs::p2p_timeout_ns of wall clock (FOLP_P2P_TIMEOUT_MS, default 30 s: ranks are separate processes
+// and do host work between batches) so that a lost peer surfaces as an error instead of a hung
+// device; returns true (and raises the sticky flag the host turns into an error) if it gave up.
+__device__ __forceinline__ bool p2p_wait(const Bufs& B, int kind, unsigned long long v) {
+  unsigned long long t0 = 0;
   for (int r = 0; r < B.world; ++r) {
     const unsigned long long* f = B.flags + kind * kMaxWorld + r;
     unsigned long long cur;
-    long long spins = 0;
+    unsigned spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
       if (cur >= v) break;
-      if (++spins > 20000000ll) {
-        atomicExch(B.counters + 6, 1u);  // sticky; the host turns it into an error
-        return;
+      if ((++spins & 255u) == 0u) {
+        const unsigned long long now = gtimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > B.p2p_timeout_ns || __ldcg(B.counters + 6)) {
+          atomicExch(B.counters + 6, 1u);  // sticky; the host turns it into an error
+          return true;
+        }
       }
-      __nanosleep(64);
+      if (spins > 64u) __nanosleep(32);
     }
   }
+  return false;
 }
 // "Last block done" for data that peers will read. Every block orders its (remote) stores
 // before its ticket with a gpu-scope fence; the last block, having observed every ticket, issues
@@ -68,11 +81,14 @@ __device__ __forceinline__ bool last_block_arrive_sys(unsigned* counter) {
   if (last && threadIdx.x == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
   return last;
 }
-// All threads of a CTA: block until the exchange has arrived.
-__device__ __forceinline__ void p2p_wait_cta(const Bufs& B, int kind) {
-  if (B.dbg & 2) return;
-  if (threadIdx.x == 0) p2p_wait(B, kind, p2p_value(*B.st, kind));
+// All threads of a CTA: block until the exchange has arrived. False if the wait gave up (a lost
+// peer): the caller returns without touching the half-delivered vector.
+__device__ __forceinline__ bool p2p_wait_cta(const Bufs& B, int kind) {
+  __shared__ int s_timed_out;
+  if (B.dbg & 2) return true;
+  if (threadIdx.x == 0) s_timed_out = p2p_wait(B, kind, p2p_value(*B.st, kind)) ? 1 : 0;
   __syncthreads();
+  return s_timed_out == 0;
 }
 
 // Constant-index selection keeps the kernel parameter struct out of local memory.
@@ -127,14 +143,13 @@ __device__ __forceinline__ double primal_elem(const PrimalCtx& k, double x, doub
   return d;
 }
 
-// DIST: partitioned mode (world > 1); the single-GPU instantiation carries no exchange code.
+// The primal step of one attempt over the elements t0, t0 + stride, ... (pairs of elements per trip):
+// returns this thread's share of |dx|^2. DIST: partitioned mode (world > 1), the slice is also
+// pushed into every peer's copy of xbar; the single-GPU instantiation carries no exchange code.
+// No __restrict__ / non-coherent loads on the iterates: the persistent kernel rewrites them between
+// grid barriers of one launch.
 template <bool DIST>
-__global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
-  __shared__ double sh[32];
-  pdl_wait();
-  pdl_release();
-  const DevState& s = *B.st;
-  if (!s.active) return;
+__device__ __forceinline__ double primal_range(const Bufs& B, const DevState& s, int t0, int stride) {
   double trial, theta;
   attempt_params(s, trial, theta);
   const bool mp = s.policy == FOLP_STEP_MALITSKY_POCK;
@@ -148,15 +163,13 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
   k.w_old = s.mp_old_step;
   k.has_q = B.has_q != 0;
   const int cur = s.cur;
-  const double* __restrict__ xc = sel(B.x, cur);
-  double* __restrict__ xn = sel(B.x, cur ^ 1);
-  const double* __restrict__ at = sel(B.aty, cur);
-  const double* __restrict__ qxc = sel(B.qx, cur);
+  const double* xc = sel(B.x, cur);
+  double* xn = sel(B.x, cur ^ 1);
+  const double* at = sel(B.aty, cur);
+  const double* qxc = sel(B.qx, cur);
   const bool avg = k.pend || k.pend_old;
   const bool rd_xn = k.pend_old || !k.do_primal;
   double acc = 0.0;
-  const int stride = gridDim.x * blockDim.x;
-  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
   // two elements per thread and trip: every stream moves as 16-byte accesses
   const int n2 = B.n >> 1;
   for (int j = t0; j < n2; j += stride) {
@@ -200,6 +213,17 @@ __global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
     }
     acc += d * d;
   }
+  return acc;
+}
+
+template <bool DIST>
+__global__ void __launch_bounds__(kVecThreads) k_primal(Bufs B) {
+  __shared__ double sh[32];
+  pdl_wait();
+  pdl_release();
+  const DevState& s = *B.st;
+  if (!s.active) return;
+  const double acc = primal_range<DIST>(B, s, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
   const double t = block_reduce<false>(acc, sh);
   if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 0)[blockIdx.x] = t;
   // the last block to finish announces this rank's slice on every rank
@@ -297,17 +321,19 @@ __device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double d
 // ---------------------------------------------------------------------------
 // K2 epilogue: dual step on row i given (A*xbar)_i
 // ---------------------------------------------------------------------------
-template <bool DIST>
+// BR = Bufs (an epilogue passed by value as a kernel parameter) or const Bufs& (built inside the
+// persistent kernel around its own parameter). setup() / publish() are the halves of begin() /
+// finish() that the persistent kernel uses: it holds the state in shared memory and closes an
+// attempt behind a grid barrier instead of a last-block ticket.
+template <bool DIST, class BR = Bufs>
 struct EpiDualT {
   static constexpr int kNumIn = 3;  // y, b, sum_y
-  Bufs B;
+  BR B;
   const double* yc;
   double* yn;
   double f, w, acc;
   bool pend;
-  __device__ bool begin() {
-    const DevState& s = *B.st;
-    if (!s.active) return false;
+  __device__ void setup(const DevState& s) {
     double trial, theta;
     attempt_params(s, trial, theta);
     f = s.primal_weight * trial;  // pdhg.jl:488
@@ -316,7 +342,12 @@ struct EpiDualT {
     pend = s.pending_avg & 1;
     w = s.pending_w;
     acc = 0.0;
-    if (DIST && B.p2p) p2p_wait_cta(B, 0);  // every rank's slice of xbar has landed
+  }
+  __device__ bool begin() {
+    const DevState& s = *B.st;
+    if (!s.active) return false;
+    setup(s);
+    if (DIST && B.p2p) return p2p_wait_cta(B, 0);  // every rank's slice of xbar has landed
     return true;
   }
   __device__ const double* input() const { return B.xbar_priv ? B.xbar_priv : B.xbar; }
@@ -339,41 +370,66 @@ struct EpiDualT {
     const double d = yp - yv;
     acc += d * d;
   }
-  __device__ void finish(double* sh) {
+  __device__ void publish(double* sh) {
     const double t = block_reduce<false>(acc, sh);
     if (threadIdx.x == 0) part_ptr(B, kSlotDual, 0)[blockIdx.x] = t;
+  }
+  __device__ void finish(double* sh) {
+    publish(sh);
     if (DIST && B.p2p && last_block_arrive_sys(B.counters + 5) && threadIdx.x == 0)
       p2p_signal(B, 1, p2p_value(*B.st, 1));
   }
 };
 
+// The five totals of an attempt, side by side: warp w < 5 of the calling CTA sums total w over the
+// per-block partials (lanes stride the blocks in a fixed order, then a shuffle tree) into
+// sh[16 + w]: |dx|^2, |dy|^2, dx . dA'y, |dA'y|^2, dx' Q dx. Ends with a barrier.
+__device__ __forceinline__ void attempt_totals(const Bufs& B, int g_primal, int g_dual, int g_trans, int g_q,
+                                               double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 5) {
+    const double* src = warp == 0 ? part_ptr(B, kSlotPrimal, 0)
+                      : warp == 1 ? part_ptr(B, kSlotDual, 0)
+                      : warp == 2 ? part_ptr(B, kSlotTrans, 0)
+                      : warp == 3 ? part_ptr(B, kSlotTrans, 1) : part_ptr(B, kSlotPrimal, 1);
+    const int count = warp == 0 ? g_primal : warp == 1 ? g_dual : warp == 4 ? g_q : g_trans;
+    double t = 0.0;
+    for (int j = lane; j < count; j += 32) t += __ldcg(src + j);
+    t = warp_sum(t);
+    if (lane == 0) sh[16 + warp] = t;
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // K3 epilogue: (A'*y+)_j, interaction dot, and the scalar rule in the last CTA
 // ---------------------------------------------------------------------------
-template <bool DIST>
+template <bool DIST, class BR = Bufs>
 struct EpiTransT {
   static constexpr int kNumIn = 3;  // x, x+, A'y
-  Bufs B;
+  BR B;
   int g_primal, g_dual;  // grids of K1 and K2 (number of partials they wrote)
   int g_q = 0;           // grid of the dx' Q dx kernel (QP only), 0 for an LP
-  const double *xc, *xn, *atc;
+  const double *xc, *xn, *atc, *yin;
   double* atn;
   double inter, dp2;
-  __device__ bool begin() {
-    const DevState& s = *B.st;
-    if (!s.active) return false;
+  __device__ void setup(const DevState& s) {
     xc = sel(B.x, s.cur);
     xn = sel(B.x, s.cur ^ 1);
     atc = sel(B.aty, s.cur);
     atn = sel(B.aty, s.cur ^ 1);
+    yin = DIST ? (B.yfull_priv ? B.yfull_priv : B.y_full) : sel(B.y, s.cur ^ 1);
     inter = 0.0;
     dp2 = 0.0;
-    if (DIST && B.p2p) p2p_wait_cta(B, 1);  // every rank's rows of y+ have landed
+  }
+  __device__ bool begin() {
+    const DevState& s = *B.st;
+    if (!s.active) return false;
+    setup(s);
+    if (DIST && B.p2p) return p2p_wait_cta(B, 1);  // every rank's rows of y+ have landed
     return true;
   }
-  __device__ const double* input() const {
-    return DIST ? (B.yfull_priv ? B.yfull_priv : B.y_full) : sel(B.y, B.st->cur ^ 1);
-  }
+  __device__ const double* input() const { return yin; }
   __device__ const double* in_ptr(int v) const { return v == 0 ? xc : (v == 1 ? xn : atc); }
   __device__ void row(int j, double at, double xcj, double xnj, double atcj) {
     atn[j] = at;
@@ -382,8 +438,8 @@ struct EpiTransT {
     inter += dx * dat;  // pdhg.jl:542-544
     dp2 += dat * dat;   // pdhg.jl:615 (Malitsky-Pock)
   }
-  __device__ void finish(double* sh) {
-    // sh: 32 doubles. One barrier for both sums: warp leaders park them, threads 0/1 combine.
+  // sh: 32 doubles. One barrier for both sums: warp leaders park them, threads 0/1 combine.
+  __device__ void publish(double* sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double wa = warp_sum(inter), wb = warp_sum(dp2);
     if (lane == 0) {
@@ -396,23 +452,12 @@ struct EpiTransT {
       for (int w = 1; w < kSpmvWarps; ++w) t += sh[threadIdx.x * kSpmvWarps + w];
       part_ptr(B, kSlotTrans, threadIdx.x)[blockIdx.x] = t;
     }
+  }
+  __device__ void finish(double* sh) {
+    publish(sh);
     if (!last_block_arrive(B.counters + kSlotTrans)) return;
-    // The last CTA closes the attempt; this tail is serial time of every iteration, so the five
-    // totals are formed side by side: warp w sums total w over the per-block partials (lanes
-    // stride the blocks in a fixed order, then a shuffle tree).
-    if (warp < 5) {
-      const double* src = warp == 0 ? part_ptr(B, kSlotPrimal, 0)
-                        : warp == 1 ? part_ptr(B, kSlotDual, 0)
-                        : warp == 2 ? part_ptr(B, kSlotTrans, 0)
-                        : warp == 3 ? part_ptr(B, kSlotTrans, 1) : part_ptr(B, kSlotPrimal, 1);
-      const int count = warp == 0 ? g_primal : warp == 1 ? g_dual : warp == 4 ? g_q
-                                                                              : static_cast<int>(gridDim.x);
-      double t = 0.0;
-      for (int j = lane; j < count; j += 32) t += __ldcg(src + j);
-      t = warp_sum(t);
-      if (lane == 0) sh[16 + warp] = t;
-    }
-    __syncthreads();
+    // The last CTA closes the attempt; this tail is serial time of every iteration.
+    attempt_totals(B, g_primal, g_dual, static_cast<int>(gridDim.x), g_q, sh);
     const double dx2 = sh[16], dy2 = sh[17], it = sh[18], dp = sh[19], qd = sh[20];
     if (threadIdx.x != 0) return;
     if (!DIST) {
@@ -468,27 +513,34 @@ __global__ void k_finalize_dist(Bufs B) {
 //   EpiQDot  sum_j dx_j (Q * dx)_j      the objective part of the interaction (pdhg.jl:536-541);
 //            computed from dx itself, not as a difference of products (no cancellation)
 // ---------------------------------------------------------------------------
-struct EpiQx {
+template <class BR = Bufs>
+struct EpiQxT {
   static constexpr int kNumIn = 0;
-  Bufs B;
+  BR B;
   const double* in;
   double* out;
+  __device__ void setup(const DevState& s) {
+    in = sel(B.x, s.cur ^ 1);
+    out = sel(B.qx, s.cur ^ 1);
+  }
   __device__ bool begin() {
     const DevState& s = *B.st;
     if (!s.active) return false;
-    in = sel(B.x, s.cur ^ 1);
-    out = sel(B.qx, s.cur ^ 1);
+    setup(s);
     return true;
   }
   __device__ const double* input() const { return in; }
   __device__ const double* in_ptr(int) const { return nullptr; }
   __device__ void row(int j, double s, double, double, double) { out[j] = s; }
+  __device__ void publish(double*) {}
   __device__ void finish(double*) {}
 };
-struct EpiQDot {
+template <class BR = Bufs>
+struct EpiQDotT {
   static constexpr int kNumIn = 1;  // dx
-  Bufs B;
+  BR B;
   double acc;
+  __device__ void setup(const DevState&) { acc = 0.0; }
   __device__ bool begin() {
     acc = 0.0;
     return B.st->active != 0;
@@ -496,16 +548,295 @@ struct EpiQDot {
   __device__ const double* input() const { return B.dxv; }
   __device__ const double* in_ptr(int) const { return B.dxv; }
   __device__ void row(int, double s, double dxj, double, double) { acc += dxj * s; }
-  __device__ void finish(double* sh) {
+  __device__ void publish(double* sh) {
     const double t = block_reduce<false>(acc, sh);
     if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 1)[blockIdx.x] = t;
   }
+  __device__ void finish(double* sh) { publish(sh); }
 };
 
 using EpiDual = EpiDualT<false>;
 using EpiTrans = EpiTransT<false>;
 using EpiDualDist = EpiDualT<true>;
 using EpiTransDist = EpiTransT<true>;
+using EpiQx = EpiQxT<>;
+using EpiQDot = EpiQDotT<>;
+
+// ---------------------------------------------------------------------------
+// k_take_steps: a whole batch of take_step attempts as ONE cooperative launch.
+//
+// The three kernels of an attempt become three phases of a persistent grid (one CTA set resident
+// for the whole batch, static striding over the same work items as k_spmv), separated by grid
+// barriers instead of kernel boundaries: no launch ramp / drain between phases (ncu on the
+// per-kernel form: 7 K of k_primal's 27 K cycles, 13 K of 109 K and 22 K of 127 K for the two
+// products are spent with SMs waiting to be filled or emptied), the solver scalars live in shared
+// memory (every CTA holds a bit-identical copy, refreshed once per attempt), and A'y+ / x+ written
+// by one phase are still in L2 when the next one reads them.
+//
+// The barrier is two-level (groups of kBarGroupSize CTAs arrive on their own counter, the last of a
+// group on the top counter) and runs a callback in the LAST CTA to arrive before it releases the
+// others. That callback is where an attempt is closed -- the five totals are formed from the
+// per-CTA partials in a fixed order and the scalar rule runs -- and where, in partitioned mode, the
+// peer exchanges ride: one thread of one CTA per GPU fences system-wide, raises this rank's flag
+// on every rank and waits for the peers' flags, instead of every CTA polling eight system-scope
+// flags at the head of the next kernel and a one-thread kernel for the step rule (DESIGN.md
+// section 6). A wait that gives up (lost peer) aborts the whole grid through the release word.
+// ---------------------------------------------------------------------------
+constexpr unsigned long long kBarAbortBit = 1ull << 63;
+constexpr unsigned long long kBarTimeoutNs = 20000000000ull;  // co-resident CTAs: only a bug gets here
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Grid-wide barrier of a cooperative launch with a callback in the LAST CTA to arrive.
+// All threads of all CTAs call it. `gen` = generation of the last completed barrier (same in every
+// thread). last_fn() runs in every thread of the last CTA to arrive, after all other CTAs' writes are
+// visible to it, and returns (uniformly) whether the grid must abort. s_flag: one shared int.
+// Returns true in every thread of every CTA if the grid aborts.
+//   arrival  ONE acq_rel atomic per CTA on one counter. CTAs finish a phase spread over microseconds,
+//            so what counts is the latency of the LAST arrival: one round trip (a two-level tree costs
+//            the last CTA two, measured +1.5 us per barrier).
+//   release  the last CTA writes the new generation into one word per group of kBarGroupSize CTAs; a
+//            CTA polls its own group's word. (With one shared word ~600 pollers keep a single L2 slice
+//            busy at about one request per clock while the slowest CTAs still gather through it.)
+template <class F>
+__device__ __forceinline__ bool grid_barrier(const Bufs& B, unsigned long long& gen, int* s_flag, F&& last_fn) {
+  const int group = blockIdx.x / kBarGroupSize;
+  const int ngroups = (static_cast<int>(gridDim.x) + kBarGroupSize - 1) / kBarGroupSize;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev;
+    // release: this CTA's writes (observed through the barrier above) before its arrival;
+    // acquire: the last arrival sees every other CTA's
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(B.bar_top) : "memory");
+    int last = 0;
+    if (prev == gridDim.x - 1u) {
+      *B.bar_top = 0u;  // re-armed: nobody arrives again before the release below
+      last = 1;
+    }
+    *s_flag = last;
+  }
+  __syncthreads();
+  bool aborted;
+  if (*s_flag == 1) {
+    aborted = last_fn();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long v = (gen + 1ull) | (aborted ? kBarAbortBit : 0ull);
+      fence_gpu();
+      for (int g = 0; g <= ngroups; ++g) st_relaxed_gpu_u64(B.bar_gen + g * kBarGenStride, v);
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      const unsigned long long* word = B.bar_gen + (group + 1) * kBarGenStride;
+      unsigned long long v, t0 = 0;
+      unsigned spins = 0;
+      for (;;) {
+        v = ld_relaxed_gpu_u64(word);
+        if ((v & ~kBarAbortBit) > gen) break;
+        if ((++spins & 4095u) == 0u) {
+          const unsigned long long now = gtimer_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > kBarTimeoutNs + B.p2p_timeout_ns) {  // never on a healthy device
+            atomicExch(B.counters + 6, 2u);
+            v = kBarAbortBit;
+            break;
+          }
+        }
+      }
+      fence_gpu();
+      *s_flag = (v & kBarAbortBit) ? 2 : 0;
+    }
+    __syncthreads();
+    aborted = *s_flag == 2;
+  }
+  gen += 1ull;
+  __syncthreads();  // s_flag is reused by the next barrier
+  return aborted;
+}
+
+// phase timers (development / bench probe): thread 0 of the last CTA of a barrier
+__device__ __forceinline__ void stamp_phase(const Bufs& B, int phase) {
+  if (!B.timers) return;
+  const unsigned long long now = gtimer_ns();
+  const unsigned long long prev = B.timers[0];
+  if (prev) B.timers[1 + phase] += now - prev;
+  B.timers[0] = now;
+  if (phase == 2) B.timers[4] += 1ull;
+}
+
+// every thread of the CTA: the CTA's copy of the solver scalars <- global
+__device__ __forceinline__ void load_state(DevState* dst, const DevState* src) {
+  static_assert(sizeof(DevState) % 8 == 0, "copied as 8-byte words");
+  constexpr int kWords = sizeof(DevState) / 8;
+  if (threadIdx.x < kWords)
+    reinterpret_cast<unsigned long long*>(dst)[threadIdx.x] =
+        __ldcg(reinterpret_cast<const unsigned long long*>(src) + threadIdx.x);
+}
+
+__device__ __forceinline__ void store_state(DevState* dst, const DevState* src) {
+  constexpr int kWords = sizeof(DevState) / 8;
+  if (threadIdx.x < kWords)
+    reinterpret_cast<unsigned long long*>(dst)[threadIdx.x] =
+        reinterpret_cast<const unsigned long long*>(src)[threadIdx.x];
+}
+
+template <bool DIST>
+__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm)
+k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, const __grid_constant__ SpmvMat At,
+             const __grid_constant__ SpmvMat Q, int max_attempts) {
+  __shared__ double s_red[32];
+  __shared__ DevState st;
+  __shared__ int s_flag, s_abort;
+  __shared__ unsigned long long s_gen;
+  load_state(&st, B.st);
+  if (threadIdx.x == 0) s_gen = ld_relaxed_gpu_u64(B.bar_gen) & ~kBarAbortBit;
+  __syncthreads();
+  unsigned long long gen = s_gen;
+  const int G = static_cast<int>(gridDim.x);
+  const int warp_first = blockIdx.x * kSpmvWarps + (threadIdx.x >> 5), warp_stride = G * kSpmvWarps;
+  const int t0 = blockIdx.x * kSpmvThreads + threadIdx.x, tstride = G * kSpmvThreads;
+  if (B.timers && blockIdx.x == 0 && threadIdx.x == 0) B.timers[0] = gtimer_ns();
+
+  // one peer exchange (partitioned mode), by thread 0 of the last CTA of a barrier: everything this
+  // rank pushed during the phase is fenced system-wide, the rank's flag goes up on every rank, and
+  // the peers' flags are awaited. Returns true if a peer was lost.
+  auto exchange = [&](int kind) -> bool {
+    if (!(DIST && B.p2p)) return false;
+    if (threadIdx.x == 0) {
+      bool lost = false;
+      if (!(B.dbg & 2)) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        const unsigned long long v = p2p_value(st, kind);
+        p2p_signal(B, kind, v);
+        lost = p2p_wait(B, kind, v);
+      }
+      s_abort = lost ? 1 : 0;
+    }
+    __syncthreads();
+    return s_abort != 0;
+  };
+
+  for (int a = 0; a < max_attempts; ++a) {
+    if (!st.active) break;  // the same in every CTA: the copies are bit-identical
+    // ---- phase 1: primal step on the (local slice of the) variables, xbar ----
+    {
+      const double acc = primal_range<DIST>(B, st, t0, tstride);
+      const double t = block_reduce<false>(acc, s_red);
+      if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 0)[blockIdx.x] = t;
+    }
+    if (grid_barrier(B, gen, &s_flag, [&]() -> bool {
+          const bool lost = exchange(0);
+          if (threadIdx.x == 0) stamp_phase(B, 0);
+          return lost;
+        }))
+      break;
+    // ---- phase 2: A * xbar, dual step (and, with a quadratic objective, Q * x+ and dx' Q dx) ----
+    {
+      EpiDualT<DIST, const Bufs&> ed{B};
+      ed.setup(st);
+      spmv_items<EpiDualT<DIST, const Bufs&>, true>(A, ed, warp_first, warp_stride);
+      __syncthreads();
+      ed.publish(s_red);
+      if (B.has_q) {
+        EpiQxT<const Bufs&> ex{B};
+        ex.setup(st);
+        spmv_items<EpiQxT<const Bufs&>, true>(Q, ex, warp_first, warp_stride);
+        EpiQDotT<const Bufs&> eq{B};
+        eq.setup(st);
+        spmv_items<EpiQDotT<const Bufs&>, true>(Q, eq, warp_first, warp_stride);
+        __syncthreads();
+        eq.publish(s_red);
+      }
+    }
+    if (grid_barrier(B, gen, &s_flag, [&]() -> bool {
+          const bool lost = exchange(1);
+          if (threadIdx.x == 0) stamp_phase(B, 1);
+          return lost;
+        }))
+      break;
+    // ---- phase 3: A' * y+, interaction; the last CTA of the barrier closes the attempt ----
+    {
+      EpiTransT<DIST, const Bufs&> et{B};
+      et.setup(st);
+      spmv_items<EpiTransT<DIST, const Bufs&>, true>(At, et, warp_first, warp_stride);
+      __syncthreads();
+      et.publish(s_red);
+    }
+    if (grid_barrier(B, gen, &s_flag, [&]() -> bool {
+          attempt_totals(B, G, G, G, B.has_q ? G : 0, s_red);
+          if (threadIdx.x == 0) {
+            double t[5] = {s_red[16], s_red[17], s_red[18], s_red[19], s_red[20]};
+            bool lost = false;
+            if (DIST) {  // every rank sums the ranks' totals in rank order: identical decisions everywhere
+#pragma unroll
+              for (int r = 0; r < kMaxWorld; ++r)
+                if (r < B.world) {
+                  double* slot = B.sc_peer[r] + B.rank * kScBlock;
+                  slot[0] = t[0];
+                  slot[1] = t[1];
+                  slot[2] = t[2];
+                  slot[3] = t[3];
+                }
+              asm volatile("fence.acq_rel.sys;" ::: "memory");
+              const unsigned long long v = p2p_value(st, 2);
+              p2p_signal(B, 2, v);
+              lost = (B.dbg & 2) ? false : p2p_wait(B, 2, v);
+              for (int k = 0; k < 4; ++k) t[k] = 0.0;
+              for (int r = 0; r < B.world; ++r)
+                for (int k = 0; k < 4; ++k) t[k] += __ldcg(B.sc_recv + r * kScBlock + k);
+              t[4] = 0.0;  // partitioned mode is LP only
+            }
+            if (lost) {
+              st.p2p_timeout = 1;
+              st.active = 0;
+            } else {
+              finalize_attempt(&st, t[0], t[1], t[2], t[3], t[4]);  // on this CTA's copy (shared memory)
+            }
+            stamp_phase(B, 2);
+            s_abort = lost ? 1 : 0;
+          }
+          __syncthreads();
+          store_state(B.st, &st);  // published to the other CTAs (and the host) by the barrier's release
+          return s_abort != 0;
+        }))
+      break;
+    if (s_flag != 1) load_state(&st, B.st);  // the closing CTA already holds the new state
+    __syncthreads();
+  }
+}
+
+int take_steps_grid(int sm_count, bool dist) {
+  int per_sm = 0;
+  const cudaError_t e = dist ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_take_steps<true>, kSpmvThreads, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_take_steps<false>, kSpmvThreads, 0);
+  if (e != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (per_sm > kSpmvCtasPerSm) per_sm = kSpmvCtasPerSm;
+  int g = sm_count * per_sm;
+  const int cap = kBarGroupSize * kBarMaxGroups;
+  if (g > cap) g = cap;
+  if (g > kMaxPartialBlocks) g = kMaxPartialBlocks;
+  return g;
+}
+
+int launch_take_steps(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q, int attempts,
+                      int grid, cudaStream_t s) {
+  void* args[] = {const_cast<Bufs*>(&B), const_cast<SpmvMat*>(&A), const_cast<SpmvMat*>(&At),
+                  const_cast<SpmvMat*>(&Q), &attempts};
+  const void* fn = B.world > 1 ? reinterpret_cast<const void*>(k_take_steps<true>)
+                               : reinterpret_cast<const void*>(k_take_steps<false>);
+  return cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kSpmvThreads), args, 0, s);
+}
 
 static int spmv_grid(const SpmvMat& A, int grid_spmv);
 // every block of a pushing kernel ends with one system-scope fence, and those serialise:
@@ -1261,6 +1592,23 @@ __device__ __forceinline__ void grid_totals(cg::grid_group& grid, const Bufs& B,
 __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, TrState* trs,
                                                          double* part, unsigned long long seq_first) {
   cg::grid_group grid = cg::this_grid();
+  if (P.param_src != kTrParamHost) {  // same arithmetic as the host's (evaluate / run_restart_scheme in folp_api.cu)
+    if (P.param_src == kTrParamBounds) {
+      const double xs2 = B.red[SN_xs2], ys2 = B.red[kMaxScalars + SM_ys2];
+      double rp = sqrt(P.wp * xs2), rd = sqrt(P.wd * ys2);
+      rp = (rp != rp) ? rp : (1e-8 > rp ? 1e-8 : rp);  // Julia's max(1e-8, .) propagates NaN
+      rd = (rd != rd) ? rd : (1e-8 > rd ? 1e-8 : rd);
+      P.wp = P.wp / (rp * rp);
+      P.wd = P.wd / (rd * rd);
+      P.radius = 1.0;
+    } else {
+      const double* dist = B.red + 2 * kMaxScalars;
+      const bool avg = P.param_src == kTrParamDistAvg;
+      const double px = sqrt(P.wp * dist[avg ? SD_avg_x : SD_cur_x]);
+      const double dy = sqrt(P.wd * dist[avg ? SD_avg_y : SD_cur_y]);
+      P.radius = sqrt(px * px + dy * dy);
+    }
+  }
   TrXchg xc{seq_first, 0};
   __shared__ double sh[kTrMaxK * kTrWarps];
   __shared__ double tot[kTrMaxK];

@@ -59,6 +59,11 @@ struct Bufs {
   // evaluation-block scalar exchanges: two alternating receive buffers of world * kScBlock doubles
   double* scx = nullptr;                // local
   double* scx_peer[kMaxWorld] = {};
+  unsigned long long p2p_timeout_ns = 30000000000ull;  // a peer wait gives up after this long (FOLP_P2P_TIMEOUT_MS)
+  // ---- persistent take_step kernel (k_take_steps): grid barrier words and phase timers ----
+  unsigned* bar_top = nullptr;          // arrival counter of the grid barrier
+  unsigned long long* bar_gen = nullptr;  // release words (kBarGenStride apart): [0] master, [1 + g] group g: generation of the last completed barrier | abort bit
+  unsigned long long* timers = nullptr;   // [0] last stamp, [1..3] ns spent in the phases, [4] attempts (nullptr: off)
 };
 constexpr int kScBlock = 64;
 
@@ -101,17 +106,40 @@ struct TrState {
   int reserved0;
 };
 
+// Where k_tr_solve takes the weights / radius from: the struct as the host filled it, or -- so that
+// a whole evaluation block can be enqueued without a host round trip -- the reduced statistics of
+// the kernels that ran before it on the same stream (Bufs::red):
+//   kTrParamBounds  update_objective_bound_estimates (sp.jl:1015-1047): wp, wd are the norm weights;
+//                   the kernel divides them by max(1e-8, sqrt(wp |x_avg|^2))^2 resp. the dual analogue
+//                   (k_stats_n / k_stats_m sums), radius 1
+//   kTrParamDistAvg / kTrParamDistCur  compute_localized_duality_gaps (sp.jl:432-496): radius = weighted
+//                   distance of the average / current iterate to the last restart point (k_dist sums)
+enum TrParamSrc : int { kTrParamHost = 0, kTrParamBounds = 1, kTrParamDistAvg = 2, kTrParamDistCur = 3 };
 struct TrProblem {
   const double *px, *atp;   // primal center and A' * dual center
   const double *py, *axp;   // dual center and A * primal center
   double wp, wd, radius;
   int use_primal, use_dual, approx;
   const double* qxp;        // Q * primal center; nullptr for an LP
+  int param_src = kTrParamHost;
+  int reserved0 = 0;
 };
+constexpr int kTrSlots = 5;  // results of one evaluation block: bound estimates (primal, dual), gaps at avg / current / last restart
 
 // Q: CSR of the objective matrix, used only when B.has_q
 void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q,
                           int attempts, cudaStream_t s);
+// The same attempts as ONE cooperative launch (k_take_steps): the three phases of an attempt are
+// separated by grid barriers instead of kernel boundaries, the state lives in shared memory, and in
+// partitioned mode the peer exchanges ride on the barriers. take_steps_grid: co-resident CTAs the
+// kernel may use on this device (0: cooperative launch unavailable). Returns a cudaError_t.
+int take_steps_grid(int sm_count, bool dist);
+int launch_take_steps(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q, int attempts,
+                      int grid, cudaStream_t s);
+constexpr int kBarGroupSize = 32;       // CTAs polling one release word of the grid barrier
+constexpr int kBarL1Stride = 32;        // unsigned words between first-level counters (128 bytes)
+constexpr int kBarMaxGroups = 64;
+constexpr int kBarGenStride = 16;       // unsigned long long words between release words (128 bytes)
 // The pieces of one attempt in partitioned mode; without peer memory folp_api.cu interleaves them
 // with the NCCL exchanges (allgather xbar | allgather y+ | allgather of the 4 step-rule scalars).
 void launch_dist_primal(const Bufs& B, cudaStream_t s);

@@ -58,18 +58,23 @@ __device__ __forceinline__ TileHot load_hot(const Tile* tiles, int idx) {
   return h;
 }
 
-template <class Epi>
-__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A, Epi epi) {
-  __shared__ double s_red[32];
-  pdl_wait();
-  pdl_release();
-  if (!epi.begin()) return;
-  const double* __restrict__ xin = epi.input();
+// gather of the input vector. COH = false: read-only for the lifetime of the kernel (one product per
+// launch), the non-coherent path. COH = true: the persistent take_step kernel, where the gathered
+// vector is rewritten between grid barriers of the same launch -- a plain (coherent) load.
+template <bool COH>
+__device__ __forceinline__ double ld_gather(const double* p) {
+  if (COH) return *p;
+  return __ldg(p);
+}
+
+// The work items `first`, `first + stride`, ... of A, one per warp at a time; every row's sum goes to
+// epi.row(). Called by all threads of the CTA.
+template <class Epi, bool COH>
+__device__ __forceinline__ void spmv_items(const SpmvMat& A, Epi& epi, int first, int stride) {
+  const double* xin = epi.input();
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int warps_total = gridDim.x * kSpmvWarps;
-  for (int item = blockIdx.x * kSpmvWarps + (threadIdx.x >> 5); item < A.ntiles;
-       item += warps_total) {
+  for (int item = first; item < A.ntiles; item += stride) {
     const TileHot t = load_hot(A.tiles, item);
     const int kind = t.kind();
     if (kind == kTileThreadPerRow || kind == kTileThreadPerRowSorted) {
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
       if (maxlen > 0) load_round(0, c, a);
       for (int p0 = 0; p0 < maxlen; p0 += kGatherUnroll) {
 #pragma unroll
-        for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
+        for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? ld_gather<COH>(xin + c[u]) : 0.0;
         const bool more = p0 + kGatherUnroll < maxlen;  // warp-uniform
         if (more) load_round(p0 + kGatherUnroll, cn, an);
 #pragma unroll
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
         double a[kGatherUnroll], x[kGatherUnroll];
         load_round(p0, c, a);
 #pragma unroll
-        for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? __ldg(xin + c[u]) : 0.0;
+        for (int u = 0; u < kGatherUnroll; ++u) x[u] = c[u] >= 0 ? ld_gather<COH>(xin + c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u)
           if (c[u] >= 0) s += a[u] * x[u];  // ascending column order
@@ -153,13 +158,14 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
         const int c2 = ld_stream(A.colidx + k + 64), c3 = ld_stream(A.colidx + k + 96);
         const double a0 = ld_stream(A.vals + k), a1 = ld_stream(A.vals + k + 32);
         const double a2 = ld_stream(A.vals + k + 64), a3 = ld_stream(A.vals + k + 96);
-        const double x0 = __ldg(xin + c0), x1 = __ldg(xin + c1), x2 = __ldg(xin + c2), x3 = __ldg(xin + c3);
+        const double x0 = ld_gather<COH>(xin + c0), x1 = ld_gather<COH>(xin + c1);
+        const double x2 = ld_gather<COH>(xin + c2), x3 = ld_gather<COH>(xin + c3);
         s0 += a0 * x0;
         s1 += a1 * x1;
         s2 += a2 * x2;
         s3 += a3 * x3;
       }
-      for (; k < t.nnz_end; k += 32) s0 += ld_stream(A.vals + k) * __ldg(xin + ld_stream(A.colidx + k));
+      for (; k < t.nnz_end; k += 32) s0 += ld_stream(A.vals + k) * ld_gather<COH>(xin + ld_stream(A.colidx + k));
       double s = (s0 + s1) + (s2 + s3);
       s = warp_sum(s);
       const int r = t.row_begin;
@@ -188,6 +194,15 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A
                 Epi::kNumIn > 1 ? epi.in_ptr(1)[r] : 0.0, Epi::kNumIn > 2 ? epi.in_ptr(2)[r] : 0.0);
     }
   }
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(SpmvMat A, Epi epi) {
+  __shared__ double s_red[32];
+  pdl_wait();
+  pdl_release();
+  if (!epi.begin()) return;
+  spmv_items<Epi, false>(A, epi, blockIdx.x * kSpmvWarps + (threadIdx.x >> 5), gridDim.x * kSpmvWarps);
   __syncthreads();
   epi.finish(s_red);
 }

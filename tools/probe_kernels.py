@@ -54,8 +54,22 @@ def main():
         kms, ran = s.profile_attempts(args.attempts)
         per = [k / args.attempts for k in kms]
         if distributed.state() is not None:
-            out = {"rank": rank, "exchange": s.shard_info()["exchange"],
-                   "us": {k: v * 1e3 for k, v in zip(("primal", "dual", "trans", "finalize"), per)}, "iter_us": sum(per) * 1e3}
+            out = {"rank": rank, "env": env, "exchange": s.shard_info()["exchange"],
+                   "us": {k: round(v * 1e3, 2) for k, v in zip(("primal", "dual", "trans", "finalize"), per)},
+                   "iter_us": sum(per) * 1e3}
+            if args.iters:
+                import torch
+                import torch.distributed as td
+                c0 = s.counters()
+                td.barrier(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                bench.run_until(s, c0["iterations"] + args.iters)
+                torch.cuda.synchronize(); td.barrier()
+                dt = time.perf_counter() - t0
+                c1 = s.counters()
+                out["run_it_per_s"] = (c1["iterations"] - c0["iterations"]) / dt
+                out["pure_step_it_per_s"] = (c1["iterations"] - c0["iterations"]) / (
+                    c1["basic_algorithm_seconds"] - c0["basic_algorithm_seconds"])
             s.close()
             print(json.dumps(out), flush=True)
             continue
