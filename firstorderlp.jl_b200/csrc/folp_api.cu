@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <mutex>
+#include <tuple>
 #include <atomic>
 #include <new>
 #include <thread>
@@ -25,6 +27,13 @@ using namespace folp;
 
 namespace {
 thread_local std::string g_create_error;
+
+// NCCL communicators outlive handles: ncclCommInitRank costs 1.3 s (2 ranks) to 4.8 s (8 ranks), which
+// every folp_create of a process used to pay again. One communicator per (world, rank, device) is kept
+// for the lifetime of the process and reused by later handles (all ranks create their handles in the
+// same order, so either every rank finds its entry or none does). FOLP_NO_COMM_CACHE=1 disables it.
+std::mutex g_comm_mutex;
+std::map<std::tuple<int, int, int>, ncclComm_t> g_comm_cache;
 
 double now_sec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -136,6 +145,7 @@ struct folp_handle {
   int rank = 0, world = 1;
   const NcclApi* nccl = nullptr;
   ncclComm_t comm = nullptr;
+  bool comm_cached = false;         // the communicator belongs to the process-wide cache
   int64_t n_glob = 0, m_glob = 0;  // global sizes; n / m above are the local slice / rows
   int64_t n_pad = 0, m_pad = 0;    // exchange strides: ceil(n/world) (even), max rows per rank
   int64_t col0 = 0, row0 = 0;      // first global column / row owned by this rank
@@ -476,7 +486,7 @@ static void free_handle(folp_handle* h) {
   if (h->h_sc) cudaFreeHost(h->h_sc);
   for (int r = 0; r < kMaxWorld; ++r)
     if (h->peer_region[r]) cudaIpcCloseMemHandle(h->peer_region[r]);
-  if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
+  if (h->comm && h->nccl && !h->comm_cached) h->nccl->CommDestroy(h->comm);
   if (h->region) cudaFree(h->region);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -609,7 +619,8 @@ static int setup_peer_exchange(folp_handle* h) {
     B.yfull_peer[r] = base + fx;
     B.sc_peer[r] = base + fx + fy;
     B.scx_peer[r] = base + fx + fy + static_cast<size_t>(P) * kScBlock;
-    B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock);
+    B.hx_peer[r] = base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock;
+    B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
   }
   B.p2p = 1;
   if (const char* d = getenv("FOLP_DEBUG_FLAGS")) B.dbg = atoi(d);
@@ -930,7 +941,24 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "folp_dist carries a 128-byte id");
     memcpy(&id, dist->nccl_unique_id, sizeof(id));
-    NCCL_TRY(h->nccl->CommInitRank(&h->comm, h->world, id, h->rank));
+    const bool use_cache = getenv("FOLP_NO_COMM_CACHE") == nullptr;
+    const auto key = std::make_tuple(h->world, h->rank, h->device);
+    if (use_cache) {
+      std::lock_guard<std::mutex> lock(g_comm_mutex);
+      auto it = g_comm_cache.find(key);
+      if (it != g_comm_cache.end()) {
+        h->comm = it->second;
+        h->comm_cached = true;
+      }
+    }
+    if (!h->comm) {
+      NCCL_TRY(h->nccl->CommInitRank(&h->comm, h->world, id, h->rank));
+      if (use_cache) {
+        std::lock_guard<std::mutex> lock(g_comm_mutex);
+        g_comm_cache[key] = h->comm;
+        h->comm_cached = true;
+      }
+    }
   }
 
   pt.mark("device, stream, pinned state");
@@ -1089,7 +1117,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   } else {
     // one allocation, so that one CUDA IPC handle exposes everything a peer touches
     const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
-    const size_t region_doubles = fx + fy + 3 * static_cast<size_t>(P) * kScBlock +
+    const size_t region_doubles = fx + fy + 5 * static_cast<size_t>(P) * kScBlock +
                                   kNumFlagKinds * kMaxWorld + 16;
     TRY(cudaMalloc(&h->region, region_doubles * sizeof(double)));
     TRY(cudaMemsetAsync(h->region, 0, region_doubles * sizeof(double), h->stream));
@@ -1099,7 +1127,10 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     B.m_pad = static_cast<int>(h->m_pad);
     B.sc_recv = base + fx + fy;
     B.scx = base + fx + fy + static_cast<size_t>(P) * kScBlock;
-    B.flags = reinterpret_cast<unsigned long long*>(base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock);
+    B.hx = base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock;
+    B.flags = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
+    if ((rc = dev_alloc(h, &B.dseq, 2))) return rc;
+    TRY(cudaMemsetAsync(B.dseq, 0, 2 * sizeof(unsigned long long), h->stream));
     if ((rc = dev_zeros(h, &B.col_tmp, na))) return rc;
     if ((rc = dev_zeros(h, &B.sc_send, kScBlock))) return rc;
     if ((rc = dev_zeros(h, &h->d_rows, fy))) return rc;
@@ -1304,7 +1335,7 @@ static int exchange_block(folp_handle* h, const double* src, int count, const do
     launch_exchange(B, src, count, h->xchg_seq, parity, h->stream);
     CHECK_LAUNCH();
     h->launches += 1;
-    *recv = B.scx + static_cast<size_t>(parity) * h->world * kScBlock;
+    *recv = B.hx + static_cast<size_t>(parity) * h->world * kScBlock;
     return FOLP_OK;
   }
   NCCL_TRY(h->nccl->AllGather(src, B.sc_recv, kScBlock, ncclDouble, h->comm, h->stream));
@@ -1348,7 +1379,14 @@ static int pull_red(folp_handle* h, int off, int count, int nsum) {
 // out = A_r * v where v is a primal-indexed vector held as slices (local rows out)
 static int spmv_A(folp_handle* h, const double* v_slice, double* out_rows) {
   const double* in = v_slice;
-  if (h->world > 1) {
+  if (h->world > 1 && h->B.p2p) {
+    // peer memory: the slice is pushed into every rank's xbar (free between batches of attempts: the
+    // evaluation block of every rank lies between exchanges that all ranks take part in)
+    h->xchg_seq += 1;
+    launch_push_vec(h->B, v_slice, 0, h->xchg_seq, h->stream);
+    h->launches += 1;
+    in = h->B.xbar;
+  } else if (h->world > 1) {
     int rc = allgather_cols(h, v_slice, h->d_cols);
     if (rc) return rc;
     in = h->d_cols;
@@ -1361,7 +1399,12 @@ static int spmv_A(folp_handle* h, const double* v_slice, double* out_rows) {
 // out = (A' * w) on the local slice where w is dual-indexed, held as local rows
 static int spmv_At(folp_handle* h, const double* w_rows, double* out_slice) {
   const double* in = w_rows;
-  if (h->world > 1) {  // the column-slice matrix gathers from the padded rank-major full vector
+  if (h->world > 1 && h->B.p2p) {
+    h->xchg_seq += 1;
+    launch_push_vec(h->B, w_rows, 1, h->xchg_seq, h->stream);
+    h->launches += 1;
+    in = h->B.y_full;
+  } else if (h->world > 1) {  // the column-slice matrix gathers from the padded rank-major full vector
     NCCL_TRY(h->nccl->AllGather(w_rows, h->d_rows, static_cast<size_t>(h->m_pad), ncclDouble, h->comm,
                                 h->stream));
     in = h->d_rows;
@@ -1572,7 +1615,7 @@ static int tr_solve(folp_handle* h, const TrProblem& P, TrState* out, int slot) 
       TRY(cudaStreamSynchronize(h->stream));
       *out = *h->h_trs;
       h->tr_passes += out->passes;
-      h->xchg_seq += static_cast<unsigned long long>(out->exchanges);  // same count on every rank
+      // (k_tr_solve numbers its exchanges from the device-resident counter Bufs::dseq)
       if (h->world > 1) {
         unsigned timed_out = 0;
         TRY(cudaMemcpy(&timed_out, h->B.counters + 6, sizeof(unsigned), cudaMemcpyDeviceToHost));
@@ -1769,6 +1812,7 @@ static int run_restart_scheme(folp_handle* h, int64_t iterations_completed, doub
 // stops early and the remaining pieces are computed by the synchronous path.
 static int evaluate_enqueue_blind(folp_handle* h) {
   if (h->tr_grid <= 0 || getenv("FOLP_EVAL_SYNC") != nullptr) return FOLP_OK;
+  if (h->world > 1 && !h->B.p2p) return FOLP_OK;
   DevState* s = h->hs;
   const folp_params* rp = &h->prm;
   Bufs& B = h->B;
@@ -1796,14 +1840,23 @@ static int evaluate_enqueue_blind(folp_handle* h) {
   if (!(s->count_x > 0 && s->count_y > 0)) return FOLP_OK;  // run_restart_scheme returns at once
   launch_dist(B, B.red + 2 * kMaxScalars, h->stream);
   h->launches += 1;
+  if (h->world > 1) {  // rank-ordered totals of the local sums, back into B.red on every rank
+    const double* recv = nullptr;
+    int rc = exchange_block(h, B.red + 2 * kMaxScalars, kScBlock, &recv);
+    if (rc) return rc;
+    launch_combine_red(B, recv, 2 * kMaxScalars, SD_TOTAL, SD_TOTAL, 0, 0, 0, h->stream);
+    h->launches += 1;
+  }
   h->pre_dist = true;
   if (rp->restart_scheme == FOLP_NO_RESTARTS) return FOLP_OK;
   const int approx = rp->use_approximate_localized_duality_gap;
   TrProblem Pa{B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, 0.0, 1, 1, approx, B.has_q ? B.qx_avg : nullptr};
   Pa.param_src = kTrParamDistAvg;
   if (!solve(Pa, 2)) return FOLP_OK;
-  launch_spmv_plain(h->A, B.x[s->cur], B.ax_cur, B.grid_spmv, h->stream);
-  h->launches += 1;
+  {
+    int rc = spmv_A(h, B.x[s->cur], B.ax_cur);
+    if (rc) return rc;
+  }
   h->pre_ax_cur = true;
   TrProblem Pc{B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, 0.0, 1, 1, approx,
                B.has_q ? B.qx[s->cur] : nullptr};
@@ -1846,19 +1899,37 @@ static int evaluate(folp_handle* h, folp_eval* out) {
   h->launches += 3;
   h->pre_mask = 0;
   h->pre_dist = h->pre_ax_cur = false;
-  if (h->world == 1) {
-    // One GPU: the REST of the block's device work -- both bound-estimate solves, the distances to the
-    // last restart point, A * x_cur and the localized-gap solves -- is enqueued behind the statistics
+  const bool blind = (h->world == 1 || h->B.p2p) && h->tr_grid > 0 && getenv("FOLP_EVAL_SYNC") == nullptr;
+  if (h->world == 1 || blind) {
+    // The REST of the block's device work -- both bound-estimate solves, the distances to the last
+    // restart point, A * x_cur and the localized-gap solves -- is enqueued behind the statistics
     // without a host round trip (their weights / radii are formed on the device from the sums in
     // B.red, see TrParamSrc), and everything comes back with ONE copy and ONE synchronisation. The
     // scalar decisions below then consume the fetched results instead of launching and waiting seven
     // times per evaluation. (A terminating evaluation has computed restart candidates it does not use.)
+    // Partitioned mode over peer memory: the ranks' local sums are exchanged and combined in rank order
+    // on the device (same bits on every rank), the products gather through peer pushes: no NCCL call.
+    if (h->world > 1) {
+      static_assert(2 * kMaxScalars <= kScBlock, "both statistics blocks travel in one exchange");
+      const double* recv = nullptr;
+      if ((rc = exchange_block(h, B.red, kScBlock, &recv))) return rc;
+      launch_combine_red(B, recv, 0, SN_TOTAL, SN_NSUM, kMaxScalars, SM_TOTAL, SM_NSUM, h->stream);
+      h->launches += 1;
+    }
     if ((rc = evaluate_enqueue_blind(h))) return rc;
     TRY(cudaMemcpyAsync(h->h_red, B.red, sizeof(double) * 3 * kMaxScalars, cudaMemcpyDeviceToHost,
                         h->stream));
     if (h->pre_mask)
       TRY(cudaMemcpyAsync(h->h_trs, h->d_trs, sizeof(TrState) * kTrSlots, cudaMemcpyDeviceToHost, h->stream));
+    unsigned* timed_out = reinterpret_cast<unsigned*>(h->h_sc);
+    *timed_out = 0;
+    if (h->world > 1)
+      TRY(cudaMemcpyAsync(timed_out, B.counters + 6, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     TRY(cudaStreamSynchronize(h->stream));
+    if (*timed_out) {
+      h->err = "peer exchange timed out: a rank of the row partition stopped responding";
+      return FOLP_CUDA_ERROR;
+    }
     for (int k = 0; k < kTrSlots; ++k)
       if (h->pre_mask & (1u << k)) h->pre[k] = h->h_trs[k];
   } else {
@@ -2047,13 +2118,14 @@ extern "C" int folp_solve(folp_handle* h, folp_eval* evals, int64_t max_evals, i
   for (;;) {
     int rc = folp_run(h, &e);
     if (rc) return rc;
-    if (evals && (h->prm.record_iteration_stats || e.termination_reason != 0)) {  // :958-960
-      if (cnt < max_evals) evals[cnt++] = e;
-      else if (max_evals > 0) evals[max_evals - 1] = e;
+    if (h->prm.record_iteration_stats || e.termination_reason != 0) {  // :958-960
+      if (evals && cnt < max_evals) evals[cnt] = e;
+      else if (evals && max_evals > 0) evals[max_evals - 1] = e;  // full: the last slot follows the latest record
+      cnt += 1;
     }
     if (e.termination_reason != 0) break;
   }
-  if (num_evals) *num_evals = cnt;
+  if (num_evals) *num_evals = cnt;  // records produced; more than max_evals = the history was truncated
   if (termination_reason) *termination_reason = e.termination_reason;
   if (iteration_count) *iteration_count = e.iteration_number;
   return folp_get_solution(h, 0, 1, x_out, y_out);

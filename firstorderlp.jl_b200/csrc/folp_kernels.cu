@@ -40,6 +40,16 @@ __device__ __forceinline__ void p2p_signal(const Bufs& B, int kind, unsigned lon
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
     }
 }
+// The same after ONE system-scope fence issued by the caller: plain (relaxed) flag stores, so that
+// the fence's wait for the acknowledgements of everything pushed is paid once, not once per peer.
+__device__ __forceinline__ void p2p_signal_fenced(const Bufs& B, int kind, unsigned long long v) {
+#pragma unroll
+  for (int r = 0; r < kMaxWorld; ++r)
+    if (r < B.world) {
+      unsigned long long* f = B.flag_peer[r] + kind * kMaxWorld + B.rank;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+    }
+}
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -715,7 +725,7 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
       if (!(B.dbg & 2)) {
         asm volatile("fence.acq_rel.sys;" ::: "memory");
         const unsigned long long v = p2p_value(st, kind);
-        p2p_signal(B, kind, v);
+        p2p_signal_fenced(B, kind, v);
         lost = p2p_wait(B, kind, v);
       }
       s_abort = lost ? 1 : 0;
@@ -787,7 +797,7 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
                 }
               asm volatile("fence.acq_rel.sys;" ::: "memory");
               const unsigned long long v = p2p_value(st, 2);
-              p2p_signal(B, 2, v);
+              p2p_signal_fenced(B, 2, v);
               lost = (B.dbg & 2) ? false : p2p_wait(B, 2, v);
               for (int k = 0; k < 4; ++k) t[k] = 0.0;
               for (int r = 0; r < B.world; ++r)
@@ -1592,6 +1602,7 @@ __device__ __forceinline__ void grid_totals(cg::grid_group& grid, const Bufs& B,
 __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, TrState* trs,
                                                          double* part, unsigned long long seq_first) {
   cg::grid_group grid = cg::this_grid();
+  if (B.world > 1 && B.dseq) seq_first = __ldcg(B.dseq) + 1ull;  // every block reads it before block 0 rewrites it at the end (grid barriers in between)
   if (P.param_src != kTrParamHost) {  // same arithmetic as the host's (evaluate / run_restart_scheme in folp_api.cu)
     if (P.param_src == kTrParamBounds) {
       const double xs2 = B.red[SN_xs2], ys2 = B.red[kMaxScalars + SM_ys2];
@@ -1709,6 +1720,7 @@ __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, Tr
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st.exchanges = xc.count;
     *trs = st;
+    if (B.world > 1 && B.dseq) *B.dseq = xc.seq - 1ull;
   }
 }
 
@@ -1755,18 +1767,62 @@ __global__ void k_exchange(Bufs B, const double* __restrict__ src, int count, un
     const size_t slot = static_cast<size_t>(parity) * B.world * kScBlock + B.rank * kScBlock + k;
 #pragma unroll
     for (int r = 0; r < kMaxWorld; ++r)
-      if (r < B.world) B.scx_peer[r][slot] = v;
+      if (r < B.world) B.hx_peer[r][slot] = v;
   }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    p2p_signal(B, 3, seq);
-    p2p_wait(B, 3, seq);
+    p2p_signal(B, 4, seq);
+    p2p_wait(B, 4, seq);
   }
 }
 void launch_exchange(const Bufs& B, const double* src, int count, unsigned long long seq, int parity,
                      cudaStream_t s) {
   k_exchange<<<1, kScBlock, 0, s>>>(B, src, count, seq, parity);
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_push_vec(Bufs B, const double* __restrict__ src, int which,
+                                                          unsigned long long seq) {
+  const int len = which == 0 ? B.n : B.m;
+  const size_t off = which == 0 ? static_cast<size_t>(B.xbar_off) : static_cast<size_t>(B.rank) * B.m_pad;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const double v = src[i];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < B.world) (which == 0 ? B.xbar_peer[r] : B.yfull_peer[r])[off + i] = v;
+  }
+  if (last_block_arrive_sys(B.counters + 7) && threadIdx.x == 0) {
+    p2p_signal(B, 4, seq);
+    p2p_wait(B, 4, seq);
+  }
+}
+void launch_push_vec(const Bufs& B, const double* src, int which, unsigned long long seq, cudaStream_t s) {
+  const int len = which == 0 ? B.n : B.m;
+  int g = (len + kVecThreads - 1) / kVecThreads;
+  if (g > B.grid_vec / 2) g = B.grid_vec / 2;
+  if (g < 1) g = 1;
+  k_push_vec<<<g, kVecThreads, 0, s>>>(B, src, which, seq);
+}
+
+__global__ void k_combine_red(Bufs B, const double* __restrict__ recv, int off0, int count0, int nsum0,
+                              int off1, int count1, int nsum1) {
+  const int t = threadIdx.x;
+  int off, k, nsum;
+  if (t < count0) { off = off0; k = t; nsum = nsum0; }
+  else if (t < count0 + count1) { off = off1; k = t - count0; nsum = nsum1; }
+  else return;
+  const int col = off - off0 + k;  // position inside the exchanged block (it starts at off0)
+  double v = __ldcg(recv + col);
+  for (int r = 1; r < B.world; ++r) {
+    const double w = __ldcg(recv + r * kScBlock + col);
+    v = k < nsum ? v + w : fmax(v, w);
+  }
+  B.red[off + k] = v;
+}
+void launch_combine_red(const Bufs& B, const double* recv, int off0, int count0, int nsum0, int off1,
+                        int count1, int nsum1, cudaStream_t s) {
+  k_combine_red<<<1, 2 * kScBlock, 0, s>>>(B, recv, off0, count0, nsum0, off1, count1, nsum1);
 }
 
 // ---------------------------------------------------------------------------

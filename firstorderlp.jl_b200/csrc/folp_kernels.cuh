@@ -6,7 +6,7 @@
 namespace folp {
 
 constexpr int kMaxWorld = 8;
-constexpr int kNumFlagKinds = 4;  // xbar pushed | partial A'y ready | step-rule scalars pushed | evaluation scalars
+constexpr int kNumFlagKinds = 5;  // xbar pushed | y+ pushed | step-rule scalars pushed | device-sequenced evaluation scalars (k_tr_solve) | host-sequenced evaluation exchanges
 
 // Device pointers of one rank. Lengths: n_loc primal slice, m_loc dual rows.
 struct Bufs {
@@ -59,6 +59,12 @@ struct Bufs {
   // evaluation-block scalar exchanges: two alternating receive buffers of world * kScBlock doubles
   double* scx = nullptr;                // local
   double* scx_peer[kMaxWorld] = {};
+  // the same for the exchanges the HOST numbers (k_exchange, k_push_vec: flag kind 4); the ones above belong
+  // to k_tr_solve, which numbers its own (flag kind 3) from the device-resident counter dseq, so that a
+  // solve can be enqueued without the host knowing how many passes the previous one took
+  double* hx = nullptr;
+  double* hx_peer[kMaxWorld] = {};
+  unsigned long long* dseq = nullptr;   // exchanges made by k_tr_solve so far (the same on every rank)
   unsigned long long p2p_timeout_ns = 30000000000ull;  // a peer wait gives up after this long (FOLP_P2P_TIMEOUT_MS)
   // ---- persistent take_step kernel (k_take_steps): grid barrier words and phase timers ----
   unsigned* bar_top = nullptr;          // arrival counter of the grid barrier
@@ -179,6 +185,15 @@ void launch_tr_combine(const Bufs& B, const TrProblem& P, TrState* d_trs, int st
 // host-side count of such exchanges, identical on every rank)
 void launch_exchange(const Bufs& B, const double* src, int count, unsigned long long seq, int parity,
                      cudaStream_t s);
+// peer-memory allgather of the evaluation block: this rank's slice of a primal-indexed vector
+// (which = 0: into every rank's xbar staging) or its rows of a dual-indexed one (which = 1: into
+// y_full), then the same flag exchange; when the kernel has completed the full vector is local.
+void launch_push_vec(const Bufs& B, const double* src, int which, unsigned long long seq, cudaStream_t s);
+// Combines the per-rank blocks of reduced scalars an exchange delivered (recv: world * kScBlock,
+// rank-major) in rank order into B.red: two segments [off, off + count), the first nsum entries of a
+// segment are sums, the rest maxima (count1 = 0: one segment).
+void launch_combine_red(const Bufs& B, const double* recv, int off0, int count0, int nsum0, int off1,
+                        int count1, int nsum1, cudaStream_t s);
 void launch_scale_div(const double* in, const double* scale, double* out, int len, int grid,
                       cudaStream_t s);
 void launch_fill(double* p, double v, int64_t len, cudaStream_t s);

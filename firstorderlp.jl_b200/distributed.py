@@ -13,6 +13,7 @@ import os
 from typing import Optional
 
 _STATE: Optional[dict] = None
+_UID: Optional[bytes] = None  # the library keeps one NCCL communicator per process (and reuses it), so one id suffices
 
 
 def init(backend: str = "nccl") -> Optional[dict]:
@@ -45,12 +46,15 @@ def state() -> Optional[dict]:
 
 def new_dist():
     """Collective over all ranks: a folp_dist carrying a fresh ncclUniqueId (None when single)."""
+    global _UID
     if _STATE is None:
         return None
+    from . import lib
+
+    if _UID is not None and not os.environ.get("FOLP_NO_COMM_CACHE"):
+        return lib.make_dist(_STATE["rank"], _STATE["world_size"], _STATE["device"], _UID)
     import torch
     import torch.distributed as td
-
-    from . import lib
 
     dev = torch.device("cuda", _STATE["device"]) if _STATE["backend"] == "nccl" else torch.device("cpu")
     buf = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -58,4 +62,5 @@ def new_dist():
         buf.copy_(torch.frombuffer(bytearray(lib.nccl_unique_id()), dtype=torch.uint8))
     td.broadcast(buf, src=0)
     uid = bytes(buf.cpu().numpy().tobytes())
+    _UID = uid
     return lib.make_dist(_STATE["rank"], _STATE["world_size"], _STATE["device"], uid)

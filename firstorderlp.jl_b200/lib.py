@@ -263,7 +263,16 @@ class Solver:
         self._check(lib().folp_run(self._h, C.byref(e)))
         return e
 
-    def solve(self, max_evals: int = 1 << 16):
+    def solve(self, max_evals: Optional[int] = None):
+        """folp_solve. The record buffer is sized from the parameters: every evaluation when
+        record_iteration_stats is set (iteration_limit / termination_evaluation_frequency + the ten
+        per-iteration evaluations of the start), the final record only otherwise."""
+        if max_evals is None:
+            if self.params.record_iteration_stats:
+                freq = max(1, int(self.params.termination_evaluation_frequency))
+                max_evals = min(1 << 22, max(0, int(self.params.iteration_limit)) // freq + 16)
+            else:
+                max_evals = 1
         evals = (FolpEval * max_evals)()
         n_ev = C.c_int64()
         reason = C.c_int32()
@@ -272,7 +281,11 @@ class Solver:
         y = np.zeros(self.m)
         self._check(lib().folp_solve(self._h, evals, max_evals, C.byref(n_ev), C.byref(reason),
                                      C.byref(iters), _p(x), _p(y)))
-        return x, y, reason.value, iters.value, [evals[i] for i in range(n_ev.value)]
+        if n_ev.value > max_evals:  # folp_solve reports how many records there were, not how many fit
+            import warnings
+            warnings.warn(f"folp_solve produced {n_ev.value} records, only the first {max_evals - 1} and the "
+                          "last one were kept")
+        return x, y, reason.value, iters.value, [evals[i] for i in range(min(n_ev.value, max_evals))]
 
     def get_solution(self, which=0, unscaled=True):
         x = np.zeros(self.n)

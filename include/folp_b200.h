@@ -287,8 +287,12 @@ int folp_run(folp_handle* h, folp_eval* out);
 
 /* Loops folp_run until termination. evals may be NULL; otherwise up to
  * max_evals records are stored following record_iteration_stats semantics
- * (pdhg.jl:958-960) and *num_evals receives the count. x_out (n) / y_out (m)
- * receive the UNSCALED average iterate (sp.jl:55-77). */
+ * (pdhg.jl:958-960). *num_evals receives the number of records PRODUCED: if it
+ * exceeds max_evals the history was truncated (the first max_evals - 1 records
+ * and, in the last slot, the final one are kept) -- size the buffer from
+ * iteration_limit / termination_evaluation_frequency + 16 when
+ * record_iteration_stats is set, 1 otherwise. x_out (n) / y_out (m) receive the
+ * UNSCALED average iterate (sp.jl:55-77). */
 int folp_solve(folp_handle* h, folp_eval* evals, int64_t max_evals,
                int64_t* num_evals, int32_t* termination_reason,
                int32_t* iteration_count, double* x_out, double* y_out);
