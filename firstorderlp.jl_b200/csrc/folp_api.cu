@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -97,8 +99,79 @@ using IVec = std::vector<int, NoInit<int>>;
 using DVec = std::vector<double, NoInit<double>>;
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Single-process multi-GPU (folp_create_multi): the wrapper handle owns one sub-handle per device,
+// each driven by its own host thread running exactly the per-rank code of the one-process-per-GPU
+// mode; the threads meet only at create time (to swap the addresses of their exchange regions --
+// direct peer access inside one process, no CUDA IPC, no NCCL) and otherwise synchronise through the
+// same device-side flags as separate processes do.
+// ---------------------------------------------------------------------------
+struct MultiCtx {
+  int world = 0;
+  std::vector<folp_handle*> sub;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::function<int(int)> job;
+  uint64_t job_id = 0;
+  int pending = 0;
+  std::vector<int> rcs;
+  bool stop = false;
+  // create-time rendezvous of the ranks
+  std::vector<void*> regions;
+  std::vector<int> peer_ok;
+  int bar_count = 0;
+  uint64_t bar_gen = 0;
+  std::condition_variable cv_bar;
+  void barrier() {
+    std::unique_lock<std::mutex> lock(mu);
+    const uint64_t g = bar_gen;
+    if (++bar_count == world) {
+      bar_count = 0;
+      bar_gen += 1;
+      cv_bar.notify_all();
+    } else {
+      cv_bar.wait(lock, [&] { return bar_gen != g; });
+    }
+  }
+  // runs f(rank) on every rank's thread; returns the first non-zero status
+  int call(std::function<int(int)> f) {
+    std::unique_lock<std::mutex> lock(mu);
+    job = std::move(f);
+    job_id += 1;
+    pending = world;
+    cv_job.notify_all();
+    cv_done.wait(lock, [&] { return pending == 0; });
+    for (int r = 0; r < world; ++r)
+      if (rcs[r]) return rcs[r];
+    return 0;
+  }
+  void worker(int rank) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<int(int)> f;
+      {
+        std::unique_lock<std::mutex> lock(mu);
+        cv_job.wait(lock, [&] { return stop || job_id != seen; });
+        if (stop) return;
+        seen = job_id;
+        f = job;
+      }
+      const int rc = f(rank);
+      {
+        std::unique_lock<std::mutex> lock(mu);
+        rcs[rank] = rc;
+        if (--pending == 0) cv_done.notify_all();
+      }
+    }
+  }
+};
+
 struct folp_handle {
   std::string err;
+  MultiCtx* multi = nullptr;    // wrapper handle of folp_create_multi: everything below lives in multi->sub[r]
+  MultiCtx* shared = nullptr;   // sub-handle of a single-process multi-GPU solve: its ranks' rendezvous
+  bool shared_rendezvous_done = false;
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
@@ -137,6 +210,7 @@ struct folp_handle {
   TrState pre[kTrSlots];
   unsigned pre_mask = 0;
   bool pre_dist = false, pre_ax_cur = false;
+  int trm_grid = 0;   // > 0: all trust-region solves of an evaluation run as one cooperative kernel (k_tr_multi)
   int take_grid = 0;  // > 0: batches of take_step attempts run as one cooperative kernel (k_take_steps) on this many blocks
   unsigned long long* d_timers = nullptr;  // phase timers of k_take_steps (folp_debug_profile_attempts)
   std::map<int, cudaGraphExec_t> step_graphs;
@@ -550,9 +624,57 @@ extern "C" int folp_partition(int64_t m, int64_t n, int64_t nnz, const int64_t* 
 // attempt travel as plain stores. Falls back to the NCCL exchanges
 // (FOLP_NO_P2P=1, more than kMaxWorld ranks, or IPC refused on any rank).
 // ---------------------------------------------------------------------------
+// The pointers of one rank's exchange region as the kernels use them (own region or a peer's mapping).
+static void set_peer_pointers(folp_handle* h, int r, void* region) {
+  Bufs& B = h->B;
+  const int P = h->world;
+  const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
+  double* base = static_cast<double*>(region);
+  B.xbar_peer[r] = base;
+  B.yfull_peer[r] = base + fx;
+  B.sc_peer[r] = base + fx + fy;
+  B.scx_peer[r] = base + fx + fy + static_cast<size_t>(P) * kScBlock;
+  B.hx_peer[r] = base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock;
+  B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
+}
+
+// Single-process multi-GPU: the ranks are threads of this process; every device enables direct
+// peer access to every other one and the region addresses are swapped through host memory.
+static int setup_peer_exchange_in_process(folp_handle* h) {
+  MultiCtx* mc = h->shared;
+  const int P = h->world;
+  int ok = P <= kMaxWorld ? 1 : 0;
+  for (int r = 0; r < P && ok; ++r) {
+    const int peer = mc->sub[r]->device;
+    if (r == h->rank || peer == h->device) continue;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, h->device, peer) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+    cudaGetLastError();
+  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) ok = 0;  // the region is zeroed before any peer can write into it
+  mc->regions[h->rank] = h->region;
+  mc->peer_ok[h->rank] = ok;
+  h->shared_rendezvous_done = true;
+  mc->barrier();
+  for (int r = 0; r < P; ++r) ok = ok && mc->peer_ok[r];
+  if (!ok) {
+    h->err = "single-process multi-GPU needs direct peer access between all selected devices";
+    mc->barrier();
+    return FOLP_UNSUPPORTED;
+  }
+  for (int r = 0; r < P; ++r) set_peer_pointers(h, r, mc->regions[r]);
+  h->B.p2p = 1;
+  if (const char* d = getenv("FOLP_DEBUG_FLAGS")) h->B.dbg = atoi(d);
+  mc->barrier();
+  return FOLP_OK;
+}
+
 static int setup_peer_exchange(folp_handle* h) {
   Bufs& B = h->B;
   const int P = h->world;
+  if (h->shared) return setup_peer_exchange_in_process(h);
   static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(int) <= kScBlock * sizeof(double), "handle fits a block");
   struct Msg {
     cudaIpcMemHandle_t handle;
@@ -612,16 +734,7 @@ static int setup_peer_exchange(folp_handle* h) {
     B.p2p = 0;
     return FOLP_OK;
   }
-  const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
-  for (int r = 0; r < P; ++r) {
-    double* base = static_cast<double*>(r == h->rank ? h->region : h->peer_region[r]);
-    B.xbar_peer[r] = base;
-    B.yfull_peer[r] = base + fx;
-    B.sc_peer[r] = base + fx + fy;
-    B.scx_peer[r] = base + fx + fy + static_cast<size_t>(P) * kScBlock;
-    B.hx_peer[r] = base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock;
-    B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
-  }
+  for (int r = 0; r < P; ++r) set_peer_pointers(h, r, r == h->rank ? h->region : h->peer_region[r]);
   B.p2p = 1;
   if (const char* d = getenv("FOLP_DEBUG_FLAGS")) B.dbg = atoi(d);
   if (B.dbg & 4) {  // probe: gather from private copies of the exchanged vectors
@@ -900,7 +1013,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   h->use_graphs = getenv("FOLP_NO_GRAPHS") == nullptr;
   h->world = dist ? dist->world_size : 1;
   h->rank = dist ? dist->rank : 0;
-  if (h->world > 1 && !dist->nccl_unique_id) {
+  if (h->world > 1 && !dist->nccl_unique_id && !h->shared) {
     h->err = "folp_dist.nccl_unique_id is required when world_size > 1";
     return FOLP_INVALID_ARGUMENT;
   }
@@ -935,7 +1048,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_trs), sizeof(TrState) * kTrSlots));
   TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_sc), sizeof(double) * h->world * kScBlock));
 
-  if (h->world > 1) {
+  if (h->world > 1 && !h->shared) {
     h->nccl = nccl_api(&h->err);
     if (!h->nccl) return FOLP_NCCL_ERROR;
     ncclUniqueId id;
@@ -1002,7 +1115,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         const size_t q_bytes = has_q ? static_cast<size_t>(4 * (n + 17) + 12 * (qnnz + 32) + 32 * (n / 8 + qnnz / kChunkNnz + 64) +
                                                            8 * (n + 16) + 8 * 256 + 5 * 8 * (n + 48))
                                      : 0;
-        const size_t vec_bytes = static_cast<size_t>(8) * (19 * (n + 48) + 13 * (m + 48)) +
+        const size_t vec_bytes = static_cast<size_t>(8) * (27 * (n + 48) + 21 * (m + 48)) +
                                  sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 17);
         if ((rc = arena_reserve(h, mat_bytes(n, nnz, hm.pk_t) + mat_bytes(m, nnz, hm.pk_a) + q_bytes + vec_bytes)))
           return rc;
@@ -1181,6 +1294,11 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   }
   if ((rc = dev_zeros(h, &B.tr_t, std::max(nl + ml, P > 1 ? P * std::max(na, ma) : n + m)))) return rc;
   if ((rc = dev_zeros(h, &B.tr_d, std::max(nl + ml, n + m)))) return rc;
+  if (h->tr_grid > 0 && getenv("FOLP_TR_SINGLE") == nullptr) h->trm_grid = tr_multi_grid(h->sm_count);
+  if (h->trm_grid > 0) {
+    if ((rc = dev_zeros(h, &B.trm_t, static_cast<size_t>(4) * (nl + ml)))) return rc;
+    if ((rc = dev_zeros(h, &B.trm_d, static_cast<size_t>(4) * (nl + ml)))) return rc;
+  }
   if ((rc = dev_zeros(h, &B.part, static_cast<size_t>(kNumSlots) * kMaxScalars * kMaxPartialBlocks)))
     return rc;
   if ((rc = dev_zeros(h, &B.red, static_cast<size_t>(4) * kMaxScalars))) return rc;
@@ -1273,7 +1391,116 @@ extern "C" int folp_create(const folp_problem* problem, const folp_params* param
   return FOLP_OK;
 }
 
+static void destroy_multi(folp_handle* w) {
+  MultiCtx* mc = w->multi;
+  if (!mc) return;
+  if (!mc->workers.empty()) {
+    mc->call([mc](int r) {
+      free_handle(mc->sub[r]);
+      mc->sub[r] = nullptr;
+      return 0;
+    });
+    {
+      std::unique_lock<std::mutex> lock(mc->mu);
+      mc->stop = true;
+      mc->cv_job.notify_all();
+    }
+    for (auto& t : mc->workers) t.join();
+  } else {
+    for (folp_handle* q : mc->sub) free_handle(q);
+  }
+  delete mc;
+  w->multi = nullptr;
+}
+
+extern "C" int folp_create_multi(const folp_problem* problem, const folp_params* params, int32_t n_gpus,
+                                 const int32_t* device_ids, folp_handle** out) {
+  if (!problem || !params || !out || n_gpus < 1 || n_gpus > kMaxWorld) {
+    g_create_error = "null argument or n_gpus outside 1..8";
+    return FOLP_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  if (n_gpus == 1) {
+    folp_dist d{0, 1, device_ids ? device_ids[0] : 0, 0, nullptr};
+    if (!device_ids && cudaGetDevice(&d.device) != cudaSuccess) d.device = 0;
+    return folp_create(problem, params, &d, out);
+  }
+  for (int a = 0; a < n_gpus; ++a)
+    for (int b = 0; b < a; ++b)
+      if (device_ids && device_ids[a] == device_ids[b]) {
+        g_create_error = "device_ids must be distinct";
+        return FOLP_INVALID_ARGUMENT;
+      }
+  folp_handle* w = new (std::nothrow) folp_handle();
+  MultiCtx* mc = new (std::nothrow) MultiCtx();
+  if (!w || !mc) {
+    delete w;
+    delete mc;
+    g_create_error = "host allocation failed";
+    return FOLP_OUT_OF_MEMORY;
+  }
+  w->multi = mc;
+  mc->world = n_gpus;
+  mc->rcs.assign(static_cast<size_t>(n_gpus), 0);
+  mc->regions.assign(static_cast<size_t>(n_gpus), nullptr);
+  mc->peer_ok.assign(static_cast<size_t>(n_gpus), 0);
+  for (int r = 0; r < n_gpus; ++r) {
+    folp_handle* q = new folp_handle();
+    q->shared = mc;
+    q->device = device_ids ? device_ids[r] : r;
+    mc->sub.push_back(q);
+  }
+  for (int r = 0; r < n_gpus; ++r) mc->workers.emplace_back([mc, r] { mc->worker(r); });
+  const int rc = mc->call([&](int r) {
+    folp_handle* q = mc->sub[r];
+    folp_dist d{r, n_gpus, q->device, 0, nullptr};
+    int rc_;
+    try {
+      rc_ = create_impl(q, problem, params, &d);
+    } catch (const std::bad_alloc&) {
+      q->err = "host allocation failed";
+      rc_ = FOLP_OUT_OF_MEMORY;
+    }
+    if (rc_ && !q->shared_rendezvous_done) {  // failed before the ranks met: let the others through (they fail too)
+      mc->peer_ok[r] = 0;
+      q->shared_rendezvous_done = true;
+      mc->barrier();
+      mc->barrier();
+    }
+    return rc_;
+  });
+  if (rc) {
+    g_create_error = "folp_create_multi failed";
+    for (folp_handle* q : mc->sub)
+      if (q && !q->err.empty()) { g_create_error = q->err; break; }
+    destroy_multi(w);
+    delete w;
+    return rc;
+  }
+  w->prm = *params;
+  w->world = n_gpus;
+  w->n_glob = problem->num_variables;
+  w->m_glob = problem->num_constraints;
+  *out = w;
+  return FOLP_OK;
+}
+
+// runs fn on every rank's thread and surfaces the first failing rank's message
+static int multi_dispatch(folp_handle* w, std::function<int(folp_handle*, int)> fn) {
+  MultiCtx* mc = w->multi;
+  const int rc = mc->call([&](int r) { return fn(mc->sub[r], r); });
+  if (rc)
+    for (folp_handle* q : mc->sub)
+      if (q && !q->err.empty()) { w->err = q->err; break; }
+  return rc;
+}
+
 extern "C" void folp_destroy(folp_handle* h) {
+  if (h && h->multi) {
+    destroy_multi(h);
+    delete h;
+    return;
+  }
   if (h && getenv("FOLP_TIMING"))
     fprintf(stderr, "[folp_destroy] iterations %lld, launches %lld, trust-region solves %lld, passes %lld, "
                     "take_step seconds %.4f\n",
@@ -1414,33 +1641,70 @@ static int spmv_At(folp_handle* h, const double* w_rows, double* out_slice) {
   h->launches += 1;
   return FOLP_OK;
 }
-// host_out (global length) <- a primal-indexed device vector held as slices
-static int fetch_cols(folp_handle* h, const double* slice, double* host_out) {
-  if (!host_out || h->n_glob == 0) return FOLP_OK;
-  const double* src = slice;
-  if (h->world > 1) {
-    int rc = allgather_cols(h, slice, h->d_cols);
-    if (rc) return rc;
-    src = h->d_cols;
-  }
-  TRY(cudaMemcpyAsync(host_out, src, sizeof(double) * h->n_glob, cudaMemcpyDeviceToHost, h->stream));
+// Peer-memory mode: an all-rank rendezvous with no payload. A rank raises its flag from a kernel that is
+// stream-ordered behind everything it enqueued before, so once a rank has passed the rendezvous every
+// peer has finished reading (or copying out) whatever the previous exchange delivered into its staging.
+static int peer_rendezvous(folp_handle* h) {
+  h->xchg_seq += 1;
+  launch_exchange(h->B, nullptr, 0, h->xchg_seq, 0, h->stream);
+  CHECK_LAUNCH();
+  h->launches += 1;
   return FOLP_OK;
 }
-// host_out (global length) <- a dual-indexed device vector held as local rows
+// host_out (global length) <- a primal-indexed device vector held as slices. A collective in
+// partitioned mode: every rank takes part in the gather even when it wants no copy (host_out NULL).
+// Peer-memory mode stages the gather in xbar / y_full (free outside a batch of attempts); unlike the
+// pushes of the evaluation block, which are separated by exchanges all ranks take part in, fetches
+// may follow each other directly and are read by the copy engine: a rendezvous before (the peers are
+// done with the staging) and after (so is this rank, before anybody's next push).
+static int fetch_cols(folp_handle* h, const double* slice, double* host_out) {
+  if (h->n_glob == 0) return FOLP_OK;
+  if (h->world == 1 && !host_out) return FOLP_OK;
+  const double* src = slice;
+  int rc;
+  if (h->world > 1 && h->B.p2p) {
+    if ((rc = peer_rendezvous(h))) return rc;
+    h->xchg_seq += 1;
+    launch_push_vec(h->B, slice, 0, h->xchg_seq, h->stream);
+    h->launches += 1;
+    src = h->B.xbar;
+  } else if (h->world > 1) {
+    if ((rc = allgather_cols(h, slice, h->d_cols))) return rc;
+    src = h->d_cols;
+  }
+  if (host_out)
+    TRY(cudaMemcpyAsync(host_out, src, sizeof(double) * h->n_glob, cudaMemcpyDeviceToHost, h->stream));
+  if (h->world > 1 && h->B.p2p && (rc = peer_rendezvous(h))) return rc;
+  return FOLP_OK;
+}
+// host_out (global length) <- a dual-indexed device vector held as local rows (collective, as above)
 static int fetch_rows(folp_handle* h, const double* rows, double* host_out) {
-  if (!host_out || h->m_glob == 0) return FOLP_OK;
+  if (h->m_glob == 0) return FOLP_OK;
   if (h->world == 1) {
-    TRY(cudaMemcpyAsync(host_out, rows, sizeof(double) * h->m_glob, cudaMemcpyDeviceToHost, h->stream));
+    if (host_out)
+      TRY(cudaMemcpyAsync(host_out, rows, sizeof(double) * h->m_glob, cudaMemcpyDeviceToHost, h->stream));
     return FOLP_OK;
   }
-  NCCL_TRY(h->nccl->AllGather(rows, h->d_rows, static_cast<size_t>(h->m_pad), ncclDouble, h->comm,
-                              h->stream));
-  for (int r = 0; r < h->world; ++r) {
-    const int64_t cnt = h->row_begin[r + 1] - h->row_begin[r];
-    if (cnt > 0)
-      TRY(cudaMemcpyAsync(host_out + h->row_begin[r], h->d_rows + r * h->m_pad, sizeof(double) * cnt,
-                          cudaMemcpyDeviceToHost, h->stream));
+  const double* full = h->d_rows;
+  int rc;
+  if (h->B.p2p) {
+    if ((rc = peer_rendezvous(h))) return rc;
+    h->xchg_seq += 1;
+    launch_push_vec(h->B, rows, 1, h->xchg_seq, h->stream);
+    h->launches += 1;
+    full = h->B.y_full;
+  } else {
+    NCCL_TRY(h->nccl->AllGather(rows, h->d_rows, static_cast<size_t>(h->m_pad), ncclDouble, h->comm,
+                                h->stream));
   }
+  if (host_out)
+    for (int r = 0; r < h->world; ++r) {
+      const int64_t cnt = h->row_begin[r + 1] - h->row_begin[r];
+      if (cnt > 0)
+        TRY(cudaMemcpyAsync(host_out + h->row_begin[r], full + r * h->m_pad, sizeof(double) * cnt,
+                            cudaMemcpyDeviceToHost, h->stream));
+    }
+  if (h->B.p2p && (rc = peer_rendezvous(h))) return rc;
   return FOLP_OK;
 }
 
@@ -1836,39 +2100,83 @@ static int evaluate_enqueue_blind(folp_handle* h) {
   TrProblem Pd = Pp;
   Pd.use_primal = 0;
   Pd.use_dual = 1;
-  if (!solve(Pp, 0) || !solve(Pd, 1)) return FOLP_OK;
-  if (!(s->count_x > 0 && s->count_y > 0)) return FOLP_OK;  // run_restart_scheme returns at once
-  launch_dist(B, B.red + 2 * kMaxScalars, h->stream);
-  h->launches += 1;
-  if (h->world > 1) {  // rank-ordered totals of the local sums, back into B.red on every rank
-    const double* recv = nullptr;
-    int rc = exchange_block(h, B.red + 2 * kMaxScalars, kScBlock, &recv);
-    if (rc) return rc;
-    launch_combine_red(B, recv, 2 * kMaxScalars, SD_TOTAL, SD_TOTAL, 0, 0, 0, h->stream);
-    h->launches += 1;
-  }
-  h->pre_dist = true;
-  if (rp->restart_scheme == FOLP_NO_RESTARTS) return FOLP_OK;
+  const bool restart_possible = s->count_x > 0 && s->count_y > 0;  // else run_restart_scheme returns at once
+  const bool gaps = restart_possible && rp->restart_scheme != FOLP_NO_RESTARTS;
   const int approx = rp->use_approximate_localized_duality_gap;
   TrProblem Pa{B.avg_x, B.aty_avg, B.avg_y, B.ax_avg, wp, wd, 0.0, 1, 1, approx, B.has_q ? B.qx_avg : nullptr};
   Pa.param_src = kTrParamDistAvg;
+  TrProblem Pc{B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, 0.0, 1, 1, approx,
+               B.has_q ? B.qx[s->cur] : nullptr};
+  Pc.param_src = kTrParamDistCur;
+  const double pw = s->primal_weight;
+  const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);  // sp.jl:549-593
+  TrProblem Pl{B.last_x, B.last_aty, B.last_y, B.last_ax, wp, wd, d_last, 1, 1, approx,
+               B.has_q ? B.last_qx : nullptr};
+  auto distances = [&]() -> int {
+    launch_dist(B, B.red + 2 * kMaxScalars, h->stream);
+    h->launches += 1;
+    if (h->world > 1) {  // rank-ordered totals of the local sums, back into B.red on every rank
+      const double* recv = nullptr;
+      int rc = exchange_block(h, B.red + 2 * kMaxScalars, kScBlock, &recv);
+      if (rc) return rc;
+      launch_combine_red(B, recv, 2 * kMaxScalars, SD_TOTAL, SD_TOTAL, 0, 0, 0, h->stream);
+      h->launches += 1;
+    }
+    h->pre_dist = true;
+    return FOLP_OK;
+  };
+  if (h->trm_grid > 0) {
+    // every solve of the block in ONE cooperative kernel, behind everything it reads
+    TrMulti M{};
+    M.P[0] = Pp;
+    M.P[1] = Pd;
+    M.nslots = 2;
+    int rc;
+    if (restart_possible && (rc = distances())) return rc;
+    if (gaps) {
+      if ((rc = spmv_A(h, B.x[s->cur], B.ax_cur))) return rc;
+      h->pre_ax_cur = true;
+      M.P[2] = Pa;
+      M.P[3] = Pc;
+      M.nslots = 4;
+      if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) {
+        M.P[4] = Pl;
+        M.nslots = 5;
+      }
+    }
+    const cudaError_t le = static_cast<cudaError_t>(launch_tr_multi(B, M, h->d_trs, h->trm_grid, h->stream));
+    if (le == cudaSuccess) {
+      h->launches += 1;
+      h->pre_mask = (1u << M.nslots) - 1u;
+      return FOLP_OK;
+    }
+    cudaGetLastError();
+    if (h->world > 1) {
+      h->err = std::string("cooperative launch of k_tr_multi refused on this rank: ") + cudaGetErrorString(le);
+      return FOLP_CUDA_ERROR;
+    }
+    h->trm_grid = 0;  // one kernel per solve from now on; dist / ax_cur above stay valid
+    if (!solve(Pp, 0) || !solve(Pd, 1)) return FOLP_OK;
+    if (!gaps) return FOLP_OK;
+    if (!solve(Pa, 2) || !solve(Pc, 3)) return FOLP_OK;
+    if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) solve(Pl, 4);
+    return FOLP_OK;
+  }
+  if (!solve(Pp, 0) || !solve(Pd, 1)) return FOLP_OK;
+  if (!restart_possible) return FOLP_OK;
+  {
+    int rc = distances();
+    if (rc) return rc;
+  }
+  if (!gaps) return FOLP_OK;
   if (!solve(Pa, 2)) return FOLP_OK;
   {
     int rc = spmv_A(h, B.x[s->cur], B.ax_cur);
     if (rc) return rc;
   }
   h->pre_ax_cur = true;
-  TrProblem Pc{B.x[s->cur], B.aty[s->cur], B.y[s->cur], B.ax_cur, wp, wd, 0.0, 1, 1, approx,
-               B.has_q ? B.qx[s->cur] : nullptr};
-  Pc.param_src = kTrParamDistCur;
   if (!solve(Pc, 3)) return FOLP_OK;
-  if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) {  // sp.jl:549-593 (needed unless the restart is forced)
-    const double pw = s->primal_weight;
-    const double d_last = sqrt(h->pd_last * h->pd_last * pw + h->dd_last * h->dd_last / pw);
-    TrProblem Pl{B.last_x, B.last_aty, B.last_y, B.last_ax, wp, wd, d_last, 1, 1, approx,
-                 B.has_q ? B.last_qx : nullptr};
-    solve(Pl, 4);
-  }
+  if (rp->restart_scheme == FOLP_ADAPTIVE_NORMALIZED) solve(Pl, 4);
   return FOLP_OK;
 }
 
@@ -2060,6 +2368,12 @@ static int64_t next_evaluation(const folp_handle* h, int64_t k) {
 
 extern "C" int folp_run(folp_handle* h, folp_eval* out) {
   if (!h || !out) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) {  // every rank returns the same global record; rank 0's goes to the caller
+    std::vector<folp_eval> scratch(static_cast<size_t>(h->multi->world));
+    const int rc = multi_dispatch(h, [&](folp_handle* q, int r) { return folp_run(q, r == 0 ? out : &scratch[r]); });
+    if (!rc) h->terminated = out->termination_reason != 0;
+    return rc;
+  }
   if (h->terminated) {
     *out = h->last_eval;
     return FOLP_OK;
@@ -2078,6 +2392,10 @@ extern "C" int folp_run(folp_handle* h, folp_eval* out) {
 extern "C" int folp_get_solution(folp_handle* h, int which, int unscaled, double* x_out,
                                  double* y_out) {
   if (!h) return FOLP_INVALID_ARGUMENT;
+  if (h->multi)
+    return multi_dispatch(h, [&](folp_handle* q, int r) {
+      return folp_get_solution(q, which, unscaled, r == 0 ? x_out : nullptr, r == 0 ? y_out : nullptr);
+    });
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   Bufs& B = h->B;
@@ -2136,6 +2454,7 @@ extern "C" int folp_solve(folp_handle* h, folp_eval* evals, int64_t max_evals, i
 // ---------------------------------------------------------------------------
 extern "C" int folp_debug_attempts(folp_handle* h, int64_t attempts) {
   if (!h) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) return multi_dispatch(h, [&](folp_handle* q, int) { return folp_debug_attempts(q, attempts); });
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   int rc;
@@ -2162,6 +2481,11 @@ extern "C" int folp_debug_attempts(folp_handle* h, int64_t attempts) {
 extern "C" int folp_debug_state(folp_handle* h, double* x, double* y, double* dual_product,
                                 double* sum_x, double* sum_y, folp_debug_scalars* out) {
   if (!h) return FOLP_INVALID_ARGUMENT;
+  if (h->multi)
+    return multi_dispatch(h, [&](folp_handle* q, int r) {
+      return r == 0 ? folp_debug_state(q, x, y, dual_product, sum_x, sum_y, out)
+                    : folp_debug_state(q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    });
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   Bufs& B = h->B;
@@ -2202,6 +2526,8 @@ extern "C" int folp_debug_state(folp_handle* h, double* x, double* y, double* du
 extern "C" int folp_debug_set_state(folp_handle* h, const double* x, const double* y,
                                     double step_size, double primal_weight) {
   if (!h) return FOLP_INVALID_ARGUMENT;
+  if (h->multi)
+    return multi_dispatch(h, [&](folp_handle* q, int) { return folp_debug_set_state(q, x, y, step_size, primal_weight); });
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   Bufs& B = h->B;
@@ -2230,6 +2556,14 @@ extern "C" int folp_debug_set_state(folp_handle* h, const double* x, const doubl
 
 extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, double* out) {
   if (!h || !in || !out) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) {
+    const size_t len = static_cast<size_t>(transpose ? h->n_glob : h->m_glob);
+    std::vector<std::vector<double>> scratch(static_cast<size_t>(h->multi->world));
+    return multi_dispatch(h, [&](folp_handle* q, int r) {
+      if (r != 0) scratch[r].resize(len + 1);
+      return folp_debug_spmv(q, transpose, in, r == 0 ? out : scratch[r].data());
+    });
+  }
   cudaSetDevice(h->device);
   Bufs& B = h->B;
   int rc;
@@ -2256,6 +2590,12 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
 extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, double ms_out[8],
                                            int64_t* attempts_run) {
   if (!h || !ms_out) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) {
+    std::vector<double> scratch(static_cast<size_t>(8 * h->multi->world));
+    return multi_dispatch(h, [&](folp_handle* q, int r) {
+      return folp_debug_profile_attempts(q, attempts, r == 0 ? ms_out : &scratch[8 * r], r == 0 ? attempts_run : nullptr);
+    });
+  }
   cudaSetDevice(h->device);
   DevState* s = h->hs;
   int rc;
@@ -2327,6 +2667,12 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
 
 extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, double* ms_out) {
   if (!h || !ms_out || reps < 1) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) {
+    std::vector<double> scratch(static_cast<size_t>(h->multi->world));
+    return multi_dispatch(h, [&](folp_handle* q, int r) {
+      return folp_debug_time_spmv(q, transpose, reps, r == 0 ? ms_out : &scratch[r]);
+    });
+  }
   cudaSetDevice(h->device);
   Bufs& B = h->B;
   // input: the live iterate (x or y); output: trust-region scratch
@@ -2471,11 +2817,20 @@ extern "C" int folp_debug_host_problem_spmv(const folp_problem* p, int transpose
                    : emulate_packed_spmv(hm.pk_a, hm.rp2, hm.ac, hm.av, m, x, y, 0, nullptr);
 }
 
-extern "C" void* folp_debug_stream(folp_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+extern "C" void* folp_debug_stream(folp_handle* h) {
+  if (h && h->multi) h = h->multi->sub[0];
+  return h ? static_cast<void*>(h->stream) : nullptr;
+}
 
 extern "C" int folp_counters(folp_handle* h, int64_t* kernel_launches,
                              double* basic_algorithm_seconds, int64_t* iterations) {
   if (!h) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) {  // rank 0's clocks; launches summed over the devices
+    int rc = folp_counters(h->multi->sub[0], kernel_launches, basic_algorithm_seconds, iterations);
+    if (!rc && kernel_launches)
+      for (int r = 1; r < h->multi->world; ++r) *kernel_launches += h->multi->sub[r]->launches;
+    return rc;
+  }
   if (kernel_launches) *kernel_launches = h->launches;
   if (basic_algorithm_seconds) *basic_algorithm_seconds = h->basic_time;
   if (iterations) *iterations = h->hs->iterations;
@@ -2484,12 +2839,14 @@ extern "C" int folp_counters(folp_handle* h, int64_t* kernel_launches,
 
 extern "C" int folp_exchange_mode(folp_handle* h) {
   if (!h) return -1;
+  if (h->multi) h = h->multi->sub[0];
   return h->world == 1 ? 0 : (h->B.p2p ? 2 : 1);
 }
 
 extern "C" int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end,
                                int64_t* col_begin, int64_t* col_end, int64_t* local_nonzeros) {
   if (!h) return FOLP_INVALID_ARGUMENT;
+  if (h->multi) h = h->multi->sub[0];  // rank 0's shard
   if (row_begin) *row_begin = h->row0;
   if (row_end) *row_end = h->row0 + h->m;
   if (col_begin) *col_begin = h->col0;

@@ -1724,6 +1724,418 @@ __global__ void __launch_bounds__(kTrThreads) k_tr_solve(Bufs B, TrProblem P, Tr
   }
 }
 
+// ---------------------------------------------------------------------------
+// k_tr_multi: ALL trust-region solves of one evaluation block in one cooperative kernel.
+//
+// An evaluation needs up to five bound-constrained trust-region problems (slots: bound estimates
+// on the primal / on the dual part at the average, localized duality gaps at the average, at the
+// current iterate and at the last restart point). As five k_tr_solve launches they cost ~480 us of
+// the ~740 us evaluation block on the 1e6 x 1e6 x 1e7 workload, and ~30 grid-wide barriers -- in
+// partitioned mode as many cross-rank scalar exchanges. Here the searches advance together: one
+// barrier (and one exchange of up to 42 scalars) per stage for all slots, the slots that share a
+// centre (the three at the average) share its loads, and the passes of a slot stop as soon as its
+// own partition stops changing. Per slot the arithmetic is k_tr_solve's (same per-element
+// formulas, tr_setup / tr_update); only the shape of the reductions differs (512 threads).
+// Per centre there is at most one slot over both index ranges (a gap), one over the primal range
+// and one over the dual range only (the bound estimates); the host checks that.
+// Scratch: slots 0 and 1 cover disjoint index ranges and share one (n+m) pair of B.trm_t / B.trm_d,
+// slots 2..4 own one each.
+// ---------------------------------------------------------------------------
+constexpr int kTrmThreads = 512;
+constexpr int kTrmWarps = kTrmThreads / 32;
+constexpr int kTrmMaxK = 48;   // values per grid-wide reduction (init: 3 centres x 4 + 5 slots x 6 = 42)
+constexpr int kTrmV = 6;       // per-slot sums of the init stage and of a pass
+constexpr int kTrmLag = 3 * 4; // first value of the per-slot blocks in the init stage
+static_assert(kTrmMaxK <= kScBlock, "one exchange block carries a stage's scalars");
+static_assert(2 * kTrmMaxK * 1024 <= kMaxScalars * kMaxPartialBlocks, "partials fit the evaluation slot");
+
+// block-level reduction of NV per-thread values -> buf[(kbase + k) * G + blockIdx.x]
+template <int NV>
+__device__ __forceinline__ void trm_publish(const double (&v)[NV], unsigned max_mask, int kbase, double* buf,
+                                            double* sh /* kTrmV * kTrmWarps */) {
+  static_assert(NV <= kTrmV, "shared scratch");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = gridDim.x;
+  __syncthreads();  // sh may still be read by the previous publish
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double w = (max_mask >> k) & 1u ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) sh[k * kTrmWarps + warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    const int k = threadIdx.x;
+    const bool is_max = (max_mask >> k) & 1u;
+    double t = sh[k * kTrmWarps];
+    for (int w = 1; w < kTrmWarps; ++w) t = is_max ? fmax(t, sh[k * kTrmWarps + w]) : t + sh[k * kTrmWarps + w];
+    buf[static_cast<size_t>(kbase + k) * G + blockIdx.x] = t;
+  }
+}
+
+// grid-wide totals of the K published values -> tot[0..K) in every block (and, partitioned, the
+// rank-ordered totals over all ranks). Bit k of max_mask: value k is a maximum. Values nobody
+// published this stage hold stale numbers and are ignored by the caller.
+__device__ __forceinline__ void trm_totals(cg::grid_group& grid, const Bufs& B, int K, unsigned long long max_mask,
+                                           const double* buf, double* tot, TrXchg& xc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = gridDim.x;
+  grid.sync();
+  for (int k = warp; k < K; k += kTrmWarps) {
+    const bool is_max = (max_mask >> k) & 1ull;
+    double t = is_max ? -CUDART_INF : 0.0;
+    for (int j = lane; j < G; j += 32) {
+      const double q = __ldcg(buf + static_cast<size_t>(k) * G + j);
+      t = is_max ? fmax(t, q) : t + q;
+    }
+    t = is_max ? warp_max(t) : warp_sum(t);
+    if (lane == 0) tot[k] = t;
+  }
+  __syncthreads();
+  if (B.world > 1) {
+    const int xpar = static_cast<int>(xc.seq & 1ull);
+    const size_t base = static_cast<size_t>(xpar) * B.world * kScBlock;
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < K) {
+        const double mine = tot[threadIdx.x];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+          if (r < B.world) B.scx_peer[r][base + B.rank * kScBlock + threadIdx.x] = mine;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        p2p_signal(B, 3, xc.seq);
+        p2p_wait(B, 3, xc.seq);
+      }
+    }
+    grid.sync();
+    if (threadIdx.x < K) {
+      const int k = threadIdx.x;
+      const bool is_max = (max_mask >> k) & 1ull;
+      double t = is_max ? -CUDART_INF : 0.0;
+      for (int r = 0; r < B.world; ++r) {
+        double q;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(q) : "l"(B.scx + base + r * kScBlock + k) : "memory");
+        t = is_max ? fmax(t, q) : t + q;
+      }
+      tot[k] = t;
+    }
+    __syncthreads();
+    xc.seq += 1;
+    xc.count += 1;
+  }
+}
+
+__global__ void __launch_bounds__(kTrmThreads, 2) k_tr_multi(Bufs B, TrMulti M, TrState* trs, double* part) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[kTrmV * kTrmWarps];
+  __shared__ double tot[kTrmMaxK];
+  __shared__ TrState st[kTrSlots];
+  __shared__ double s_wp[kTrSlots], s_wd[kTrSlots], s_radius[kTrSlots];
+  __shared__ int s_centre[kTrSlots];  // index of the slot's centre among the distinct centres
+  __shared__ int s_any;
+  TrXchg xc{0ull, 0};
+  if (B.world > 1) xc.seq = __ldcg(B.dseq) + 1ull;  // read by every block before block 0 rewrites it at the end
+  const int NS = M.nslots;
+  const int G = gridDim.x;
+  const int stride = G * kTrmThreads;
+  const int tid = blockIdx.x * kTrmThreads + threadIdx.x;
+  const int n = B.n, total = B.n + B.m;
+  auto same_centre = [&](int a, int b) { return M.P[a].px == M.P[b].px && M.P[a].py == M.P[b].py; };
+  // weights / radii: from the host, or from the reduced statistics in HBM (TrParamSrc; the same
+  // arithmetic as evaluate() / run_restart_scheme() in folp_api.cu)
+  if (threadIdx.x < NS) {
+    const int s_ = threadIdx.x;
+    const TrProblem& P = M.P[s_];
+    double wp = P.wp, wd = P.wd, radius = P.radius;
+    if (P.param_src == kTrParamBounds) {
+      const double xs2 = B.red[SN_xs2], ys2 = B.red[kMaxScalars + SM_ys2];
+      double rp = sqrt(P.wp * xs2), rd = sqrt(P.wd * ys2);
+      rp = (rp != rp) ? rp : (1e-8 > rp ? 1e-8 : rp);  // Julia's max(1e-8, .) propagates NaN
+      rd = (rd != rd) ? rd : (1e-8 > rd ? 1e-8 : rd);
+      wp = P.wp / (rp * rp);
+      wd = P.wd / (rd * rd);
+      radius = 1.0;
+    } else if (P.param_src == kTrParamDistAvg || P.param_src == kTrParamDistCur) {
+      const double* dist = B.red + 2 * kMaxScalars;
+      const bool avg = P.param_src == kTrParamDistAvg;
+      const double px = sqrt(P.wp * dist[avg ? SD_avg_x : SD_cur_x]);
+      const double dy = sqrt(P.wd * dist[avg ? SD_avg_y : SD_cur_y]);
+      radius = sqrt(px * px + dy * dy);
+    }
+    s_wp[s_] = wp;
+    s_wd[s_] = wd;
+    s_radius[s_] = radius;
+    int ci = 0;  // number of distinct centres among the slots before the first slot with this centre
+    int first = s_;
+    for (int q = s_ - 1; q >= 0; --q)
+      if (same_centre(q, s_)) first = q;
+    for (int q = 0; q < first; ++q) {
+      bool lead = true;
+      for (int r = 0; r < q; ++r) lead = lead && !same_centre(r, q);
+      ci += lead ? 1 : 0;
+    }
+    s_centre[s_] = ci;
+  }
+  __syncthreads();
+  double* const buf0 = part;
+  double* const buf1 = part + static_cast<size_t>(kTrmMaxK) * G;
+  int parity = 0;
+  auto scratch_t = [&](int s_) { return B.trm_t + static_cast<size_t>(s_ <= 1 ? 0 : s_ - 1) * total; };
+  auto scratch_d = [&](int s_) { return B.trm_d + static_cast<size_t>(s_ <= 1 ? 0 : s_ - 1) * total; };
+  // the slots of the centre led by slot `lead`: over both ranges (gap), primal range only, dual range only
+  auto centre_slots = [&](int lead, int& sg, int& sp, int& sd) {
+    sg = sp = sd = -1;
+    for (int q = lead; q < NS; ++q) {
+      if (!same_centre(lead, q)) continue;
+      if (M.P[q].use_primal && M.P[q].use_dual) sg = q;
+      else if (M.P[q].use_primal) sp = q;
+      else if (M.P[q].use_dual) sd = q;
+    }
+  };
+  auto is_lead = [&](int q) {
+    bool lead = true;
+    for (int r = 0; r < q; ++r) lead = lead && !same_centre(r, q);
+    return lead;
+  };
+
+  // ================= init: one sweep per distinct centre =================
+  {
+    double* buf = parity ? buf1 : buf0;
+    for (int lead = 0; lead < NS; ++lead) {
+      if (!is_lead(lead)) continue;
+      const TrProblem& PL = M.P[lead];
+      int sg, sp, sd;
+      centre_slots(lead, sg, sp, sd);
+      double lag[4] = {0.0, 0.0, 0.0, 0.0};  // c.x, x.A'y, y.b, x.Qx of the centre
+      double vg[kTrmV] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      // one element of slot s_ (weight w): direction, threshold, sums.
+      // value layout: exact {g2, H0, Hinf, Ltot, cnt0, max_t}, approximate {g2, norm2, gdp, gdd, -, -}
+      auto element = [&](int s_, double (&v)[kTrmV], int idx, bool primal, double x0, double g, double lb,
+                         double ub, bool skip) {
+        const double w = primal ? s_wp[s_] : s_wd[s_];
+        v[0] += g * g;
+        const double d = skip ? 0.0 : -g / w;
+        scratch_d(s_)[idx] = d;
+        if (M.P[s_].approx) {  // tr.jl:194-224
+          v[1] += w * d * d;
+          if (primal) v[2] += g * d;
+          else v[3] += g * d;
+          return;
+        }
+        double t = 0.0;  // tr.jl:104-116
+        if (d > 0.0) t = (ub - x0) / d;
+        else if (d < 0.0) t = (lb - x0) / d;
+        scratch_t(s_)[idx] = t;
+        const double hh = w * d * d;
+        if (isinf(t)) {
+          v[2] += hh;
+          v[1] += hh;
+        } else {
+          if (t > 0.0) v[1] += hh;
+          else v[4] += 1.0;
+          v[3] += hh * t * t;
+          v[5] = fmax(v[5], t);
+        }
+      };
+      {  // ---- primal range ----
+        double vh[kTrmV] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int idx = tid; idx < n; idx += stride) {
+          const double x0 = PL.px[idx];
+          const double at = PL.atp[idx], cj = B.c[idx];
+          const double qx = PL.qxp ? PL.qxp[idx] : 0.0;
+          const double g = PL.qxp ? (qx + cj) - at : cj - at;  // sp.jl:1081-1091
+          const double lb = B.l[idx], ub = B.u[idx];
+          lag[0] += x0 * cj;  // compute_lagrangian_value, sp.jl:1109-1120
+          lag[1] += x0 * at;
+          if (PL.qxp) lag[3] += x0 * qx;
+          const bool skip = (x0 >= ub && g <= 0.0) || (x0 <= lb && g >= 0.0);  // tr.jl:96-103
+          if (sg >= 0) element(sg, vg, idx, true, x0, g, lb, ub, skip);
+          if (sp >= 0) element(sp, vh, idx, true, x0, g, lb, ub, skip);
+        }
+        if (sp >= 0) trm_publish<kTrmV>(vh, M.P[sp].approx ? 0u : (1u << 5), kTrmLag + kTrmV * sp, buf, sh);
+      }
+      {  // ---- dual range ----
+        double vh[kTrmV] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int idx = n + tid; idx < total; idx += stride) {
+          const int i = idx - n;
+          const double x0 = PL.py[i];
+          const double bi = B.b[i];
+          const double g = -(bi - PL.axp[i]);  // tr.jl:291, :312
+          const double lb = i < B.neq ? -CUDART_INF : 0.0, ub = CUDART_INF;  // tr.jl:288-290
+          lag[2] += x0 * bi;
+          const bool skip = (x0 >= ub && g <= 0.0) || (x0 <= lb && g >= 0.0);
+          if (sg >= 0) element(sg, vg, idx, false, x0, g, lb, ub, skip);
+          if (sd >= 0) element(sd, vh, idx, false, x0, g, lb, ub, skip);
+        }
+        if (sd >= 0) trm_publish<kTrmV>(vh, M.P[sd].approx ? 0u : (1u << 5), kTrmLag + kTrmV * sd, buf, sh);
+      }
+      if (sg >= 0) trm_publish<kTrmV>(vg, M.P[sg].approx ? 0u : (1u << 5), kTrmLag + kTrmV * sg, buf, sh);
+      trm_publish<4>(lag, 0u, 4 * s_centre[lead], buf, sh);
+    }
+    unsigned long long mask = 0ull;
+    for (int q = 0; q < NS; ++q)
+      if (!M.P[q].approx) mask |= 1ull << (kTrmLag + kTrmV * q + 5);
+    trm_totals(grid, B, kTrmLag + kTrmV * NS, mask, buf, tot, xc);
+    parity ^= 1;
+    if (threadIdx.x < NS) {
+      const int s_ = threadIdx.x;
+      const double* v = tot + kTrmLag + kTrmV * s_;
+      const double* lg = tot + 4 * s_centre[s_];
+      double r[TI_TOTAL];
+      for (int k = 0; k < TI_TOTAL; ++k) r[k] = 0.0;
+      r[TI_g2] = v[0];
+      if (M.P[s_].approx) {
+        r[TI_norm2] = v[1]; r[TI_gdp] = v[2]; r[TI_gdd] = v[3];
+      } else {
+        r[TI_H0] = v[1]; r[TI_Hinf] = v[2]; r[TI_Ltot] = v[3]; r[TI_cnt0] = v[4]; r[TI_max_t] = v[5];
+      }
+      r[TI_cx] = lg[0]; r[TI_xaty] = lg[1]; r[TI_yb] = lg[2]; r[TI_xqx] = lg[3];
+      TrProblem P = M.P[s_];
+      P.wp = s_wp[s_]; P.wd = s_wd[s_]; P.radius = s_radius[s_];
+      tr_setup(&st[s_], r, P);
+    }
+    __syncthreads();
+  }
+
+  // ================= passes: every unfinished slot, one barrier per round =================
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int any = 0;
+      for (int q = 0; q < NS; ++q) any |= st[q].done ? 0 : 1;
+      s_any = any;
+    }
+    __syncthreads();
+    if (!s_any) break;
+    double* buf = parity ? buf1 : buf0;
+    for (int q = 0; q < NS; ++q) {
+      if (st[q].done) continue;
+      const double c0 = st[q].cand[0], c1 = st[q].cand[1];
+      const double wp = s_wp[q], wd = s_wd[q];
+      const double* pt = scratch_t(q);
+      const double* pd = scratch_d(q);
+      double v[kTrmV] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // L0,H0,cnt0,L1,H1,cnt1
+      const int begin = M.P[q].use_primal ? 0 : n;
+      const int end = M.P[q].use_dual ? total : n;
+#pragma unroll 2
+      for (int idx = begin + tid; idx < end; idx += stride) {
+        const double t = pt[idx], d = pd[idx];
+        const double hh = (idx < n ? wp : wd) * d * d;
+        const double lt = hh * t * t;
+        if (t <= c0) { v[0] += lt; v[2] += 1.0; } else { v[1] += hh; }
+        if (t <= c1) { v[3] += lt; v[5] += 1.0; } else { v[4] += hh; }
+      }
+      trm_publish<kTrmV>(v, 0u, kTrmV * q, buf, sh);
+    }
+    trm_totals(grid, B, kTrmV * NS, 0ull, buf, tot, xc);
+    parity ^= 1;
+    if (threadIdx.x < NS && !st[threadIdx.x].done) {
+      TrState* t_ = &st[threadIdx.x];
+      tr_update(t_, tot + kTrmV * threadIdx.x);
+      // non-finite data (a diverged iterate) can keep the partition changing for ever; a lost peer ends the search too
+      if (!t_->done && (t_->passes >= 120 || (B.world > 1 && __ldcg(B.counters + 6)))) {
+        t_->done = 2;
+        t_->zero_value = 1;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ================= final values: one sweep per distinct centre =================
+  {
+    if (threadIdx.x == 0) {
+      int any = 0;
+      for (int q = 0; q < NS; ++q) any |= st[q].zero_value ? 0 : 1;
+      s_any = any;
+    }
+    __syncthreads();
+    if (s_any) {
+      double* buf = parity ? buf1 : buf0;
+      for (int lead = 0; lead < NS; ++lead) {
+        if (!is_lead(lead)) continue;
+        const TrProblem& PL = M.P[lead];
+        int sg, sp, sd;
+        centre_slots(lead, sg, sp, sd);
+        if (sg >= 0 && st[sg].zero_value) sg = -1;
+        if (sp >= 0 && st[sp].zero_value) sp = -1;
+        if (sd >= 0 && st[sd].zero_value) sd = -1;
+        if (sg < 0 && sp < 0 && sd < 0) continue;
+        const double tau_g = sg >= 0 ? st[sg].tau : 0.0, tau_p = sp >= 0 ? st[sp].tau : 0.0,
+                     tau_d = sd >= 0 ? st[sd].tau : 0.0;
+        double vgap[2] = {0.0, 0.0}, vhp[1] = {0.0}, vhd[1] = {0.0};
+        if (sg >= 0 || sp >= 0) {
+          for (int idx = tid; idx < n; idx += stride) {
+            const double x0 = PL.px[idx];
+            const double at = PL.atp[idx], cj = B.c[idx];
+            const double g = PL.qxp ? (PL.qxp[idx] + cj) - at : cj - at;
+            const double lb = B.l[idx], ub = B.u[idx];
+            if (sg >= 0) {
+              const double sol = jl_clamp(x0 + tau_g * scratch_d(sg)[idx], lb, ub);  // tr.jl:182-188
+              vgap[0] += g * (sol - x0);
+            }
+            if (sp >= 0) {
+              const double sol = jl_clamp(x0 + tau_p * scratch_d(sp)[idx], lb, ub);
+              vhp[0] += g * (sol - x0);
+            }
+          }
+        }
+        if (sg >= 0 || sd >= 0) {
+          for (int idx = n + tid; idx < total; idx += stride) {
+            const int i = idx - n;
+            const double x0 = PL.py[i];
+            const double g = -(B.b[i] - PL.axp[i]);
+            const double lb = i < B.neq ? -CUDART_INF : 0.0, ub = CUDART_INF;
+            if (sg >= 0) {
+              const double sol = jl_clamp(x0 + tau_g * scratch_d(sg)[idx], lb, ub);
+              vgap[1] += g * (sol - x0);
+            }
+            if (sd >= 0) {
+              const double sol = jl_clamp(x0 + tau_d * scratch_d(sd)[idx], lb, ub);
+              vhd[0] += g * (sol - x0);
+            }
+          }
+        }
+        if (sg >= 0) trm_publish<2>(vgap, 0u, 2 * sg, buf, sh);
+        if (sp >= 0) trm_publish<1>(vhp, 0u, 2 * sp, buf, sh);
+        if (sd >= 0) trm_publish<1>(vhd, 0u, 2 * sd + 1, buf, sh);
+      }
+      trm_totals(grid, B, 2 * NS, 0ull, buf, tot, xc);
+      if (threadIdx.x < NS && !st[threadIdx.x].zero_value) {
+        const int s_ = threadIdx.x;
+        st[s_].v_primal = M.P[s_].use_primal ? tot[2 * s_] : 0.0;
+        st[s_].v_dual = M.P[s_].use_dual ? tot[2 * s_ + 1] : 0.0;
+      }
+      __syncthreads();
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < NS) {
+      st[threadIdx.x].exchanges = xc.count;
+      trs[threadIdx.x] = st[threadIdx.x];
+    }
+    if (threadIdx.x == 0 && B.world > 1) *B.dseq = xc.seq - 1ull;
+  }
+}
+
+int tr_multi_grid(int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tr_multi, kTrmThreads, 0) != cudaSuccess ||
+      per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  int g = sm_count * (per_sm < 2 ? per_sm : 2);
+  if (g > 1024) g = 1024;
+  return g;
+}
+
+int launch_tr_multi(const Bufs& B, const TrMulti& M, TrState* d_trs, int grid, cudaStream_t s) {
+  double* part = B.part + static_cast<size_t>(kSlotEval) * kMaxScalars * kMaxPartialBlocks;
+  void* args[] = {const_cast<Bufs*>(&B), const_cast<TrMulti*>(&M), &d_trs, &part};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tr_multi), dim3(grid), dim3(kTrmThreads), args,
+                                     0, s);
+}
+
 int tr_solve_grid(int sm_count) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tr_solve, kTrThreads, 0) != cudaSuccess ||

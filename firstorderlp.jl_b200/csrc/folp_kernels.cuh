@@ -23,6 +23,7 @@ struct Bufs {
   double *D = nullptr, *E = nullptr;         // variable_rescaling, constraint_rescaling
   double *c_orig = nullptr, *l_orig = nullptr, *u_orig = nullptr, *b_orig = nullptr;
   double *tr_t = nullptr, *tr_d = nullptr;   // trust-region scratch, n+m each
+  double *trm_t = nullptr, *trm_d = nullptr; // k_tr_multi scratch, 4 * (n+m) each (nullptr: not allocated)
   // ---- quadratic objective (has_q: the scaled objective matrix has a nonzero entry) ----
   // qx[k] = Q * x[k] travels with the iterate buffers (same parity), dxv holds x+ - x of the
   // running attempt, qx_avg / last_qx are Q times the evaluated / the last restart point.
@@ -130,7 +131,15 @@ struct TrProblem {
   int param_src = kTrParamHost;
   int reserved0 = 0;
 };
-constexpr int kTrSlots = 5;  // results of one evaluation block: bound estimates (primal, dual), gaps at avg / current / last restart
+constexpr int kTrSlots = 5;
+// all trust-region problems of one evaluation block for k_tr_multi (slot k's result goes to d_trs[k])
+struct TrMulti {
+  TrProblem P[kTrSlots];
+  int nslots;
+  int reserved0;
+};
+int tr_multi_grid(int sm_count);  // co-resident blocks of k_tr_multi (0: unavailable)
+int launch_tr_multi(const Bufs& B, const TrMulti& M, TrState* d_trs, int grid, cudaStream_t s);  // cudaError_t  // results of one evaluation block: bound estimates (primal, dual), gaps at avg / current / last restart
 
 // Q: CSR of the objective matrix, used only when B.has_q
 void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q,

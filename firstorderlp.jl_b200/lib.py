@@ -22,7 +22,7 @@ _pd = C.POINTER(C.c_double)
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
-    "folp_nccl_unique_id", "folp_partition", "folp_rescale_problem", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
+    "folp_nccl_unique_id", "folp_create_multi", "folp_partition", "folp_rescale_problem", "folp_shard_info", "folp_exchange_mode", "folp_create", "folp_run", "folp_solve", "folp_get_solution",
     "folp_debug_attempts", "folp_debug_state", "folp_debug_set_state", "folp_debug_spmv",
     "folp_debug_profile_attempts", "folp_debug_time_spmv", "folp_debug_host_spmv", "folp_debug_host_prepare", "folp_debug_host_problem_spmv", "folp_debug_stream", "folp_counters", "folp_destroy", "folp_last_error", "folp_build_info",
 ]
@@ -64,6 +64,8 @@ def lib() -> C.CDLL:
         L.folp_exchange_mode.argtypes = [C.c_void_p]
         L.folp_create.argtypes = [C.POINTER(FolpProblem), C.POINTER(FolpParams), C.POINTER(FolpDist),
                                   C.POINTER(C.c_void_p)]
+        L.folp_create_multi.argtypes = [C.POINTER(FolpProblem), C.POINTER(FolpParams), C.c_int32,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
         L.folp_run.argtypes = [C.c_void_p, C.POINTER(FolpEval)]
         L.folp_solve.argtypes = [C.c_void_p, C.POINTER(FolpEval), C.c_int64, C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), _pd, _pd]
@@ -221,13 +223,28 @@ def make_dist(rank: int, world_size: int, device: int, unique_id: Optional[bytes
 class Solver:
     """One folp_handle: the device-resident PDHG state of one optimize() call."""
 
-    def __init__(self, problem_holder, params: FolpParams, dist: Optional[FolpDist] = None):
+    def __init__(self, problem_holder, params: FolpParams, dist: Optional[FolpDist] = None,
+                 devices: Optional[list] = None):
+        """dist: one rank of a one-process-per-GPU solve (folp_dist; default under torchrun after
+        distributed.init()). devices: single-process multi-GPU (folp_create_multi) on these CUDA
+        devices; the environment variable FOLP_DEVICES="0,1,..." selects it for every Solver."""
         self._holder = problem_holder
         self.params = params
         self.n = problem_holder.struct.num_variables
         self.m = problem_holder.struct.num_constraints
         self._h = C.c_void_p()
         L = lib()
+        if devices is None and dist is None and os.environ.get("FOLP_DEVICES"):
+            devices = [int(d) for d in os.environ["FOLP_DEVICES"].split(",") if d.strip() != ""]
+        self.devices = devices
+        if devices is not None:
+            self.dist = None
+            ids = (C.c_int32 * len(devices))(*devices)
+            rc = L.folp_create_multi(problem_holder.byref(), C.byref(params), len(devices), ids,
+                                     C.byref(self._h))
+            if rc != 0:
+                raise FolpError(rc, L.folp_last_error(None).decode())
+            return
         if dist is None:  # under torchrun after distributed.init(): join all ranks
             from . import distributed
             dist = distributed.new_dist()

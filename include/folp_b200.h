@@ -276,6 +276,20 @@ int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end, int64_
 int folp_create(const folp_problem* problem, const folp_params* params,
                 const folp_dist* dist, folp_handle** out);
 
+/* Single-process multi-GPU entry: ONE call from ONE host
+ * thread -- what FirstOrderLp.optimize (pdhg.jl:782-785) is -- drives n_gpus
+ * devices of this process (device_ids[0..n_gpus), NULL = devices 0..n_gpus-1;
+ * n_gpus <= 8). The problem is partitioned exactly as with one process per GPU
+ * (folp_partition); each device is driven by a host thread of the library, the
+ * devices reach each other's exchange regions through direct peer access
+ * (cudaDeviceEnablePeerAccess: no CUDA IPC, no NCCL, no communicator to set up),
+ * and the returned handle is used with folp_run / folp_solve / folp_get_solution /
+ * folp_destroy like any other: records and solutions are the global ones.
+ * FOLP_UNSUPPORTED if some pair of the devices lacks peer access. n_gpus == 1 is
+ * folp_create on device_ids[0]. */
+int folp_create_multi(const folp_problem* problem, const folp_params* params,
+                      int32_t n_gpus, const int32_t* device_ids, folp_handle** out);
+
 /* Replaces one trip round the while-loop of pdhg.jl:886-1048 up to and
  * including the next evaluation block (:892-1023): runs take_step until the
  * trigger of :892-895 fires, evaluates the KKT statistics of the average

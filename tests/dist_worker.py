@@ -1,10 +1,12 @@
 """Row-partitioned (multi-GPU) parity worker. Launch:
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-      --master-port P tests/dist_worker.py
+      --master-port P tests/dist_worker.py          # one process per GPU (folp_dist)
+  python tests/dist_worker.py --single-process N     # one process driving N GPUs (folp_create_multi)
 
 Every rank runs the same GPU-vs-oracle checks as tests/test_gpu_parity.py, with the GPU
-solver spread over all ranks (folp_b200.distributed makes every Solver join the ranks)."""
+solver spread over all ranks (folp_b200.distributed makes every Solver join the ranks; in the
+single-process form FOLP_DEVICES makes every Solver a folp_create_multi handle)."""
 import os
 import sys
 import traceback
@@ -16,30 +18,13 @@ sys.path.insert(0, HERE)
 import numpy as np  # noqa: E402
 
 
-def main():
-    import torch
+def parity_checks(check, world, rank):
+    """The partitioned-mode check list (shared by both launch forms)."""
     import folp_b200
-    from folp_b200 import RestartScheme, distributed
-    from folp_b200.lib import Solver
+    from folp_b200 import RestartScheme
     from folp_b200.synthetic import random_sparse_lp
-
-    st = distributed.init("nccl")
-    assert st is not None, "launch with torchrun, world_size >= 2"
-    rank, world = st["rank"], st["world_size"]
     import test_gpu_parity as T
     from shared_problems import generate_pdhg_params
-
-    failures = []
-
-    def check(name, fn):
-        try:
-            fn()
-            if rank == 0:
-                print(f"[dist x{world}] {name}: ok", flush=True)
-        except Exception:  # every rank keeps the same call sequence as long as all fail alike
-            failures.append(name)
-            print(f"[dist x{world}] rank {rank} {name}: FAILED\n{traceback.format_exc()}", flush=True)
-            raise
 
     # the shard layout is the exported partition
     problem = random_sparse_lp(3000, 2500, 8, seed=5)
@@ -49,6 +34,7 @@ def main():
     rb, cb = folp_b200.lib.partition(problem.constraint_matrix, world)
     assert (info["row_begin"], info["row_end"]) == (rb[rank], rb[rank + 1]), (info, rb)
     assert (info["col_begin"], info["col_end"]) == (cb[rank], cb[rank + 1]), (info, cb)
+    assert info["exchange"] == "peer", info
     o.close(); g.close()
 
     for i, make in enumerate([lambda: random_sparse_lp(3000, 2500, 8, seed=5), T.netlib_shaped_lp,
@@ -68,6 +54,54 @@ def main():
     check("short_horizon", T.test_full_solve_trajectory_short_horizon)
     check("deterministic", T.test_deterministic_run_to_run)
     check("example_lp", T.test_example_lp_exact_record)  # 3 rows on N ranks: empty shards
+
+
+def main_single_process(world):
+    """One process, `world` GPUs: every Solver is a folp_create_multi handle."""
+    os.environ["FOLP_DEVICES"] = ",".join(str(d) for d in range(world))
+
+    def check(name, fn):
+        try:
+            fn()
+            print(f"[multi x{world}] {name}: ok", flush=True)
+        except Exception:
+            print(f"[multi x{world}] {name}: FAILED\n{traceback.format_exc()}", flush=True)
+            raise
+
+    parity_checks(check, world, 0)
+    import folp_b200
+    from folp_b200.synthetic import random_sparse_lp
+    problem = random_sparse_lp(2500, 2000, 7, seed=71)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.iteration_limit = 120
+    out = folp_b200.optimize(params, problem)
+    assert out.iteration_count == 120
+    print(f"[multi x{world}] ALL OK", flush=True)
+
+
+def main():
+    import torch
+    import folp_b200
+    from folp_b200 import distributed
+    from folp_b200.synthetic import random_sparse_lp
+
+    st = distributed.init("nccl")
+    assert st is not None, "launch with torchrun, world_size >= 2"
+    rank, world = st["rank"], st["world_size"]
+
+    failures = []
+
+    def check(name, fn):
+        try:
+            fn()
+            if rank == 0:
+                print(f"[dist x{world}] {name}: ok", flush=True)
+        except Exception:  # every rank keeps the same call sequence as long as all fail alike
+            failures.append(name)
+            print(f"[dist x{world}] rank {rank} {name}: FAILED\n{traceback.format_exc()}", flush=True)
+            raise
+
+    parity_checks(check, world, rank)
 
     # every rank holds the same global records and solution
     import torch.distributed as td
@@ -89,4 +123,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--single-process":
+        main_single_process(int(sys.argv[2]))
+    else:
+        main()

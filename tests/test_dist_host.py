@@ -2,10 +2,12 @@
 
 * folp_partition (the pure-host arithmetic folp_create applies) covers rows and columns,
   balances nonzeros and is what a NumPy restatement gives;
-* a world_size-2 `gloo` emulation of one take_step in the library's exchange pattern --
-  primal step on a column slice | allgather xbar | dual step on a row block | partial
-  A_r' y_r | reduce-scatter | interaction on the slice | rank-ordered scalar exchange --
-  reproduces the single-process oracle, and both ranks take bit-identical decisions.
+* a world_size-2 `gloo` emulation of take_step in the library's exchange pattern (DESIGN.md
+  section 6) -- primal step on the rank's column slice | allgather xbar | dual step on the rank's
+  row block A[rows, :] | allgather y+ (padded, rank-major) | A[:, slice]' y+ and the interaction on
+  the slice (full-length rows: no partial sums cross ranks) | rank-ordered exchange of the four
+  step-rule scalars -- reproduces the single-process oracle, and both ranks take bit-identical
+  decisions.
 """
 import os
 import sys
@@ -81,8 +83,14 @@ def _worker(rank, world, port, out_q):
         rb, cb = partition(P.constraint_matrix, world)
         r0, r1, c0, c1 = rb[rank], rb[rank + 1], cb[rank], cb[rank + 1]
         n_pad = int(cb[1] - cb[0]) if world > 1 else n
-        A_r = A[r0:r1, :]
-        At_r = sp.csr_matrix(A_r.T)
+        m_pad = int(max(rb[q + 1] - rb[q] for q in range(world)))
+        A_r = A[r0:r1, :]                                  # row block: A * xbar and the dual step
+        At_s = sp.csr_matrix(sp.csc_matrix(A)[:, c0:c1].T)  # column slice: rows of full length m
+        # its column indices address the padded rank-major layout of the gathered y+
+        owner_off = np.zeros(m, dtype=np.int64)
+        for q in range(world):
+            owner_off[rb[q]:rb[q + 1]] = q * m_pad + np.arange(rb[q + 1] - rb[q])
+        At_s = sp.csr_matrix((At_s.data, owner_off[At_s.indices], At_s.indptr), shape=(c1 - c0, world * m_pad))
         c, l, u, b = (np.asarray(v, dtype=np.float64) for v in (
             P.objective_vector, P.variable_lower_bound, P.variable_upper_bound, P.right_hand_side))
         rng = np.random.default_rng(1)
@@ -93,12 +101,16 @@ def _worker(rank, world, port, out_q):
         o = oracle.OracleSolver(holder, fparams)
         o.debug_set_state(x0, y0, step_size=step, primal_weight=pw)
 
+        def gather(local, pad):
+            send = torch.zeros(pad, dtype=torch.float64)
+            send[: len(local)] = torch.from_numpy(np.ascontiguousarray(local))
+            recv = [torch.zeros(pad, dtype=torch.float64) for _ in range(world)]
+            td.all_gather(recv, send)
+            return torch.cat(recv).numpy()
+
         # local state: primal slice + row block
         x, y = x0[c0:c1].copy(), y0[r0:r1].copy()
-        part = torch.zeros(world * n_pad, dtype=torch.float64)
-        part[:n] = torch.from_numpy(At_r @ y)
-        td.all_reduce(part)  # reduce-scatter = all-reduce + slice on gloo
-        aty = part[c0:c1].numpy().copy()
+        aty = At_s @ gather(y, m_pad)
         total_iterations = 0
         decisions = []
         for _ in range(4):
@@ -106,27 +118,21 @@ def _worker(rank, world, port, out_q):
             xn = np.minimum(u[c0:c1], np.maximum(l[c0:c1], x - (step / pw) * (c[c0:c1] - aty)))
             xbar_loc = xn + 1.0 * (xn - x)
             dx2 = float(np.sum((xn - x) ** 2))
-            # allgather xbar (equal padded slices)
-            send = torch.zeros(n_pad, dtype=torch.float64)
-            send[: c1 - c0] = torch.from_numpy(xbar_loc)
-            recv = [torch.zeros(n_pad, dtype=torch.float64) for _ in range(world)]
-            td.all_gather(recv, send)
-            xbar = torch.cat(recv).numpy()[:n]
+            xbar = gather(xbar_loc, n_pad)[:n]           # exchange 1: allgather xbar
             # K2 on the row block
             yn = y + (pw * step) * (b[r0:r1] - A_r @ xbar)
             ineq = np.arange(r0, r1) >= neq
             yn[ineq] = np.maximum(yn[ineq], 0.0)
             dy2 = float(np.sum((yn - y) ** 2))
-            # K3 partial product + reduce-scatter
-            part = torch.zeros(world * n_pad, dtype=torch.float64)
-            part[:n] = torch.from_numpy(At_r @ yn)
-            td.all_reduce(part)
-            atn = part[c0:c1].numpy().copy()
+            y_full = gather(yn, m_pad)                   # exchange 2: allgather y+
+            # K3 on the slice: full-length rows, no reduction across ranks
+            atn = At_s @ y_full
             inter = float(np.sum((xn - x) * (atn - aty)))
-            # rank-ordered scalar exchange
-            sc = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
-            td.all_gather(sc, torch.tensor([dx2, dy2, inter], dtype=torch.float64))
-            tot = np.zeros(3)
+            dp2 = float(np.sum((atn - aty) ** 2))
+            # exchange 3: the four scalars, summed in rank order on every rank
+            sc = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
+            td.all_gather(sc, torch.tensor([dx2, dy2, inter, dp2], dtype=torch.float64))
+            tot = np.zeros(4)
             for t in sc:
                 tot += t.numpy()
             # the scalar rule (pdhg.jl:689-728), identical on every rank
@@ -144,14 +150,10 @@ def _worker(rank, world, port, out_q):
             # the oracle, one attempt
             o.debug_attempts(1)
             so = o.debug_state()
-            xs = [torch.zeros(n_pad, dtype=torch.float64) for _ in range(world)]
-            sx = torch.zeros(n_pad, dtype=torch.float64)
-            sx[: c1 - c0] = torch.from_numpy(x)
-            td.all_gather(xs, sx)
-            x_full = torch.cat(xs).numpy()[:n]
+            x_full = gather(x, n_pad)[:n]
             assert np.max(np.abs(x_full - so["x"])) <= 1e-13 * max(1.0, np.max(np.abs(so["x"])))
             assert np.max(np.abs(y - so["y"][r0:r1])) <= 1e-13 * max(1.0, np.max(np.abs(so["y"])))
-            assert np.max(np.abs(aty - so["dual_product"][c0:c1])) <= 1e-12 * max(1.0, np.max(np.abs(so["dual_product"])))
+            assert np.max(np.abs(aty - so["dual_product"][c0:c1])) <= 1e-13 * max(1.0, np.max(np.abs(so["dual_product"])))
             assert abs(step - so["step_size"]) <= 1e-12 * so["step_size"]
             assert so["total_number_iterations"] == total_iterations
         o.close()
@@ -169,7 +171,7 @@ def _worker(rank, world, port, out_q):
         td.destroy_process_group()
 
 
-def test_row_partitioned_attempt_gloo_world2():
+def test_partitioned_attempt_gloo_world2():
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")

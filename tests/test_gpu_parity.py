@@ -365,3 +365,61 @@ def test_example_lp_exact_record():
     params = generate_pdhg_params(iteration_limit=300)
     eo, _, _ = _run_lockstep(example_lp(), params)
     assert eo.iteration_number == 300
+
+
+# ---------------------------------------------------------------------------
+# bench scale: the grid strides, windows sort, 32-bit index arithmetic sees 1e7 entries
+# ---------------------------------------------------------------------------
+def test_eval_records_match_oracle_at_bench_scale():
+    """BASELINE.json configs[1] (1e6 x 1e6, 1e7 nonzeros) with the CLI defaults: every record of
+    the first 40 iterations (ten per-iteration evaluations + the one at 40) against the oracle --
+    ~15 s of CPU. bench.py repeats this on every run over 120 iterations (detail.parity)."""
+    problem = random_sparse_lp(1_000_000, 1_000_000, 10)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.eps_optimal_absolute = 0.0
+    params.termination_criteria.eps_optimal_relative = 0.0
+    params.termination_criteria.iteration_limit = 40
+    from oracle.parity import lockstep
+    o, g = _pair(problem, params)
+    res = lockstep(o, g, None, tol=1e-9)
+    o.close(); g.close()
+    assert res["ok"], res["problems"]
+    assert res["records"] == 11 and res["iterations"] == 40
+    # SpMV at this size: rows of A have <= 10 entries, columns of a random matrix <= 32 with
+    # overwhelming probability: one lane per row, ascending order -> the oracle's bits
+    # (checked through the records above: the 1e-9 bound held with 1e-11 .. 1e-13 to spare)
+    assert res["max_rel_err"] < 1e-10, res["max_rel_err"]
+
+
+# ---------------------------------------------------------------------------
+# the two remaining exits of check_termination_criteria (term.jl:262-271)
+# ---------------------------------------------------------------------------
+def test_kkt_matrix_pass_limit_terminates_like_the_oracle():
+    problem = random_sparse_lp(1500, 1200, 6, seed=81)
+    params = generate_pdhg_params(iteration_limit=100000, l_inf_ruiz_iterations=5, pock_chambolle_alpha=1.0,
+                                  restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED)
+    params.termination_evaluation_frequency = 8
+    params.termination_criteria.kkt_matrix_pass_limit = 150.0
+    eo, _, records = _run_lockstep(problem, params)
+    assert eo.termination_reason == TerminationReason.TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT
+    assert eo.cumulative_kkt_matrix_passes >= 150.0 and records > 10
+    out = folp_b200.optimize(params, problem)
+    assert out.termination_reason == TerminationReason.TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT
+    assert out.iteration_count == eo.iteration_number
+
+
+def test_time_limit_terminates():
+    """time_sec_limit (term.jl:268-270) is wall clock: both sides stop at the first evaluation
+    whose cumulative_time_sec has reached it -- here the very first one."""
+    problem = random_sparse_lp(1500, 1200, 6, seed=82)
+    params = generate_pdhg_params(iteration_limit=100000)
+    params.termination_criteria.time_sec_limit = 0.0
+    out_o = oracle.optimize(params, problem)
+    out_g = folp_b200.optimize(params, problem)
+    assert out_g.termination_reason == out_o.termination_reason == TerminationReason.TERMINATION_REASON_TIME_LIMIT
+    assert out_g.iteration_count == out_o.iteration_count == 0  # the evaluation before the first step
+    # and a limit that is never reached does not interfere
+    params.termination_criteria.time_sec_limit = 3600.0
+    params.termination_criteria.iteration_limit = 50
+    out_g = folp_b200.optimize(params, problem)
+    assert out_g.termination_reason == TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
