@@ -45,10 +45,35 @@ WORKLOADS = {
 WORKLOAD_LABEL = {"netlib": "synthetic Netlib-shaped block-angular LP", "pagerank": "PageRank LP (Barabasi-Albert graph)",
                   "netlib_small": "synthetic Netlib-shaped block-angular LP, median Netlib size"}
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the two k_spmv launches of an
-# iteration, from the committed `ncu --set full` capture (profiles/r01b_ncu_full_c2_summary.csv:
-# K2 157.0 + 7.6 MB, K3 157.1 + 4.9 MB; algorithmic 172.0 + 164.0 MB)
-TRAFFIC_NCU = {"c2": 164.6e6 + 162.0e6}
+KERNEL_SOURCES = ("firstorderlp.jl_b200/csrc/folp_spmv.cuh", "firstorderlp.jl_b200/csrc/folp_kernels.cu",
+                  "firstorderlp.jl_b200/csrc/folp_internal.cuh")
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of the two k_spmv
+    launches of an iteration, from the committed `ncu --set full` capture. The capture is stamped
+    with the hash of the kernel sources it was taken from (profiles/traffic_ncu.json, written by
+    tools/traffic_stamp.py): a stale stamp reports null rather than an old number."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic_ncu.json")))
+    except Exception:
+        return None, "no profiles/traffic_ncu.json"
+    e = d.get(workload)
+    if not e:
+        return None, "no ncu capture of this workload"
+    if e.get("kernel_source_sha16") != kernel_source_hash():
+        return None, "the kernel sources changed since the ncu capture %s" % e.get("from")
+    return e["traffic_bytes"], "ncu --set full, %s" % e.get("from")
+
 
 
 def log(*a):
@@ -270,7 +295,16 @@ def bench_gpu(args):
         roofline = {
             "bound": "hbm", "kernel": "k_spmv (A*xbar + dual step, A'*y + interaction; two launches per iteration)",
             "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": TRAFFIC_NCU.get(args.workload),
+            "traffic": ncu_traffic(args.workload)[0], "traffic_source": ncu_traffic(args.workload)[1],
+            "per_kernel_timing": "CUDA events around each kernel of %d real attempts launched one by one (each event "
+                                 "record costs ~4 us of gap, so the three add up to more than an iteration of the "
+                                 "captured CUDA graph: see in_loop)" % prof_attempts,
+            "in_loop": {"iteration_us": 1e6 * basic_s / iters if iters else None,
+                        "kernels_us_eager_sum": sum(per[:3]) * 1e3,
+                        "iteration_gbs": (b1 + b2 + b3) * iters / basic_s / 1e9 if basic_s > 0 else None,
+                        "iteration_frac": (b1 + b2 + b3) * iters / basic_s / 1e9 / peak if basic_s > 0 else None,
+                        "what": "take_step alone inside the timed region (CUDA graph of 3 kernels per attempt, "
+                                "events around whole batches): algorithmic bytes of an iteration / its time"},
             "per_kernel": {
                 "k_primal": {"ms": per[0], "bytes": b1, "gbs": b1 / per[0] / 1e6},
                 "k_spmv<EpiDual>": {"ms": per[1], "bytes": b2, "gbs": b2 / per[1] / 1e6},
@@ -281,16 +315,34 @@ def bench_gpu(args):
                     "workload before HBM does: see DESIGN.md section 5 and tools/gather_bench.cu",
         }
     else:
-        # the per-rank kernels are the same; at N > 1 the whole-iteration figure is what can be stated
+        # per-phase device time of k_take_steps on rank 0 (its own phase timers: each phase ends with the grid
+        # barrier and the peer exchange that follows it), continuing the same solve
+        prof_attempts = 100
+        solver.profile_attempts(10)
+        kms, ran = solver.profile_attempts(prof_attempts)
+        per = [k / prof_attempts for k in kms]
         roofline = {
-            "bound": "hbm", "kernel": "whole iteration over all ranks (k_primal, k_spmv x2, k_finalize_dist; xbar and "
-                                      "y+ pushed to every rank from the producing kernels over peer memory, or "
-                                      "NCCL allgathers; four scalars per attempt)",
+            "per_kernel": {
+                "primal step on the slice + xbar exchange": {"ms": per[0]},
+                "A[rows,:]*xbar + dual step + y+ exchange": {"ms": per[1]},
+                "A[:,slice]'*y+ + interaction + scalar exchange + step rule": {"ms": per[2]},
+                "step rule kernel (kernel-per-phase form only)": {"ms": per[3]},
+                "what": "rank 0, %d attempts; phases of the persistent kernel k_take_steps (phase timers) or, with "
+                        "FOLP_PERSISTENT=0, CUDA events around the kernels" % prof_attempts},
+            "bound": "hbm", "kernel": "whole iteration over all ranks (k_take_steps: primal / A*xbar / A'*y phases of one "
+                                      "persistent cooperative kernel per rank; xbar and y+ pushed to every rank from the "
+                                      "producing phase over peer memory, flags and four scalars on the grid barriers)",
             "achieved": iteration["gbs_at_value"], "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": iteration["frac_at_value"], "traffic": None, "iteration": iteration,
             "nvlink_bytes_per_iteration_per_gpu": 8 * (n + m) * (world - 1) // world,
+            "nvlink_gbs_in_per_gpu_at_value": 8 * (n + m) * (world - 1) / world * value / 1e9,
         }
     solver.close()
+
+    # ---- the north-star target size (1e7 x 1e7, 1e8 nonzeros) on the same N GPUs: GPU arm only ----
+    target = None
+    if not args.skip_target and args.workload == "c2":
+        target = target_subrun(world, peak)
 
     # ---- e2e: the C-ABI call sequence with host buffers ----
     e2e = None
@@ -351,7 +403,7 @@ def bench_gpu(args):
                    "final_l2_primal_residual": e.l2_primal_residual,
                    "final_l2_dual_residual": e.l2_dual_residual,
                    "folp_create_seconds": t_create, "rescale_problem": rescale, "build": build_info(),
-                   "exchange": exchange, "parity": parity},
+                   "exchange": exchange, "parity": parity, "target": target},
     }
     if rank == 0:
         emit(line)
@@ -362,6 +414,54 @@ def bench_gpu(args):
     if rank == 0 and parity is not None and not parity["ok"]:
         log("[bench] PARITY FAILED against the CPU oracle:", parity["problems"])
         sys.exit(3)
+
+
+def target_subrun(world, peak):
+    """BASELINE.json's north-star target (synthetic random sparse LP, 1e7 variables, 1e7 constraints,
+    1e8 nonzeros) on the same GPUs as the headline line: one warm-up step and two timed steps of 400
+    iterations, same parameters, same timing rule (CUDA events on the library's stream, max over
+    ranks). Rescaling runs on the device (folp_rescale_problem; bit-identical to the host mirror)."""
+    import torch
+    import folp_b200
+    from folp_b200.lib import Solver
+    from folp_b200.synthetic import random_sparse_lp
+
+    t0 = time.time()
+    lp = random_sparse_lp(10_000_000, 10_000_000, 10)
+    params = folp_b200.PdhgParameters(verbosity=0)
+    params.termination_criteria.eps_optimal_absolute = 0.0
+    params.termination_criteria.eps_optimal_relative = 0.0
+    params.termination_criteria.eps_primal_infeasible = 0.0
+    params.termination_criteria.eps_dual_infeasible = 0.0
+    holder, fparams, _ = folp_b200.host_setup(params, lp, device_rescaling=True)
+    fparams.iteration_limit = 10_000_000
+    n, m, nnz = lp.num_variables, lp.num_constraints, lp.constraint_matrix.nnz
+    t_host = time.time() - t0
+    t0 = time.time()
+    solver = Solver(holder, fparams)
+    t_create = time.time() - t0
+    stream = torch.cuda.ExternalStream(solver.stream())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run_until(solver, ITERS_PER_STEP)
+    c0 = solver.counters()
+    _barrier(world)
+    ev0.record(stream)
+    run_until(solver, 3 * ITERS_PER_STEP)
+    ev1.record(stream)
+    _barrier(world)
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world)
+    c1 = solver.counters()
+    solver.close()
+    iters = c1["iterations"] - c0["iterations"]
+    basic_s = c1["basic_algorithm_seconds"] - c0["basic_algorithm_seconds"]
+    value = iters / (ms * 1e-3)
+    b = sum(algorithmic_bytes(n, m, nnz))
+    log(f"[bench] target sub-run: {value:.1f} it/s on {world} GPU(s), host {t_host:.1f}s, create {t_create:.2f}s")
+    return {"workload": f"synthetic random sparse LP n={n} m={m} nnz={nnz} fp64 (north-star target)",
+            "value": value, "unit": "iterations/s", "n_gpus": world, "iterations_timed": int(iters),
+            "pure_step_iterations_per_s": iters / basic_s if basic_s > 0 else None,
+            "iteration_gbs_at_value": b * value / 1e9, "iteration_frac_at_value": b * value / 1e9 / (peak * world),
+            "host_generate_rescale_seconds": t_host, "folp_create_seconds": t_create}
 
 
 def _collect(solver, until, records):
@@ -539,6 +639,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=80)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only (ncu)")
+    ap.add_argument("--skip-target", action="store_true",
+                    help="skip the 1e7 x 1e7 x 1e8 sub-run that accompanies the default workload (detail.target)")
     args = ap.parse_args()
     _capture_stdout()
     if args.warmup < 3 and args.impl != "reference":
