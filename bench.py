@@ -39,10 +39,13 @@ WORKLOADS = {
     "pagerank": "pagerank",  # generate_pagerank_lp.jl at 1e6 nodes: one dense row + power-law degrees, ~8e6 nonzeros
     # the median Netlib instance class (~1e3 x 2e3, ~1.5e4 nonzeros): the launch-/latency-bound regime
     "netlib_small": "netlib_small",
+    # BASELINE.json configs[3]: generate_pagerank_lp.jl at 1e7 nodes (8e7 nonzeros, one dense row of 1e7 entries)
+    "pagerank7": "pagerank7",
 }
 
 
 WORKLOAD_LABEL = {"netlib": "synthetic Netlib-shaped block-angular LP", "pagerank": "PageRank LP (Barabasi-Albert graph)",
+                  "pagerank7": "PageRank LP (Barabasi-Albert graph, 1e7 nodes)",
                   "netlib_small": "synthetic Netlib-shaped block-angular LP, median Netlib size"}
 
 KERNEL_SOURCES = ("firstorderlp.jl_b200/csrc/folp_spmv.cuh", "firstorderlp.jl_b200/csrc/folp_kernels.cu",
@@ -114,6 +117,9 @@ def make_problem(workload):
     elif workload == "pagerank":
         from folp_b200.synthetic import pagerank_lp
         lp = pagerank_lp(1_000_000)
+    elif workload == "pagerank7":
+        from folp_b200.synthetic import pagerank_lp
+        lp = pagerank_lp(10_000_000)
     else:
         n, m, k = WORKLOADS[workload]
         lp = random_sparse_lp(n, m, k)
@@ -124,9 +130,11 @@ def make_problem(workload):
     params.termination_criteria.eps_optimal_relative = 0.0
     params.termination_criteria.eps_primal_infeasible = 0.0
     params.termination_criteria.eps_dual_infeasible = 0.0
-    holder, fparams, scaled = folp_b200.host_setup(params, lp)
+    # large instances: rescale_problem on the device (folp_rescale_problem, bit-identical to the host mirror)
+    big = lp.constraint_matrix.nnz > 30_000_000
+    holder, fparams, scaled = folp_b200.host_setup(params, lp, device_rescaling=big)
     log(f"[bench] problem {workload}: n={n} m={m} nnz={lp.constraint_matrix.nnz} "
-        f"generated+rescaled on host in {time.time() - t0:.1f}s")
+        f"generated on host and rescaled on the {'device' if big else 'host'} in {time.time() - t0:.1f}s")
     return lp, params, holder, fparams, scaled
 
 

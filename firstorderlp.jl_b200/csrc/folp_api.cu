@@ -211,6 +211,7 @@ struct folp_handle {
   unsigned pre_mask = 0;
   bool pre_dist = false, pre_ax_cur = false;
   int trm_grid = 0;   // > 0: all trust-region solves of an evaluation run as one cooperative kernel (k_tr_multi)
+  bool take_cluster = false;  // the take_grid CTAs form one thread-block cluster (tiny instances, single GPU)
   int take_grid = 0;  // > 0: batches of take_step attempts run as one cooperative kernel (k_take_steps) on this many blocks
   unsigned long long* d_timers = nullptr;  // phase timers of k_take_steps (folp_debug_profile_attempts)
   std::map<int, cudaGraphExec_t> step_graphs;
@@ -1321,19 +1322,27 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   // attempt is faster (measured, 1e6 x 1e6 x 1e7: 8 250 against 7 690 take_step iterations/s; a software
   // grid barrier costs ~3 us of fences and atomic round trips against ~1.5 us for a kernel boundary
   // inside a graph) and stays the default; FOLP_PERSISTENT=1 / 0 force either form.
+  // On TINY instances (a couple of work items per warp of one 8-CTA cluster: the median Netlib LP) an
+  // iteration is three latency chains; the persistent kernel runs as ONE thread-block cluster whose
+  // hardware barrier costs ~0.2 us, against ~6 us per kernel of a graph launch.
   {
     const char* pe = getenv("FOLP_PERSISTENT");
-    const bool want = pe ? atoi(pe) != 0 : (P > 1);
+    int64_t need = std::max<int64_t>((h->A.ntiles + kSpmvWarps - 1) / kSpmvWarps,
+                                     (h->At.ntiles + kSpmvWarps - 1) / kSpmvWarps);
+    need = std::max<int64_t>(need, (nl / 2 + kSpmvThreads - 1) / kSpmvThreads);
+    if (has_q) need = std::max<int64_t>(need, (h->Q.ntiles + kSpmvWarps - 1) / kSpmvWarps);
+    const bool tiny = P == 1 && need <= 2 * kTakeClusterMax && getenv("FOLP_NO_CLUSTER") == nullptr;
+    const bool want = pe ? atoi(pe) != 0 : (P > 1 || tiny);
     if (want && prop.cooperativeLaunch && getenv("FOLP_NO_PERSISTENT") == nullptr && (P == 1 || B.p2p)) {
       const int cap = take_steps_grid(h->sm_count, P > 1);
       // no more CTAs than there is work: fewer CTAs make a cheaper barrier on small instances
-      int64_t need = std::max<int64_t>((h->A.ntiles + kSpmvWarps - 1) / kSpmvWarps,
-                                       (h->At.ntiles + kSpmvWarps - 1) / kSpmvWarps);
-      need = std::max<int64_t>(need, (nl / 2 + kSpmvThreads - 1) / kSpmvThreads);
-      if (has_q) need = std::max<int64_t>(need, (h->Q.ntiles + kSpmvWarps - 1) / kSpmvWarps);
       if (const char* g = getenv("FOLP_TAKE_GRID")) need = atoi(g);
       h->take_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(cap, need)));
       if (cap <= 0) h->take_grid = 0;
+      if (tiny && h->take_grid > 0) {
+        h->take_cluster = true;
+        h->take_grid = std::min(h->take_grid, kTakeClusterMax);
+      }
     }
   }
 
@@ -1739,8 +1748,10 @@ static int enqueue_attempts(folp_handle* h, int attempts) {
   int rc;
   if (h->take_grid > 0) {  // the whole batch as one cooperative launch
     const cudaError_t le = static_cast<cudaError_t>(
-        launch_take_steps(h->B, h->A, h->At, h->Q, attempts, h->take_grid, h->stream));
-    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
+        h->take_cluster ? launch_take_steps_cluster(h->B, h->A, h->At, h->Q, attempts, h->take_grid, h->stream)
+                        : launch_take_steps(h->B, h->A, h->At, h->Q, attempts, h->take_grid, h->stream));
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported ||
+        (h->take_cluster && le != cudaSuccess)) {
       cudaGetLastError();  // the device is shared (MPS partition, ...): kernel-per-phase form from now on
       if (h->world > 1) {  // the ranks must agree on the form: an error rather than a silent divergence
         h->err = "cooperative launch of k_take_steps refused on this rank";
@@ -1784,7 +1795,15 @@ static int run_steps(folp_handle* h, int64_t target) {
   s->active = (s->iterations < target && !s->numerical_error) ? 1 : 0;
   if ((rc = push_state(h))) return rc;
   TRY(cudaEventRecord(h->ev0, h->stream));
+  int stalled_batches = 0;
   while (s->active) {
+    const int64_t before = s->iterations;
+    if (stalled_batches >= 64) {  // 64 batches (thousands of attempts) without one accepted step: not a solve any more
+      s->numerical_error = 1;
+      s->active = 0;
+      if ((rc = push_state(h))) return rc;
+      break;
+    }
     const int64_t remaining = target - s->iterations;
     int64_t attempts = remaining + (remaining >= 8 ? remaining / 16 + 1 : 0);
     if (s->policy == FOLP_STEP_CONSTANT) attempts = remaining;
@@ -1795,6 +1814,7 @@ static int run_steps(folp_handle* h, int64_t target) {
       h->err = "peer exchange timed out: a rank of the row partition stopped responding";
       return FOLP_CUDA_ERROR;
     }
+    stalled_batches = s->iterations == before ? stalled_batches + 1 : 0;
   }
   TRY(cudaEventRecord(h->ev1, h->stream));
   TRY(cudaEventSynchronize(h->ev1));
@@ -2607,8 +2627,10 @@ extern "C" int folp_debug_profile_attempts(folp_handle* h, int64_t attempts, dou
     Bufs Bt = h->B;
     Bt.timers = h->d_timers;
     for (int64_t left = attempts; left > 0; left -= 256) {
-      const cudaError_t le = static_cast<cudaError_t>(launch_take_steps(
-          Bt, h->A, h->At, h->Q, static_cast<int>(std::min<int64_t>(left, 256)), h->take_grid, h->stream));
+      const int chunk = static_cast<int>(std::min<int64_t>(left, 256));
+      const cudaError_t le = static_cast<cudaError_t>(
+          h->take_cluster ? launch_take_steps_cluster(Bt, h->A, h->At, h->Q, chunk, h->take_grid, h->stream)
+                          : launch_take_steps(Bt, h->A, h->At, h->Q, chunk, h->take_grid, h->stream));
       TRY(le);
       h->launches += 1;
     }

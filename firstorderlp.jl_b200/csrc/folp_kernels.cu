@@ -261,7 +261,10 @@ __device__ __noinline__ void finalize_attempt(DevState* st, double dx2, double d
     s.last_interaction = interaction;
     s.last_movement = movement;
     s.kkt_passes += 1;
-    if (movement == 0.0) {  // :691-695
+    // movement == 0: the reference's numerical error (:691-695). A NaN movement or interaction (a
+    // diverged or non-finite iterate) makes the reference's `step_size <= step_size_limit` false
+    // for ever -- its take_step never returns; here it ends the solve as a numerical error too.
+    if (movement == 0.0 || movement != movement || interaction != interaction) {
       s.numerical_error = 1;
       s.step_size = trial;  // :730
       s.iterations += 1;    // the failed take_step call still advances `iteration` (:887)
@@ -698,10 +701,16 @@ __device__ __forceinline__ void store_state(DevState* dst, const DevState* src) 
         reinterpret_cast<const unsigned long long*>(src)[threadIdx.x];
 }
 
-template <bool DIST>
+// CLUSTER: the whole grid is ONE thread-block cluster of at most 8 CTAs (tiny instances: the median
+// Netlib LP has ~1e3 x 2e3 entries and a few thousand nonzeros, an iteration is three latency chains
+// and no bandwidth at all). The hardware cluster barrier (release / acquire at cluster scope, ~0.2 us)
+// then replaces the atomics and fences of grid_barrier (~3 us), and CTA 0 closes the attempt.
+template <bool DIST, bool CLUSTER>
 __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm)
 k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, const __grid_constant__ SpmvMat At,
              const __grid_constant__ SpmvMat Q, int max_attempts) {
+  static_assert(!(DIST && CLUSTER), "the cluster form is single-GPU");
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
   __shared__ double s_red[32];
   __shared__ DevState st;
   __shared__ int s_flag, s_abort;
@@ -734,6 +743,21 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
     return s_abort != 0;
   };
 
+  // grid-wide barrier with a callback in ONE CTA (the last to arrive, or CTA 0 of the cluster) that
+  // every CTA waits for; need_fn = false: the callback may be skipped (no exchange, no timers)
+  auto barrier = [&](auto&& fn, bool need_fn) -> bool {
+    if (CLUSTER) {
+      cluster.sync();
+      if (need_fn) {
+        if (blockIdx.x == 0) (void)fn();
+        cluster.sync();
+      }
+      return false;
+    }
+    return grid_barrier(B, gen, &s_flag, fn);
+  };
+  const bool phase_fn = DIST || B.timers != nullptr;
+
   for (int a = 0; a < max_attempts; ++a) {
     if (!st.active) break;  // the same in every CTA: the copies are bit-identical
     // ---- phase 1: primal step on the (local slice of the) variables, xbar ----
@@ -742,11 +766,11 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
       const double t = block_reduce<false>(acc, s_red);
       if (threadIdx.x == 0) part_ptr(B, kSlotPrimal, 0)[blockIdx.x] = t;
     }
-    if (grid_barrier(B, gen, &s_flag, [&]() -> bool {
+    if (barrier([&]() -> bool {
           const bool lost = exchange(0);
           if (threadIdx.x == 0) stamp_phase(B, 0);
           return lost;
-        }))
+        }, phase_fn))
       break;
     // ---- phase 2: A * xbar, dual step (and, with a quadratic objective, Q * x+ and dx' Q dx) ----
     {
@@ -766,11 +790,11 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
         eq.publish(s_red);
       }
     }
-    if (grid_barrier(B, gen, &s_flag, [&]() -> bool {
+    if (barrier([&]() -> bool {
           const bool lost = exchange(1);
           if (threadIdx.x == 0) stamp_phase(B, 1);
           return lost;
-        }))
+        }, phase_fn))
       break;
     // ---- phase 3: A' * y+, interaction; the last CTA of the barrier closes the attempt ----
     {
@@ -780,7 +804,7 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
       __syncthreads();
       et.publish(s_red);
     }
-    if (grid_barrier(B, gen, &s_flag, [&]() -> bool {
+    if (barrier([&]() -> bool {
           attempt_totals(B, G, G, G, B.has_q ? G : 0, s_red);
           if (threadIdx.x == 0) {
             double t[5] = {s_red[16], s_red[17], s_red[18], s_red[19], s_red[20]};
@@ -816,17 +840,18 @@ k_take_steps(const __grid_constant__ Bufs B, const __grid_constant__ SpmvMat A, 
           __syncthreads();
           store_state(B.st, &st);  // published to the other CTAs (and the host) by the barrier's release
           return s_abort != 0;
-        }))
+        }, true))
       break;
-    if (s_flag != 1) load_state(&st, B.st);  // the closing CTA already holds the new state
+    const bool closing = CLUSTER ? blockIdx.x == 0 : s_flag == 1;
+    if (!closing) load_state(&st, B.st);  // the closing CTA already holds the new state
     __syncthreads();
   }
 }
 
 int take_steps_grid(int sm_count, bool dist) {
   int per_sm = 0;
-  const cudaError_t e = dist ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_take_steps<true>, kSpmvThreads, 0)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_take_steps<false>, kSpmvThreads, 0);
+  const cudaError_t e = dist ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_take_steps<true, false>, kSpmvThreads, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_take_steps<false, false>, kSpmvThreads, 0);
   if (e != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     return 0;
@@ -843,9 +868,27 @@ int launch_take_steps(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const 
                       int grid, cudaStream_t s) {
   void* args[] = {const_cast<Bufs*>(&B), const_cast<SpmvMat*>(&A), const_cast<SpmvMat*>(&At),
                   const_cast<SpmvMat*>(&Q), &attempts};
-  const void* fn = B.world > 1 ? reinterpret_cast<const void*>(k_take_steps<true>)
-                               : reinterpret_cast<const void*>(k_take_steps<false>);
+  const void* fn = B.world > 1 ? reinterpret_cast<const void*>(k_take_steps<true, false>)
+                               : reinterpret_cast<const void*>(k_take_steps<false, false>);
   return cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kSpmvThreads), args, 0, s);
+}
+
+// The same batch as ONE thread-block cluster of `grid` <= kTakeClusterMax CTAs (single GPU, tiny instances).
+int launch_take_steps_cluster(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q, int attempts,
+                              int grid, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kSpmvThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(grid);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_take_steps<false, true>, B, A, At, Q, attempts);
 }
 
 static int spmv_grid(const SpmvMat& A, int grid_spmv);

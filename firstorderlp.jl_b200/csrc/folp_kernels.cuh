@@ -151,6 +151,9 @@ void launch_step_attempts(const Bufs& B, const SpmvMat& A, const SpmvMat& At, co
 int take_steps_grid(int sm_count, bool dist);
 int launch_take_steps(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q, int attempts,
                       int grid, cudaStream_t s);
+int launch_take_steps_cluster(const Bufs& B, const SpmvMat& A, const SpmvMat& At, const SpmvMat& Q, int attempts,
+                              int grid, cudaStream_t s);
+constexpr int kTakeClusterMax = 8;      // portable cluster size: CTAs of the cluster form of k_take_steps
 constexpr int kBarGroupSize = 32;       // CTAs polling one release word of the grid barrier
 constexpr int kBarL1Stride = 32;        // unsigned words between first-level counters (128 bytes)
 constexpr int kBarMaxGroups = 64;

@@ -19,7 +19,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 import scipy.sparse as sp
 
-from .problem import QuadraticProgrammingProblem, ScaledQpProblem
+from .problem import QuadraticProgrammingProblem, ScaledQpProblem, is_linear_programming_problem
 
 
 def _col_index(matrix: sp.csc_matrix) -> np.ndarray:
@@ -243,7 +243,7 @@ def remove_empty_rows(problem: QuadraticProgrammingProblem) -> List[int]:
 
 def remove_empty_columns(problem: QuadraticProgrammingProblem) -> List[int]:
     """src/preprocess.jl:155-186 (0-based column ids)."""
-    assert problem.objective_matrix.nnz == 0 or not np.any(problem.objective_matrix.data != 0.0)
+    assert is_linear_programming_problem(problem)
     counts = np.diff(problem.constraint_matrix.indptr)
     is_empty = counts == 0
     empty_columns = np.flatnonzero(is_empty)
@@ -271,7 +271,7 @@ def presolve(problem: QuadraticProgrammingProblem, verbosity: int = 1) -> Presol
     saved_u = problem.variable_upper_bound.copy()
     original_dual_size, original_primal_size = problem.constraint_matrix.shape
     empty_rows = remove_empty_rows(problem)
-    if problem.objective_matrix.nnz == 0 or not np.any(problem.objective_matrix.data != 0.0):
+    if is_linear_programming_problem(problem):
         empty_columns = remove_empty_columns(problem)
     else:
         empty_columns = []

@@ -88,7 +88,9 @@ def linear_programming_problem(
 
 
 def is_linear_programming_problem(problem: QuadraticProgrammingProblem) -> bool:
-    return problem.objective_matrix.nnz == 0
+    """quadratic_programming.jl: iszero(objective_matrix) -- a test on VALUES: a Q that stores only
+    explicit zeros (QUADOBJ entries of 0, cancelled duplicates) is a linear program."""
+    return not np.any(problem.objective_matrix.data != 0.0)
 
 
 def equality_range(problem):

@@ -40,3 +40,17 @@ def test_single_process_multi_gpu_parity(world):
     sys.stderr.write(out.stderr[-6000:])
     assert out.returncode == 0
     assert "ALL OK" in out.stdout
+
+
+def test_peer_timeout_is_configurable_and_surfaces_as_error():
+    """tests/dist_timeout_worker.py: a stalled rank is tolerated up to FOLP_P2P_TIMEOUT_MS, then both
+    ranks get an error instead of a hung device."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(HERE, "dist_timeout_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(out.stdout[-4000:])
+    sys.stderr.write(out.stderr[-4000:])
+    assert out.returncode == 0
+    assert out.stdout.count("TIMEOUT OK") == 2

@@ -423,3 +423,35 @@ def test_time_limit_terminates():
     params.termination_criteria.iteration_limit = 50
     out_g = folp_b200.optimize(params, problem)
     assert out_g.termination_reason == TerminationReason.TERMINATION_REASON_ITERATION_LIMIT
+
+
+# ---------------------------------------------------------------------------
+# the three forms of a batch of take_step attempts
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("form,env", [
+    ("graph of three kernels per attempt", {"FOLP_PERSISTENT": "0"}),
+    ("persistent cooperative kernel, software grid barrier", {"FOLP_PERSISTENT": "1", "FOLP_NO_CLUSTER": "1"}),
+    ("persistent kernel as one thread-block cluster", {"FOLP_PERSISTENT": "1"}),
+])
+def test_take_step_forms_match_oracle(form, env, monkeypatch):
+    """Small instances default to the cluster form, large ones to the CUDA graph, the partitioned
+    mode to the cooperative kernel: every form is held to the same records here (LP with restarts,
+    then a QP, then Malitsky-Pock), and to bit-identical results run to run."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    problem = random_sparse_lp(1200, 900, 6, seed=31, upper_fraction=0.1)
+    params = generate_pdhg_params(iteration_limit=120, l_inf_ruiz_iterations=10, pock_chambolle_alpha=1.0,
+                                  restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED)
+    params.termination_evaluation_frequency = 8
+    eo, n_restart, records = _run_lockstep(problem, params)
+    assert n_restart >= 3 and records == 10 + 14
+    qp = random_sparse_qp(1200, 900, 6, seed=33, upper_fraction=0.1)
+    _run_lockstep(qp, params)
+    mp = generate_pdhg_params(iteration_limit=120, l_inf_ruiz_iterations=10, pock_chambolle_alpha=1.0,
+                              restart_scheme=RestartScheme.ADAPTIVE_NORMALIZED, step_size_policy="malitsky-pock")
+    mp.termination_evaluation_frequency = 8
+    _run_lockstep(problem, mp)
+    a = folp_b200.optimize(params, problem)
+    b = folp_b200.optimize(params, problem)
+    assert np.array_equal(a.primal_solution, b.primal_solution)
+    assert np.array_equal(a.dual_solution, b.dual_solution)
