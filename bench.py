@@ -193,8 +193,7 @@ def config_dict(args, n, m, nnz):
                           "adaptive_normalized restarts, evaluation every 40 iterations), tolerances 0 so every "
                           "step does the same work",
             "parallelism": "single GPU" if args.gpus == 1 else
-                           f"1-D partition over {args.gpus} GPUs (nnz-balanced row blocks + primal slices), one "
-                           "process per GPU",
+                           f"1-D partition over {args.gpus} GPUs (nnz-balanced row blocks + primal slices)",
             "l2_flush": ("working set 24*nnz + vectors = %.0f MB > 126 MB L2; no explicit flush" if ws > 126e6 else
                          "working set 24*nnz + vectors = %.0f MB fits the 126 MB L2 (an L2-resident instance "
                          "class by design); no flush") % (ws / 1e6)}
@@ -243,7 +242,14 @@ def bench_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
+    devices = None
+    if args.single_process and args.gpus > 1:
+        # ONE process drives all N GPUs through folp_create_multi (no torchrun, no NCCL): the entry a Julia
+        # optimize() would use. Everything below sees "world 1": the library's handle is the whole job.
+        devices = list(range(args.gpus))
+        os.environ["FOLP_DEVICES"] = ",".join(str(d) for d in devices)
+        world = 1
+    elif world != args.gpus:
         raise SystemExit(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}: for N>1 launch one rank per "
                          "GPU with python -m torch.distributed.run --nproc-per-node N")
     torch.cuda.set_device(local_rank)
@@ -290,9 +296,9 @@ def bench_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
     iteration = {"bytes": b1 + b2 + b3, "gbs_at_value": (b1 + b2 + b3) * value / 1e9,
-                 "frac_at_value": (b1 + b2 + b3) * value / 1e9 / (peak * world),
+                 "frac_at_value": (b1 + b2 + b3) * value / 1e9 / (peak * args.gpus),
                  "matrix_only_gbs_at_value": 24 * nnz * value / 1e9}
-    if world == 1:
+    if args.gpus == 1:
         # per-kernel device time of real attempts, continuing the same solve
         prof_attempts = 100
         solver.profile_attempts(10)
@@ -340,17 +346,17 @@ def bench_gpu(args):
             "bound": "hbm", "kernel": "whole iteration over all ranks (k_take_steps: primal / A*xbar / A'*y phases of one "
                                       "persistent cooperative kernel per rank; xbar and y+ pushed to every rank from the "
                                       "producing phase over peer memory, flags and four scalars on the grid barriers)",
-            "achieved": iteration["gbs_at_value"], "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
+            "achieved": iteration["gbs_at_value"], "peak": peak * args.gpus, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": iteration["frac_at_value"], "traffic": None, "iteration": iteration,
-            "nvlink_bytes_per_iteration_per_gpu": 8 * (n + m) * (world - 1) // world,
-            "nvlink_gbs_in_per_gpu_at_value": 8 * (n + m) * (world - 1) / world * value / 1e9,
+            "nvlink_bytes_per_iteration_per_gpu": 8 * (n + m) * (args.gpus - 1) // args.gpus,
+            "nvlink_gbs_in_per_gpu_at_value": 8 * (n + m) * (args.gpus - 1) / args.gpus * value / 1e9,
         }
     solver.close()
 
     # ---- the north-star target size (1e7 x 1e7, 1e8 nonzeros) on the same N GPUs: GPU arm only ----
     target = None
     if not args.skip_target and args.workload == "c2":
-        target = target_subrun(world, peak)
+        target = target_subrun(world, peak, args.gpus)
 
     # ---- e2e: the C-ABI call sequence with host buffers ----
     e2e = None
@@ -369,7 +375,19 @@ def bench_gpu(args):
         t3 = time.perf_counter()
         t_e2e = _max_over_ranks(t3 - t0, world)
         d2h = x.nbytes + y.nbytes
+        long_solve = None
+        if args.e2e_long_iters > 0:  # the same call sequence on a solve of realistic length (fixed costs amortised)
+            fparams.iteration_limit = args.e2e_long_iters
+            _barrier(world)
+            t0l = time.perf_counter()
+            s3 = Solver(holder, fparams)
+            _, _, _, it3, _ = s3.solve(max_evals=1)
+            s3.close()
+            torch.cuda.synchronize()
+            t_long = _max_over_ranks(time.perf_counter() - t0l, world)
+            long_solve = {"iterations": it3, "seconds": t_long, "value": it3 / t_long}
         e2e = {"value": it2 / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
+               "long_solve": long_solve,
                "d2h_bytes_per_step": d2h, "iterations": it2, "seconds": t_e2e,
                "seconds_create_solve_destroy": [t1 - t0, t2 - t1, t3 - t2],
                "what": "folp_create(host CSC arrays%s) + folp_solve + folp_get_solution, wall clock, max over ranks"
@@ -389,16 +407,16 @@ def bench_gpu(args):
             return Solver(holder, gp)
 
         # N > 1: a shorter oracle run on rank 0 (the other ranks wait for it)
-        sample = args.cpu_iters if world == 1 else min(args.cpu_iters, 40)
+        sample = args.cpu_iters if args.gpus == 1 else min(args.cpu_iters, 40)
         cpu, parity = cpu_baseline(params, lp, scaled, sample_iters=sample, world=world, rank=rank,
                                    make_gpu_solver=make_gpu_solver)
-        if world == 1:
+        if args.gpus == 1:
             rescale = rescale_timing(params, lp)
         else:
             cpu = None  # the contract wants the CPU baseline at N = 1 only; parity is kept at every N
 
     line = {
-        "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
+        "metric": "PDHG iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
@@ -411,7 +429,9 @@ def bench_gpu(args):
                    "final_l2_primal_residual": e.l2_primal_residual,
                    "final_l2_dual_residual": e.l2_dual_residual,
                    "folp_create_seconds": t_create, "rescale_problem": rescale, "build": build_info(),
-                   "exchange": exchange, "parity": parity, "target": target},
+                   "exchange": exchange, "parity": parity, "target": target,
+                   "launch": ("one process driving %d GPUs (folp_create_multi)" % args.gpus) if devices else
+                             ("one process per GPU (torchrun)" if world > 1 else "one process, one GPU")},
     }
     if rank == 0:
         emit(line)
@@ -424,7 +444,7 @@ def bench_gpu(args):
         sys.exit(3)
 
 
-def target_subrun(world, peak):
+def target_subrun(world, peak, n_gpus):
     """BASELINE.json's north-star target (synthetic random sparse LP, 1e7 variables, 1e7 constraints,
     1e8 nonzeros) on the same GPUs as the headline line: one warm-up step and two timed steps of 400
     iterations, same parameters, same timing rule (CUDA events on the library's stream, max over
@@ -464,11 +484,11 @@ def target_subrun(world, peak):
     basic_s = c1["basic_algorithm_seconds"] - c0["basic_algorithm_seconds"]
     value = iters / (ms * 1e-3)
     b = sum(algorithmic_bytes(n, m, nnz))
-    log(f"[bench] target sub-run: {value:.1f} it/s on {world} GPU(s), host {t_host:.1f}s, create {t_create:.2f}s")
+    log(f"[bench] target sub-run: {value:.1f} it/s on {n_gpus} GPU(s), host {t_host:.1f}s, create {t_create:.2f}s")
     return {"workload": f"synthetic random sparse LP n={n} m={m} nnz={nnz} fp64 (north-star target)",
-            "value": value, "unit": "iterations/s", "n_gpus": world, "iterations_timed": int(iters),
+            "value": value, "unit": "iterations/s", "n_gpus": n_gpus, "iterations_timed": int(iters),
             "pure_step_iterations_per_s": iters / basic_s if basic_s > 0 else None,
-            "iteration_gbs_at_value": b * value / 1e9, "iteration_frac_at_value": b * value / 1e9 / (peak * world),
+            "iteration_gbs_at_value": b * value / 1e9, "iteration_frac_at_value": b * value / 1e9 / (peak * n_gpus),
             "host_generate_rescale_seconds": t_host, "folp_create_seconds": t_create}
 
 
@@ -644,9 +664,13 @@ def main():
     ap.add_argument("--impl", default="folp_b200", choices=["folp_b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-iters", type=int, default=2000)
+    ap.add_argument("--e2e-long-iters", type=int, default=10000,
+                    help="second end-to-end call of this many iterations (e2e.long_solve; 0 = skip)")
     ap.add_argument("--cpu-iters", type=int, default=80)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only (ncu)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N > 1 and NO torchrun: one process drives the N GPUs (folp_create_multi)")
     ap.add_argument("--skip-target", action="store_true",
                     help="skip the 1e7 x 1e7 x 1e8 sub-run that accompanies the default workload (detail.target)")
     args = ap.parse_args()

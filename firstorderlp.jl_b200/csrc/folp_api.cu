@@ -1217,7 +1217,10 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   B.world = P; B.rank = h->rank;
   B.xbar_off = P > 1 ? static_cast<int>(c0) : 0;
   B.grid_spmv = h->sm_count * kSpmvCtasPerSm;
-  B.grid_vec = h->sm_count * 8;
+#ifndef FOLP_VEC_CTAS_PER_SM
+#define FOLP_VEC_CTAS_PER_SM 8
+#endif
+  B.grid_vec = h->sm_count * FOLP_VEC_CTAS_PER_SM;
   auto at = [](const double* v, int64_t off) { return v ? v + off : nullptr; };
   int rc;
   if ((rc = dev_alloc(h, &B.st, 1))) return rc;

@@ -158,6 +158,18 @@ __device__ __forceinline__ double primal_elem(const PrimalCtx& k, double x, doub
 // pushed into every peer's copy of xbar; the single-GPU instantiation carries no exchange code.
 // No __restrict__ / non-coherent loads on the iterates: the persistent kernel rewrites them between
 // grid barriers of one launch.
+// FOLP_K1_STREAM = 1 (default): K1's read-once operands bypass L2 residency (ld.cs / st.cs);
+// 0: default cache policy (development probe: do the vectors stay L2-resident between kernels?)
+#ifndef FOLP_K1_STREAM
+#define FOLP_K1_STREAM 1
+#endif
+__device__ __forceinline__ double2 k1_ld(const double2* p) {
+#if FOLP_K1_STREAM
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
 template <bool DIST>
 __device__ __forceinline__ double primal_range(const Bufs& B, const DevState& s, int t0, int stride) {
   double trial, theta;
@@ -185,11 +197,11 @@ __device__ __forceinline__ double primal_range(const Bufs& B, const DevState& s,
   for (int j = t0; j < n2; j += stride) {
     const double2 x = reinterpret_cast<const double2*>(xc)[j];
     // read-once streams go past L2 (evict-first): at n >= 1e7 L2 is needed for the gathered vectors
-    const double2 c = __ldcs(reinterpret_cast<const double2*>(B.c) + j);
-    const double2 a = __ldcs(reinterpret_cast<const double2*>(at) + j);
-    const double2 l = __ldcs(reinterpret_cast<const double2*>(B.l) + j);
-    const double2 u = __ldcs(reinterpret_cast<const double2*>(B.u) + j);
-    double2 sx = avg ? __ldcs(reinterpret_cast<const double2*>(B.sum_x) + j) : make_double2(0.0, 0.0);
+    const double2 c = k1_ld(reinterpret_cast<const double2*>(B.c) + j);
+    const double2 a = k1_ld(reinterpret_cast<const double2*>(at) + j);
+    const double2 l = k1_ld(reinterpret_cast<const double2*>(B.l) + j);
+    const double2 u = k1_ld(reinterpret_cast<const double2*>(B.u) + j);
+    double2 sx = avg ? k1_ld(reinterpret_cast<const double2*>(B.sum_x) + j) : make_double2(0.0, 0.0);
     double2 xp = rd_xn ? reinterpret_cast<const double2*>(xn)[j] : make_double2(0.0, 0.0);
     double2 xb;
     const double2 q = k.has_q ? reinterpret_cast<const double2*>(qxc)[j] : make_double2(0.0, 0.0);
@@ -1220,14 +1232,26 @@ __global__ void __launch_bounds__(kVecThreads) k_dist(Bufs B, double* red_out) {
   reduce_and_publish<SD_TOTAL, 0>(B, s, mx, red_out, sh);
 }
 
+// The statistics kernels end in a block reduction of 4-28 values (~300 shuffles per thread): a fixed cost
+// per block. FOLP_STATS_CTAS_PER_SM blocks per SM (default 3; was 8: 3.3 elements per thread at n = 1e6),
+// never more blocks than there are elements to give every thread one.
+#ifndef FOLP_STATS_CTAS_PER_SM
+#define FOLP_STATS_CTAS_PER_SM 3
+#endif
+static int stats_grid(const Bufs& B, int len) {
+  int g = B.grid_spmv / kSpmvCtasPerSm * FOLP_STATS_CTAS_PER_SM;
+  const int need = (len + kVecThreads - 1) / kVecThreads;
+  if (g > need) g = need;
+  return g < 1 ? 1 : g;
+}
 void launch_stats_n(const Bufs& B, double* red_out, cudaStream_t s) {
-  k_stats_n<<<B.grid_vec, kVecThreads, 0, s>>>(B, red_out);
+  k_stats_n<<<stats_grid(B, B.n), kVecThreads, 0, s>>>(B, red_out);
 }
 void launch_stats_m(const Bufs& B, double* red_out, cudaStream_t s) {
-  k_stats_m<<<B.grid_vec, kVecThreads, 0, s>>>(B, red_out);
+  k_stats_m<<<stats_grid(B, B.m), kVecThreads, 0, s>>>(B, red_out);
 }
 void launch_dist(const Bufs& B, double* red_out, cudaStream_t s) {
-  k_dist<<<B.grid_vec, kVecThreads, 0, s>>>(B, red_out);
+  k_dist<<<stats_grid(B, B.n > B.m ? B.n : B.m), kVecThreads, 0, s>>>(B, red_out);
 }
 
 // The vector half of a restart (sp.jl:804-825, :921-923, pdhg.jl:1018-1022).

@@ -44,6 +44,18 @@ constexpr int kGatherUnroll = FOLP_GATHER_UNROLL;  // independent gathers per la
 // streaming loads of the matrix arrays: read once per product, keep them out of the way
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+// per-row operands of the epilogues. FOLP_EPI_STREAM = 1 (default): streamed past L2 like the matrix;
+// 0: default cache policy (development probe)
+#ifndef FOLP_EPI_STREAM
+#define FOLP_EPI_STREAM 1
+#endif
+__device__ __forceinline__ double ld_epi(const double* p) {
+#if FOLP_EPI_STREAM
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
 
 // hot half of a work-item descriptor
 struct TileHot {
@@ -74,8 +86,23 @@ __device__ __forceinline__ void spmv_items(const SpmvMat& A, Epi& epi, int first
   const double* xin = epi.input();
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
+#ifndef FOLP_TILE_PREFETCH
+#define FOLP_TILE_PREFETCH 0
+#endif
+#if FOLP_TILE_PREFETCH
+  // the descriptor of the NEXT work item is requested while this one is processed: one of the three
+  // dependent latencies (descriptor -> row extents -> first entries) at the head of an item leaves its
+  // critical path
+  TileHot t_next;
+  if (first < A.ntiles) t_next = load_hot(A.tiles, first);
+#endif
   for (int item = first; item < A.ntiles; item += stride) {
+#if FOLP_TILE_PREFETCH
+    const TileHot t = t_next;
+    if (item + stride < A.ntiles) t_next = load_hot(A.tiles, item + stride);
+#else
     const TileHot t = load_hot(A.tiles, item);
+#endif
     const int kind = t.kind();
     if (kind == kTileThreadPerRow || kind == kTileThreadPerRowSorted) {
       // ---- up to 32 narrow rows, one per lane ----
@@ -92,9 +119,9 @@ __device__ __forceinline__ void spmv_items(const SpmvMat& A, Epi& epi, int first
           len = __ldg(A.rowptr + r + 1) - __ldg(A.rowptr + r);
         }
         // per-row operands are read once: stream them past L2 so that the gathered vector stays
-        if (Epi::kNumIn > 0) in0 = ld_stream(epi.in_ptr(0) + r);
-        if (Epi::kNumIn > 1) in1 = ld_stream(epi.in_ptr(1) + r);
-        if (Epi::kNumIn > 2) in2 = ld_stream(epi.in_ptr(2) + r);
+        if (Epi::kNumIn > 0) in0 = ld_epi(epi.in_ptr(0) + r);
+        if (Epi::kNumIn > 1) in1 = ld_epi(epi.in_ptr(1) + r);
+        if (Epi::kNumIn > 2) in2 = ld_epi(epi.in_ptr(2) + r);
       }
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
       int off = t.nnz_begin;  // first entry of the current position

@@ -216,6 +216,7 @@ function optimize_b200(
   params::FirstOrderLp.PdhgParameters,
   original_problem::FirstOrderLp.QuadraticProgrammingProblem;
   device_rescaling::Bool = false,
+  device_ids::Vector{Int32} = Int32[],   # more than one entry: folp_create_multi drives all of them from this call
 )
   # ---- host half, unchanged (pdhg.jl:786-859) ----
   FirstOrderLp.validate(original_problem)
@@ -284,7 +285,10 @@ function optimize_b200(
   O = scaled_problem.original_qp
   n_out, m_out = n, m
   x_out, y_out = Vector{Float64}(undef, n_out), Vector{Float64}(undef, m_out)
-  evals = Vector{FolpEval}(undef, 1 << 16)
+  # every evaluation when record_iteration_stats is set (:958-960), the final record only otherwise
+  max_evals = params.record_iteration_stats ?
+    Int(min(tc.iteration_limit, typemax(Int32))) ÷ max(1, params.termination_evaluation_frequency) + 16 : 1
+  evals = Vector{FolpEval}(undef, max_evals)
   num_evals, reason, iters = Ref{Int64}(0), Ref{Int32}(0), Ref{Int32}(0)
   handle = Ref{Ptr{Cvoid}}(C_NULL)
   # All arrays are borrowed for the duration of folp_create only.
@@ -304,21 +308,65 @@ function optimize_b200(
       qp_cache.l_inf_norm_primal_linear_objective, qp_cache.l_inf_norm_primal_right_hand_side,
       qp_cache.l2_norm_primal_linear_objective, qp_cache.l2_norm_primal_right_hand_side,
     ))
-    rc = ccall((:folp_create, LIB), Cint,
-               (Ref{FolpProblem}, Ref{FolpParams}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
-               fp, Ref(fparams), C_NULL, handle)
+    if length(device_ids) > 1
+      # one call, several GPUs of this process: threads of the library drive the devices (folp_create_multi)
+      rc = ccall((:folp_create_multi, LIB), Cint,
+                 (Ref{FolpProblem}, Ref{FolpParams}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+                 fp, Ref(fparams), Int32(length(device_ids)), device_ids, handle)
+    else
+      rc = ccall((:folp_create, LIB), Cint,
+                 (Ref{FolpProblem}, Ref{FolpParams}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                 fp, Ref(fparams), C_NULL, handle)
+    end
     check(rc, C_NULL)
   end
+  stats = FirstOrderLp.IterationStats[]
   try
-    rc = ccall((:folp_solve, LIB), Cint,
-               (Ptr{Cvoid}, Ptr{FolpEval}, Int64, Ref{Int64}, Ref{Int32}, Ref{Int32},
-                Ptr{Float64}, Ptr{Float64}),
-               handle[], evals, length(evals), num_evals, reason, iters, x_out, y_out)
-    check(rc, handle[])
+    if params.verbosity <= 0
+      # nothing to print: the whole loop in one C call
+      rc = ccall((:folp_solve, LIB), Cint,
+                 (Ptr{Cvoid}, Ptr{FolpEval}, Int64, Ref{Int64}, Ref{Int32}, Ref{Int32},
+                  Ptr{Float64}, Ptr{Float64}),
+                 handle[], evals, length(evals), num_evals, reason, iters, x_out, y_out)
+      check(rc, handle[])
+      num_evals[] > length(evals) && @warn "iteration statistics truncated" num_evals[] length(evals)
+      stats = [to_iteration_stats(evals[k]) for k in 1:min(num_evals[], length(evals))]
+    else
+      # verbosity > 0: the loop of pdhg.jl:886-1048 evaluation by evaluation (folp_run), printing with the
+      # reference's own functions where the reference prints (iteration table :962-970, final log :972-993)
+      FirstOrderLp.display_iteration_stats_heading(params.verbosity)
+      e = Ref{FolpEval}()
+      while true
+        rc = ccall((:folp_run, LIB), Cint, (Ptr{Cvoid}, Ref{FolpEval}), handle[], e)
+        check(rc, handle[])
+        st = to_iteration_stats(e[])
+        iteration = Int(e[].iteration_number) + 1
+        terminated = e[].termination_reason != 0
+        (params.record_iteration_stats || terminated) && push!(stats, st)
+        if FirstOrderLp.print_to_screen_this_iteration(
+          terminated ? FirstOrderLp.TerminationReason(e[].termination_reason) : false,
+          iteration, params.verbosity, params.termination_evaluation_frequency)
+          FirstOrderLp.display_iteration_stats(st, params.verbosity)
+        end
+        if terminated
+          reason[] = e[].termination_reason
+          iters[] = e[].iteration_number
+          rc = ccall((:folp_get_solution, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+                     handle[], 0, 1, x_out, y_out)
+          check(rc, handle[])
+          xs, ys = similar(x_out), similar(y_out)   # the reference logs the SCALED average on the scaled problem
+          rc = ccall((:folp_get_solution, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+                     handle[], 0, 0, xs, ys)
+          check(rc, handle[])
+          FirstOrderLp.pdhg_final_log(problem, xs, ys, params.verbosity, iteration,
+                                      FirstOrderLp.TerminationReason(reason[]), st)
+          break
+        end
+      end
+    end
   finally
     ccall((:folp_destroy, LIB), Cvoid, (Ptr{Cvoid},), handle[])
   end
-  stats = [to_iteration_stats(evals[k]) for k in 1:num_evals[]]
   termination_reason = FirstOrderLp.TerminationReason(reason[])
   return FirstOrderLp.SaddlePointOutput(
     x_out, y_out, termination_reason,
