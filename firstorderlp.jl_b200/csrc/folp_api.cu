@@ -668,6 +668,7 @@ static int setup_peer_exchange_in_process(folp_handle* h) {
   for (int r = 0; r < P; ++r) set_peer_pointers(h, r, mc->regions[r]);
   h->B.p2p = 1;
   if (const char* d = getenv("FOLP_DEBUG_FLAGS")) h->B.dbg = atoi(d);
+  if (getenv("FOLP_BULK_PUSH") != nullptr) h->B.dbg |= 8;
   mc->barrier();
   return FOLP_OK;
 }
@@ -738,6 +739,7 @@ static int setup_peer_exchange(folp_handle* h) {
   for (int r = 0; r < P; ++r) set_peer_pointers(h, r, r == h->rank ? h->region : h->peer_region[r]);
   B.p2p = 1;
   if (const char* d = getenv("FOLP_DEBUG_FLAGS")) B.dbg = atoi(d);
+  if (getenv("FOLP_BULK_PUSH") != nullptr) B.dbg |= 8;
   if (B.dbg & 4) {  // probe: gather from private copies of the exchanged vectors
     B.xbar_priv = h->d_cols;
     B.yfull_priv = h->d_rows;
@@ -1139,6 +1141,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       h->n_pad += h->n_pad & 1;
       h->m_pad = 0;
       for (int r = 0; r < P; ++r) h->m_pad = std::max(h->m_pad, h->row_begin[r + 1] - h->row_begin[r]);
+      h->m_pad += h->m_pad & 1;  // every rank's rows start on a 16-byte boundary of y_full (bulk pushes)
       h->col0 = std::min<int64_t>(n, h->rank * h->n_pad);
       h->n = std::min<int64_t>(n, (h->rank + 1) * h->n_pad) - h->col0;
       h->row0 = h->row_begin[h->rank];

@@ -49,7 +49,8 @@ struct Bufs {
   // Every rank exposes one region {xbar, y_full, sc_recv, scx, flags}; *_peer[r] is rank r's copy
   // (this rank's own entries are the local pointers above).
   int p2p = 0;
-  int dbg = 0;  // development probes (FOLP_DEBUG_FLAGS): 1 = skip the remote pushes, 2 = skip flag waits
+  int dbg = 0;  // development probes (FOLP_DEBUG_FLAGS): 1 = skip the remote pushes, 2 = skip flag waits, 4 = private gather copies,
+                // 8 = copy-engine (cp.async.bulk) pushes of xbar tiles / y+ groups (also FOLP_BULK_PUSH=1), 16 = relaxed flag polling + one fence
   const double* xbar_priv = nullptr;   // when set: K2 gathers from this private copy of xbar
   const double* yfull_priv = nullptr;  // when set: K3 gathers from this private copy of y_full
   double* xbar_peer[kMaxWorld] = {};

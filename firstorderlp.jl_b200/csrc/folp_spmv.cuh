@@ -17,8 +17,8 @@
 //     (folp_internal.cuh) the 32 lanes of a warp read CONSECUTIVE values and
 //     column indices at every position: 3 coalesced wavefronts per 32 nonzeros,
 //     straight from global memory (streaming, evict-first) into registers. There is
-//     no shared-memory staging: a TMA-fed shared-memory ring (kept for the record in
-//     experimental/) costs the same pipe slots to read back, needs a second pass
+//     no shared-memory staging: a TMA-fed shared-memory ring (v1-v3 of this kernel, git history:
+//     commit 2090fdf and before) costs the same pipe slots to read back, needs a second pass
 //     for the row sums and measured 15-40 % slower;
 //   * each lane gathers, multiplies and adds in ascending column order in a
 //     register and runs the fused epilogue on its row: no products written back;
@@ -123,6 +123,7 @@ __device__ __forceinline__ void spmv_items(const SpmvMat& A, Epi& epi, int first
         if (Epi::kNumIn > 1) in1 = ld_epi(epi.in_ptr(1) + r);
         if (Epi::kNumIn > 2) in2 = ld_epi(epi.in_ptr(2) + r);
       }
+      epi.group_begin(t.row_begin, t.rows(), kind == kTileThreadPerRowSorted);  // all lanes
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
       int off = t.nnz_begin;  // first entry of the current position
       double s = 0.0;
@@ -173,7 +174,9 @@ __device__ __forceinline__ void spmv_items(const SpmvMat& A, Epi& epi, int first
       }
 #endif
       if (valid) epi.row(r, s, in0, in1, in2);
+      epi.group_end();  // all lanes
     } else {
+      epi.group_begin(t.row_begin, 1, true);  // a single row handled by the whole warp: no group staging
       // ---- one warp on (a chunk of) one row, plain CSR order ----
       // Four independent loads / gathers / partial sums per lane and trip: a chunk is a serial
       // chain otherwise (measured on the PageRank LP's dense row: 128 dependent trips of ~0.4 us
@@ -247,6 +250,8 @@ struct EpiPlain {
   __device__ const double* input() const { return in; }
   __device__ const double* in_ptr(int) const { return nullptr; }
   __device__ void row(int r, double s, double, double, double) { out[r] = s; }
+  __device__ void group_begin(int, int, bool) {}
+  __device__ void group_end() {}
   __device__ void finish(double*) {}
 };
 
