@@ -211,6 +211,8 @@ struct folp_handle {
   unsigned pre_mask = 0;
   bool pre_dist = false, pre_ax_cur = false;
   int trm_grid = 0;   // > 0: all trust-region solves of an evaluation run as one cooperative kernel (k_tr_multi)
+  std::vector<double> h_tmp;  // staging of primal-indexed vectors at the boundary (renumbering)
+  std::vector<int> new2old;   // device numbering of the variables -> the caller's (empty: identity); order_variables
   bool take_cluster = false;  // the take_grid CTAs form one thread-block cluster (tiny instances, single GPU)
   int take_grid = 0;  // > 0: batches of take_step attempts run as one cooperative kernel (k_take_steps) on this many blocks
   unsigned long long* d_timers = nullptr;  // phase timers of k_take_steps (folp_debug_profile_attempts)
@@ -401,15 +403,17 @@ static void plan_tiles(int rows, const IVec& rowptr, int warps_total, PackedMatr
       }
     }
   }
-  // Opt-in (FOLP_BALANCE_TILES=1; DESIGN.md section 10, lead 1): a cost-balanced STATIC order of
-  // the work items. k_spmv hands item i to warp i % warps_total; in row order the busiest warp of
-  // A' on the 1e6 x 1e6 x 1e7 workload carries 56 cost units against a mean of 46.4, a
-  // longest-processing-time assignment 49. Items are dealt to the least loaded warp in order of
+  // A cost-balanced STATIC order of the work items (FOLP_NO_BALANCE_TILES=1 keeps the matrix order).
+  // k_spmv hands item i to warp i % warps_total. Items are dealt to the least loaded warp in order of
   // decreasing cost (rounds of a group, 128-entry trips of a warp-per-row item, + 1), then laid out
   // so that warp w's k-th item sits at index k * warps_total + w, short lists padded with empty
   // groups. Deterministic (a function of the matrix and the grid), no atomics; the per-thread
-  // partial sums of the reductions are simply formed over other rows. Not measured yet.
-  if (getenv("FOLP_BALANCE_TILES") != nullptr && warps_total > 0 &&
+  // partial sums of the reductions are simply formed over other rows. Measured: nothing on rows in
+  // matrix order (round 1: every group of a random matrix costs about the same), but with the
+  // variables renumbered by column length (order_variables) groups differ by up to 5x and the
+  // balance is what turns fewer rounds into time: A'*y 60.6 -> 57.8 us on the 1e6 x 1e6 x 1e7 workload,
+  // 57.5 -> 48.3 us (and A*xbar 62.3 -> 56.2 us) on the PageRank LP.
+  if (getenv("FOLP_NO_BALANCE_TILES") == nullptr && warps_total > 0 &&
       tiles.size() > static_cast<size_t>(warps_total)) {
     const size_t T = tiles.size();
     std::vector<int> cost(T);
@@ -461,7 +465,9 @@ static void plan_tiles(int rows, const IVec& rowptr, int warps_total, PackedMatr
 // CSR source is read through col(k) / val(k) -- the caller's own Int64 arrays, or scratch.
 template <class GetCol, class GetVal>
 static void fill_packed(const PackedMatrix& pk, const IVec& rowptr, GetCol col, GetVal val,
-                        int* dcol, double* dval) {
+                        int* dcol, double* dval, const int* src_start = nullptr) {
+  // src_start (optional): entry `pos` of row `row` is read at col/val(src_start[row] + pos) instead of
+  // (rowptr[row] + pos): the rows of the source are a permutation of the packed rows (order_variables)
   const std::vector<Tile>& tiles = pk.tiles;
   const std::vector<int>& rowid = pk.rowid;
   parallel_for(0, static_cast<int64_t>(tiles.size()), 1 << 11, [&](int64_t lo, int64_t hi, int) {
@@ -469,9 +475,11 @@ static void fill_packed(const PackedMatrix& pk, const IVec& rowptr, GetCol col, 
       const Tile& t = tiles[ti];
       const int kind = t.rows_kind >> 16;
       if (kind != kTileThreadPerRow && kind != kTileThreadPerRowSorted) {
+        const int row = t.row_begin;
+        const int shift = src_start ? src_start[row] - rowptr[row] : 0;
         for (int k = t.nnz_begin; k < t.nnz_end; ++k) {
-          dcol[k] = col(k);
-          dval[k] = val(k);
+          dcol[k] = col(k + shift);
+          dval[k] = val(k + shift);
         }
         continue;
       }
@@ -481,7 +489,7 @@ static void fill_packed(const PackedMatrix& pk, const IVec& rowptr, GetCol col, 
         for (int q = g; q < g1; ++q) {
           const int row = rowid[q];
           if (rowptr[row + 1] - rowptr[row] > pos) {
-            const int k = rowptr[row] + pos;
+            const int k = (src_start ? src_start[row] : rowptr[row]) + pos;
             dcol[out] = col(k);
             dval[out] = val(k);
             ++out;
@@ -759,9 +767,13 @@ static int setup_peer_exchange(folp_handle* h) {
 //      a core's cache.
 // The result does not depend on the thread count. Returns false if a row index is out of range
 // (nothing is written out of bounds).
+// col_id (optional, n entries): the column index stored for column j (a renumbering of the columns;
+// the entries of a row keep the order of the ORIGINAL column numbers, so that row sums are formed
+// in the reference's order).
 template <class RowOf, class ValOf>
 static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, RowOf row_of,
-                             ValOf val_of, IVec* rp2_out, IVec* ci2_out, DVec* v2_out) {
+                             ValOf val_of, IVec* rp2_out, IVec* ci2_out, DVec* v2_out,
+                             const int* col_id = nullptr) {
   IVec& rp2 = *rp2_out;
   IVec& ci2 = *ci2_out;
   DVec& v2 = *v2_out;
@@ -826,7 +838,7 @@ static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, 
     for (int64_t j = cut[t]; j < cut[t + 1]; ++j)
       for (int64_t k = rp[j]; k < rp[j + 1]; ++k) {
         const int r = static_cast<int>(row_of(k));
-        buf[cur[r >> S]++] = Entry{r, static_cast<int>(j), val_of(k)};
+        buf[cur[r >> S]++] = Entry{r, col_id ? col_id[j] : static_cast<int>(j), val_of(k)};
       }
   });
   std::atomic<int64_t> next_block{0};
@@ -884,6 +896,77 @@ bool csr_permutation(int64_t n, int64_t m, int64_t nnz, const int64_t* colptr, c
 }
 }  // namespace folp
 
+// ---------------------------------------------------------------------------
+// Physical reordering of the VARIABLES (= the rows of A') by column length.
+//
+// k_spmv gives one lane one row, and the 32 lanes of a group wait for the longest row: on the
+// columns of a random matrix (Poisson(10) lengths, the bench workload) a group runs 6 rounds where
+// 3.5 would do, and A'*y costs 64 us against 55 us for the uniform rows of A. Sorting rows by length
+// through a slot table (the length-sorted windows of plan_tiles) removes the rounds but scatters the
+// epilogue's per-row accesses and measured no gain. Here the variables themselves are renumbered --
+// inside windows of kVarSortWindow consecutive variables, by decreasing column length, stably -- and
+// EVERYTHING primal-indexed lives in the new numbering on the device (c, l, u, x, A'y, averages, D,
+// the column indices of A, rows and columns of Q): no indirection anywhere in a kernel. The caller's
+// numbering exists only at the boundary: inputs are gathered through new2old when they are uploaded,
+// outputs scattered back when they are fetched. Row sums keep the reference's order: the entries of
+// a row of A are stored in the order of their ORIGINAL column numbers, a row of A' (one variable) is
+// untouched. Windows keep the renumbering local (structured LPs keep their column locality).
+// FOLP_NO_VAR_SORT=1 disables it.
+// ---------------------------------------------------------------------------
+constexpr int kVarSortWindow = 2048;
+struct VarOrder {
+  bool identity = true;
+  std::vector<int> new2old, old2new;
+  IVec rp_new;      // column pointers in the new numbering
+  IVec src_start;   // first entry of new column j' in the caller's arrays
+};
+static void order_variables(int64_t n, const IVec& rp, VarOrder* vo) {
+  vo->identity = true;
+  if (getenv("FOLP_NO_VAR_SORT") != nullptr || n < 64) return;
+  int64_t window = kVarSortWindow;
+  if (const char* w = getenv("FOLP_VAR_SORT_WINDOW")) window = std::max<int64_t>(64, atoll(w) / 32 * 32);
+  vo->new2old.resize(static_cast<size_t>(n));
+  constexpr int kCap = 2 * kNarrowMax;  // longer columns are warp-per-row items anyway: one bucket
+  bool changed = false;
+  for (int64_t w0 = 0; w0 < n; w0 += window) {
+    const int64_t w1 = std::min<int64_t>(n, w0 + window);
+    int start[kCap + 2] = {0};
+    auto bucket = [&](int64_t j) { return kCap - std::min<int>(kCap, rp[j + 1] - rp[j]); };  // decreasing length
+    for (int64_t j = w0; j < w1; ++j) start[bucket(j) + 1] += 1;
+    for (int b = 0; b <= kCap; ++b) start[b + 1] += start[b];
+    // The groups of a sorted window run from the longest rows to the shortest, and k_spmv hands work
+    // item i to warp i % warps_total: with a window of 64 groups and 4736 warps a warp would meet the
+    // SAME rank of every window it visits -- always the longest group, or always the shortest
+    // (measured: A'*y 79 us instead of 64). The order of the window's full groups is therefore rotated
+    // by a per-window pseudo-random amount, so that every warp meets all ranks.
+    const int64_t full = (w1 - w0) / 32;  // groups of exactly 32 variables; a shorter tail stays last
+    const int64_t rot = full > 1 ? static_cast<int64_t>((static_cast<uint64_t>(w0 / window) * 2654435761ull >> 7) % full) : 0;
+    for (int64_t j = w0; j < w1; ++j) {
+      int64_t at = start[bucket(j)]++;  // rank inside the window
+      if (at < full * 32) at = ((at / 32 + rot) % full) * 32 + at % 32;
+      at += w0;
+      vo->new2old[at] = static_cast<int>(j);
+      changed = changed || at != j;
+    }
+  }
+  if (!changed) {
+    vo->new2old.clear();
+    return;
+  }
+  vo->identity = false;
+  vo->old2new.resize(static_cast<size_t>(n));
+  vo->rp_new.resize(static_cast<size_t>(n) + 1);
+  vo->src_start.resize(static_cast<size_t>(n) + 1);
+  vo->rp_new[0] = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    const int o = vo->new2old[j];
+    vo->old2new[o] = static_cast<int>(j);
+    vo->rp_new[j + 1] = vo->rp_new[j] + (rp[o + 1] - rp[o]);
+    vo->src_start[j] = rp[o];
+  }
+  vo->src_start[n] = 0;
+}
+
 // Host half of folp_create on one GPU: A' (= the caller's CSC, read as CSR) is planned and packed
 // straight from the caller's Int64 arrays on a second thread while this one transposes into the
 // CSR of A and packs that. No CUDA call. False if a row index is out of range.
@@ -892,7 +975,7 @@ struct HostMatrices {
   IVec atc, ac, rp2;
   DVec atv, av;
 };
-static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, int warps_total,
+static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, const VarOrder& vo, int warps_total,
                                   HostMatrices* out) {
   const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
   const int base = p->index_base;
@@ -907,16 +990,18 @@ static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, int war
   const bool timing = getenv("FOLP_TIMING") != nullptr;
   const double t0 = now_sec();
   double t_side_plan = 0, t_side = 0;
+  const IVec& rp_t = vo.identity ? rp : vo.rp_new;  // rows of A' in the device numbering of the variables
   std::thread side([&] {
-    plan_tiles(static_cast<int>(n), rp, warps_total, &out->pk_t);
+    plan_tiles(static_cast<int>(n), rp_t, warps_total, &out->pk_t);
     t_side_plan = now_sec();
-    fill_packed(out->pk_t, rp, [=](int k) { return static_cast<int>(row_of(k)); }, val_of,
-                out->atc.data(), out->atv.data());
+    fill_packed(out->pk_t, rp_t, [=](int k) { return static_cast<int>(row_of(k)); }, val_of,
+                out->atc.data(), out->atv.data(), vo.identity ? nullptr : vo.src_start.data());
     t_side = now_sec();
   });
   IVec ci2;
   DVec v2;
-  const bool ok = transpose_to_csr(n, m, nnz, rp, row_of, val_of, &out->rp2, &ci2, &v2);
+  const bool ok = transpose_to_csr(n, m, nnz, rp, row_of, val_of, &out->rp2, &ci2, &v2,
+                                   vo.identity ? nullptr : vo.old2new.data());
   const double t1 = now_sec();
   double t2 = t1;
   if (ok) {
@@ -944,7 +1029,9 @@ extern "C" int folp_debug_host_prepare(const folp_problem* p, double* millisecon
   IVec rp(static_cast<size_t>(n) + 1);
   for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - p->index_base) : 0;
   HostMatrices hm;
-  const bool ok = prepare_host_matrices(p, rp, 148 * kSpmvCtasPerSm * kSpmvWarps, &hm);
+  VarOrder vo;
+  order_variables(n, rp, &vo);
+  const bool ok = prepare_host_matrices(p, rp, vo, 148 * kSpmvCtasPerSm * kSpmvWarps, &hm);
   *milliseconds = (now_sec() - t0) * 1e3;
   return ok ? FOLP_OK : FOLP_INVALID_ARGUMENT;
 }
@@ -1082,6 +1169,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   const int base = p->index_base;
   const int P = h->world;
   h->row_begin.assign(static_cast<size_t>(P) + 1, 0);
+  VarOrder vo;  // device numbering of the variables (order_variables)
   {
     IVec rp(static_cast<size_t>(n) + 1);
     for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - base) : 0;
@@ -1098,12 +1186,15 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     IVec rp2, ci2;
     DVec v2;
     int rc;
+    order_variables(n, rp, &vo);
+    if (!vo.identity) h->new2old = vo.new2old;
+    const IVec& rp_t = vo.identity ? rp : vo.rp_new;  // column pointers in the device numbering
     if (P == 1) {
       h->row_begin[1] = m;
       h->n_pad = n; h->m_pad = m;
       h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
       HostMatrices hm;
-      if (!prepare_host_matrices(p, rp, warps_total, &hm)) {
+      if (!prepare_host_matrices(p, rp, vo, warps_total, &hm)) {
         h->err = "row index out of range";
         return FOLP_INVALID_ARGUMENT;
       }
@@ -1126,10 +1217,11 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       const PackedMatrix &pk_t = hm.pk_t, &pk_a = hm.pk_a;
       const IVec &atc = hm.atc, &ac = hm.ac, &rp2 = hm.rp2;
       const DVec &atv = hm.atv, &av = hm.av;
-      if ((rc = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp, pk_t, atc, atv))) return rc;
+      if ((rc = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp_t, pk_t, atc, atv))) return rc;
       if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, pk_a, ac, av))) return rc;
     } else {
-      if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &v2)) {
+      if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &v2,
+                            vo.identity ? nullptr : vo.old2new.data())) {
         h->err = "row index out of range";
         return FOLP_INVALID_ARGUMENT;
       }
@@ -1159,17 +1251,25 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       // (A[:, slice])': the local columns of the caller's CSC, i.e. n_local rows of full length.
       // Their column indices (= global rows of A) are remapped into the padded rank-major
       // layout of y_full: row i of rank q -> q * m_pad + (i - row_begin[q]).
+      // (the slice is a range of the DEVICE numbering of the variables: its columns are gathered
+      // from the caller's arrays through the renumbering)
       const int64_t c1 = h->col0 + h->n;
-      const int t0 = rp[h->col0], t1 = rp[c1];
+      const int t0 = rp_t[h->col0], t1 = rp_t[c1];
       IVec trp(static_cast<size_t>(h->n) + 1);
-      for (int64_t j = 0; j <= h->n; ++j) trp[j] = rp[h->col0 + j] - t0;
+      for (int64_t j = 0; j <= h->n; ++j) trp[j] = rp_t[h->col0 + j] - t0;
       IVec owner_off(static_cast<size_t>(m) + 1);  // global row -> padded index
       for (int q = 0; q < P; ++q)
         for (int64_t i = h->row_begin[q]; i < h->row_begin[q + 1]; ++i)
           owner_off[i] = static_cast<int>(q * h->m_pad + (i - h->row_begin[q]));
       IVec tci(static_cast<size_t>(t1 - t0));
-      for (int k = t0; k < t1; ++k) tci[k - t0] = owner_off[row_of(k)];  // rows were range-checked above
-      DVec tv(src_val + t0, src_val + t1);
+      DVec tv(static_cast<size_t>(t1 - t0));
+      for (int64_t j = h->col0; j < c1; ++j) {
+        const int src = vo.identity ? rp[j] : vo.src_start[j];
+        for (int k = rp_t[j]; k < rp_t[j + 1]; ++k) {
+          tci[k - t0] = owner_off[row_of(src + (k - rp_t[j]))];  // rows were range-checked above
+          tv[k - t0] = src_val[src + (k - rp_t[j])];
+        }
+      }
       if ((rc = build_matrix(h, &h->At, static_cast<int>(h->n), static_cast<int>(P * h->m_pad), trp, tci, tv)))
         return rc;
       h->nnz = (k1 - k0) + (t1 - t0);
@@ -1192,17 +1292,20 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         h->err = "objective-matrix colptr is not monotone";
         return FOLP_INVALID_ARGUMENT;
       }
+    // rows and columns are variables: both in the device numbering; the entries of a row keep the
+    // order of their ORIGINAL column numbers (the reference's summation order)
+    auto dev_id = [&](int64_t j) { return vo.identity ? static_cast<int>(j) : vo.old2new[j]; };
     for (int64_t k = 0; k < qnnz; ++k) {
       const int64_t r = p->q_rowval[k] - base;
       if (r < 0 || r >= n) { h->err = "objective-matrix row index out of range"; return FOLP_INVALID_ARGUMENT; }
-      qrp[r + 1] += 1;
+      qrp[dev_id(r) + 1] += 1;
     }
     for (int64_t i = 0; i < n; ++i) qrp[i + 1] += qrp[i];
     IVec cursor(qrp.begin(), qrp.end() - 1);
     for (int64_t j = 0; j < n; ++j)
       for (int64_t k = p->q_colptr[j] - base; k < p->q_colptr[j + 1] - base; ++k) {
-        const int pos = cursor[p->q_rowval[k] - base]++;
-        qci[pos] = static_cast<int>(j);
+        const int pos = cursor[dev_id(p->q_rowval[k] - base)]++;
+        qci[pos] = dev_id(j);
         qv[pos] = p->q_nzval[k];
       }
     int rcq;
@@ -1225,6 +1328,17 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
 #endif
   B.grid_vec = h->sm_count * FOLP_VEC_CTAS_PER_SM;
   auto at = [](const double* v, int64_t off) { return v ? v + off : nullptr; };
+  // primal-indexed input: entries [c0, c0 + nl) of the DEVICE numbering, gathered from the caller's
+  std::vector<double> gathered;
+  auto upload_primal = [&](double** dst, const double* src, double fill) -> int {
+    if (!src || vo.identity) return dev_upload(h, dst, at(src, c0), nl, fill);
+    gathered.resize(static_cast<size_t>(nl));
+    for (int64_t j = 0; j < nl; ++j) gathered[j] = src[vo.new2old[c0 + j]];
+    int rc_ = dev_upload(h, dst, gathered.data(), nl, fill);
+    if (rc_) return rc_;
+    TRY(cudaStreamSynchronize(h->stream));  // `gathered` is reused by the next vector
+    return FOLP_OK;
+  };
   int rc;
   if ((rc = dev_alloc(h, &B.st, 1))) return rc;
   for (int k = 0; k < 2; ++k) {
@@ -1259,9 +1373,9 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     // the cooperative trust-region kernel exchanges its scalars through peer memory
     if (!B.p2p || getenv("FOLP_DIST_TR_MULTIKERNEL") != nullptr) h->tr_grid = 0;
   }
-  if ((rc = dev_upload(h, &B.c, at(p->objective_vector, c0), nl, 0.0))) return rc;
-  if ((rc = dev_upload(h, &B.l, at(p->variable_lower_bound, c0), nl, 0.0))) return rc;
-  if ((rc = dev_upload(h, &B.u, at(p->variable_upper_bound, c0), nl, 0.0))) return rc;
+  if ((rc = upload_primal(&B.c, p->objective_vector, 0.0))) return rc;
+  if ((rc = upload_primal(&B.l, p->variable_lower_bound, 0.0))) return rc;
+  if ((rc = upload_primal(&B.u, p->variable_upper_bound, 0.0))) return rc;
   if ((rc = dev_upload(h, &B.b, at(p->right_hand_side, r0), ml, 0.0))) return rc;
   if ((rc = dev_zeros(h, &B.sum_x, na))) return rc;
   if ((rc = dev_zeros(h, &B.sum_y, ma))) return rc;
@@ -1274,19 +1388,16 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   if ((rc = dev_zeros(h, &B.last_y, ma))) return rc;
   if ((rc = dev_zeros(h, &B.last_ax, ma))) return rc;
   if ((rc = dev_zeros(h, &B.last_aty, na))) return rc;
-  if ((rc = dev_upload(h, &B.D, at(p->variable_rescaling, c0), nl, 1.0))) return rc;
+  if ((rc = upload_primal(&B.D, p->variable_rescaling, 1.0))) return rc;
   if ((rc = dev_upload(h, &B.E, at(p->constraint_rescaling, r0), ml, 1.0))) return rc;
-  if ((rc = dev_upload(h, &B.c_orig,
-                       at(p->orig_objective_vector ? p->orig_objective_vector : p->objective_vector, c0),
-                       nl, 0.0)))
+  if ((rc = upload_primal(&B.c_orig, p->orig_objective_vector ? p->orig_objective_vector : p->objective_vector,
+                          0.0)))
     return rc;
-  if ((rc = dev_upload(h, &B.l_orig,
-                       at(p->orig_variable_lower_bound ? p->orig_variable_lower_bound
-                                                       : p->variable_lower_bound, c0), nl, 0.0)))
+  if ((rc = upload_primal(&B.l_orig, p->orig_variable_lower_bound ? p->orig_variable_lower_bound
+                                                                  : p->variable_lower_bound, 0.0)))
     return rc;
-  if ((rc = dev_upload(h, &B.u_orig,
-                       at(p->orig_variable_upper_bound ? p->orig_variable_upper_bound
-                                                       : p->variable_upper_bound, c0), nl, 0.0)))
+  if ((rc = upload_primal(&B.u_orig, p->orig_variable_upper_bound ? p->orig_variable_upper_bound
+                                                                  : p->variable_upper_bound, 0.0)))
     return rc;
   if ((rc = dev_upload(h, &B.b_orig,
                        at(p->orig_right_hand_side ? p->orig_right_hand_side : p->right_hand_side, r0),
@@ -1687,8 +1798,14 @@ static int fetch_cols(folp_handle* h, const double* slice, double* host_out) {
     if ((rc = allgather_cols(h, slice, h->d_cols))) return rc;
     src = h->d_cols;
   }
-  if (host_out)
+  if (host_out && h->new2old.empty()) {
     TRY(cudaMemcpyAsync(host_out, src, sizeof(double) * h->n_glob, cudaMemcpyDeviceToHost, h->stream));
+  } else if (host_out) {  // back to the caller's numbering of the variables
+    h->h_tmp.resize(static_cast<size_t>(h->n_glob));
+    TRY(cudaMemcpyAsync(h->h_tmp.data(), src, sizeof(double) * h->n_glob, cudaMemcpyDeviceToHost, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+    for (int64_t j = 0; j < h->n_glob; ++j) host_out[h->new2old[j]] = h->h_tmp[j];
+  }
   if (h->world > 1 && h->B.p2p && (rc = peer_rendezvous(h))) return rc;
   return FOLP_OK;
 }
@@ -2558,8 +2675,14 @@ extern "C" int folp_debug_set_state(folp_handle* h, const double* x, const doubl
   DevState* s = h->hs;
   Bufs& B = h->B;
   if (x && B.n) {
-    TRY(cudaMemcpyAsync(B.x[s->cur], x + h->col0, sizeof(double) * B.n, cudaMemcpyHostToDevice,
-                        h->stream));
+    const double* xs = x + h->col0;
+    if (!h->new2old.empty()) {  // the caller's numbering -> the device's
+      h->h_tmp.resize(static_cast<size_t>(B.n));
+      for (int j = 0; j < B.n; ++j) h->h_tmp[j] = x[h->new2old[h->col0 + j]];
+      xs = h->h_tmp.data();
+    }
+    TRY(cudaMemcpyAsync(B.x[s->cur], xs, sizeof(double) * B.n, cudaMemcpyHostToDevice, h->stream));
+    if (!h->new2old.empty()) TRY(cudaStreamSynchronize(h->stream));
     if (B.has_q) {
       launch_spmv_plain(h->Q, B.x[s->cur], B.qx[s->cur], B.grid_spmv, h->stream);
       h->launches += 1;
@@ -2595,8 +2718,16 @@ extern "C" int folp_debug_spmv(folp_handle* h, int transpose, const double* in, 
   int rc;
   if (!transpose) {  // in: global n -> out: global m
     double* d_in = h->world > 1 ? h->d_cols : B.tr_t;
-    if (h->n_glob)
-      TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * h->n_glob, cudaMemcpyHostToDevice, h->stream));
+    const double* src = in;
+    if (!h->new2old.empty()) {  // the caller's numbering -> the device's
+      h->h_tmp.resize(static_cast<size_t>(h->n_glob));
+      for (int64_t j = 0; j < h->n_glob; ++j) h->h_tmp[j] = in[h->new2old[j]];
+      src = h->h_tmp.data();
+    }
+    if (h->n_glob) {
+      TRY(cudaMemcpyAsync(d_in, src, sizeof(double) * h->n_glob, cudaMemcpyHostToDevice, h->stream));
+      if (!h->new2old.empty()) TRY(cudaStreamSynchronize(h->stream));
+    }
     launch_spmv_plain(h->A, d_in, B.tr_d, B.grid_spmv, h->stream);
     CHECK_LAUNCH();
     h->launches += 1;
@@ -2840,9 +2971,21 @@ extern "C" int folp_debug_host_problem_spmv(const folp_problem* p, int transpose
   IVec rp(static_cast<size_t>(n) + 1);
   for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - p->index_base) : 0;
   HostMatrices hm;
-  if (!prepare_host_matrices(p, rp, 148 * kSpmvCtasPerSm * kSpmvWarps, &hm)) return FOLP_INVALID_ARGUMENT;
-  return transpose ? emulate_packed_spmv(hm.pk_t, rp, hm.atc, hm.atv, n, x, y, 0, nullptr)
-                   : emulate_packed_spmv(hm.pk_a, hm.rp2, hm.ac, hm.av, m, x, y, 0, nullptr);
+  VarOrder vo;
+  order_variables(n, rp, &vo);
+  if (!prepare_host_matrices(p, rp, vo, 148 * kSpmvCtasPerSm * kSpmvWarps, &hm)) return FOLP_INVALID_ARGUMENT;
+  if (vo.identity)
+    return transpose ? emulate_packed_spmv(hm.pk_t, rp, hm.atc, hm.atv, n, x, y, 0, nullptr)
+                     : emulate_packed_spmv(hm.pk_a, hm.rp2, hm.ac, hm.av, m, x, y, 0, nullptr);
+  // the packed matrices live in the device numbering of the variables: x in / A'x out are renumbered here
+  std::vector<double> tmp(static_cast<size_t>(n));
+  if (transpose) {
+    const int rc = emulate_packed_spmv(hm.pk_t, vo.rp_new, hm.atc, hm.atv, n, x, tmp.data(), 0, nullptr);
+    for (int64_t j = 0; j < n; ++j) y[vo.new2old[j]] = tmp[j];
+    return rc;
+  }
+  for (int64_t j = 0; j < n; ++j) tmp[j] = x[vo.new2old[j]];
+  return emulate_packed_spmv(hm.pk_a, hm.rp2, hm.ac, hm.av, m, tmp.data(), y, 0, nullptr);
 }
 
 extern "C" void* folp_debug_stream(folp_handle* h) {

@@ -137,16 +137,16 @@ def test_host_preparation_rejects_bad_row_index():
 
 
 def test_cost_balanced_static_order_is_a_pure_reordering(monkeypatch):
-    """FOLP_BALANCE_TILES=1 (opt-in): the work items are dealt to the warps by
-    decreasing cost and laid out for the kernel's static striding. Same row sums bit for bit; the
-    busiest warp carries less."""
+    """The cost-balanced static order (default; FOLP_NO_BALANCE_TILES=1 keeps the matrix order): the
+    work items are dealt to the warps by decreasing cost and laid out for the kernel's static
+    striding. Same row sums bit for bit; the busiest warp carries less."""
     for M in (random_sparse_lp(60000, 60000, 10, seed=7).constraint_matrix.T.tocsr(),
               pagerank_lp(20000).constraint_matrix.tocsr(), _ragged(5)):
         x = np.random.default_rng(2).standard_normal(M.shape[1])
+        monkeypatch.setenv("FOLP_NO_BALANCE_TILES", "1")
         y0, s0 = host_packed_spmv(M, x, warps_total=256)
-        monkeypatch.setenv("FOLP_BALANCE_TILES", "1")
+        monkeypatch.delenv("FOLP_NO_BALANCE_TILES")
         y1, s1 = host_packed_spmv(M, x, warps_total=256)
-        monkeypatch.delenv("FOLP_BALANCE_TILES")
         assert np.array_equal(y0, y1)
         assert s1["busiest_warp_rounds"] <= s0["busiest_warp_rounds"]
         assert s1["narrow_rounds"] == s0["narrow_rounds"]
