@@ -253,10 +253,20 @@ struct folp_handle {
 // One cudaMalloc for (nearly) everything a handle owns: ~60 separate allocations cost tens of
 // milliseconds of folp_create and as many cudaFree calls in folp_destroy. dev_alloc carves
 // 256-byte aligned blocks out of the arena and falls back to cudaMalloc when it is absent or full.
+// Single-process multi-GPU: once cudaDeviceEnablePeerAccess is on, every cudaMalloc / cudaFree also
+// maps / unmaps the block on all peers (measured: folp_create_multi 1.65 s for ~60 allocations on 2
+// GPUs against 0.24 s with one process per GPU). Only the exchange region has to be peer-visible:
+// everything else comes from the device's stream-ordered memory pool, which peers do not map.
+static cudaError_t private_malloc(folp_handle* h, void** q, size_t bytes) {
+  if (!h->shared) return cudaMalloc(q, bytes);
+  cudaError_t e = cudaMallocAsync(q, bytes, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  return e;
+}
 static int arena_reserve(folp_handle* h, size_t bytes) {
   if (h->arena || bytes == 0) return FOLP_OK;
   void* q = nullptr;
-  TRY(cudaMalloc(&q, bytes));
+  TRY(private_malloc(h, &q, bytes));
   h->allocs.push_back(q);
   h->arena = static_cast<char*>(q);
   h->arena_cap = bytes;
@@ -273,7 +283,7 @@ static int dev_alloc(folp_handle* h, T** p, size_t count) {
     q = h->arena + h->arena_used;
     h->arena_used += bytes;
   } else {
-    TRY(cudaMalloc(&q, bytes));
+    TRY(private_malloc(h, &q, bytes));
     h->allocs.push_back(q);
   }
   TRY(cudaMemsetAsync(static_cast<char*>(q) + count * sizeof(T), 0, 16 * sizeof(T), h->stream));
@@ -562,7 +572,11 @@ static void free_handle(folp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (auto& kv : h->step_graphs) cudaGraphExecDestroy(kv.second);
-  for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->allocs) {
+    if (h->shared && h->stream) cudaFreeAsync(p, h->stream);  // private_malloc
+    else cudaFree(p);
+  }
+  if (h->shared && h->stream) cudaStreamSynchronize(h->stream);
   if (h->hs) cudaFreeHost(h->hs);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_trs) cudaFreeHost(h->h_trs);
@@ -1242,6 +1256,20 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       h->neq = std::max<int64_t>(0, std::min<int64_t>(p->num_equalities, row1) - h->row0);
       // A_r: local rows, global columns
       const int k0 = rp2[h->row0], k1 = rp2[row1];
+      {  // one allocation for this rank's matrices and vectors (upper bounds; dev_alloc falls back when it is full)
+        const int64_t c1_ = std::min<int64_t>(n, h->col0 + h->n);
+        const int64_t nz_t = rp_t[c1_] - rp_t[h->col0], nz_a = k1 - k0;
+        auto mat_bound = [&](int64_t rows, int64_t nz) {
+          const int64_t tiles = rows / 32 + 2 * (nz / 33) + nz / kChunkNnz + 3 * static_cast<int64_t>(warps_total) + 64;
+          return static_cast<size_t>(4 * (rows + 17) + 12 * (nz + 32) + 32 * tiles + 8 * (rows + 16) +
+                                     8 * (nz / kChunkNnz + 64) + 4 * (rows + 64) + 8 * 256);
+        };
+        const int64_t na_ = std::max(h->n_pad, h->n), ma_ = std::max(h->m_pad, h->m);
+        const size_t vec_bound = static_cast<size_t>(8) * (30 * (na_ + 48) + 24 * (ma_ + 48) + P * (h->n_pad + h->m_pad) +
+                                                           2 * (n + m + 64) + P * std::max(na_, ma_) + 8 * (h->n + h->m + 64)) +
+                                 sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 18);
+        if ((rc = arena_reserve(h, mat_bound(h->m, nz_a) + mat_bound(h->n, nz_t) + vec_bound))) return rc;
+      }
       h->nnz = k1 - k0;
       IVec lrp(static_cast<size_t>(h->m) + 1);
       for (int64_t i = 0; i <= h->m; ++i) lrp[i] = rp2[h->row0 + i] - k0;
