@@ -989,8 +989,10 @@ struct HostMatrices {
   IVec atc, ac, rp2;
   DVec atv, av;
 };
+// at_ready (optional) runs on the second thread as soon as A' is packed (folp_create uploads it from
+// there while this thread is still transposing).
 static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, const VarOrder& vo, int warps_total,
-                                  HostMatrices* out) {
+                                  HostMatrices* out, const std::function<void()>& at_ready = nullptr) {
   const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
   const int base = p->index_base;
   const int64_t* src_row = p->rowval;
@@ -1011,6 +1013,7 @@ static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, const V
     fill_packed(out->pk_t, rp_t, [=](int k) { return static_cast<int>(row_of(k)); }, val_of,
                 out->atc.data(), out->atv.data(), vo.identity ? nullptr : vo.src_start.data());
     t_side = now_sec();
+    if (at_ready) at_ready();
   });
   IVec ci2;
   DVec v2;
@@ -1207,32 +1210,32 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       h->row_begin[1] = m;
       h->n_pad = n; h->m_pad = m;
       h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
+      {  // device memory of the whole handle in one allocation, reserved up front from upper bounds so that
+         // A' can be uploaded while A is still being transposed (dev_alloc falls back to cudaMalloc when full)
+        auto mat_bound = [&](int64_t rows, int64_t nz) {
+          const int64_t tiles = rows / 32 + 2 * (nz / 33) + nz / kChunkNnz + 3 * static_cast<int64_t>(warps_total) + 64;
+          return static_cast<size_t>(4 * (rows + 17) + 12 * (nz + 32) + 32 * tiles + 8 * (rows + 16) +
+                                     8 * (nz / kChunkNnz + 64) + 4 * (rows + 64) + 8 * 256);
+        };
+        const int64_t qnnz = has_q ? p->q_num_nonzeros : 0;
+        const size_t q_bytes = has_q ? mat_bound(n, qnnz) + static_cast<size_t>(5 * 8 * (n + 48)) : 0;
+        const size_t vec_bytes = static_cast<size_t>(8) * (27 * (n + 48) + 21 * (m + 48)) +
+                                 sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 17);
+        if ((rc = arena_reserve(h, mat_bound(n, nnz) + mat_bound(m, nnz) + q_bytes + vec_bytes))) return rc;
+      }
       HostMatrices hm;
-      if (!prepare_host_matrices(p, rp, vo, warps_total, &hm)) {
+      int rc_at = FOLP_OK;
+      const bool ok = prepare_host_matrices(p, rp, vo, warps_total, &hm, [&] {
+        cudaSetDevice(h->device);  // second thread: A' goes to the device while the first one transposes
+        rc_at = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp_t, hm.pk_t, hm.atc, hm.atv);
+      });
+      if (!ok) {
         h->err = "row index out of range";
         return FOLP_INVALID_ARGUMENT;
       }
-      pt.mark("transpose + pack (host)");
-      {  // device memory of the whole handle in one allocation (sizes: upload_matrix + the vectors below)
-        auto mat_bytes = [](int64_t rows, int64_t nz, const PackedMatrix& pk) {
-          return static_cast<size_t>(4 * (rows + 17) + 12 * (nz + 32) + 32 * (pk.tiles.size() + 16) +
-                                     (pk.any_sorted ? 8 * (rows + 16) : 0) + 8 * (pk.nchunks_total + 16) +
-                                     4 * (pk.nlong + 16) + 8 * 256);
-        };
-        const int64_t qnnz = has_q ? p->q_num_nonzeros : 0;
-        const size_t q_bytes = has_q ? static_cast<size_t>(4 * (n + 17) + 12 * (qnnz + 32) + 32 * (n / 8 + qnnz / kChunkNnz + 64) +
-                                                           8 * (n + 16) + 8 * 256 + 5 * 8 * (n + 48))
-                                     : 0;
-        const size_t vec_bytes = static_cast<size_t>(8) * (27 * (n + 48) + 21 * (m + 48)) +
-                                 sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 17);
-        if ((rc = arena_reserve(h, mat_bytes(n, nnz, hm.pk_t) + mat_bytes(m, nnz, hm.pk_a) + q_bytes + vec_bytes)))
-          return rc;
-      }
-      const PackedMatrix &pk_t = hm.pk_t, &pk_a = hm.pk_a;
-      const IVec &atc = hm.atc, &ac = hm.ac, &rp2 = hm.rp2;
-      const DVec &atv = hm.atv, &av = hm.av;
-      if ((rc = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp_t, pk_t, atc, atv))) return rc;
-      if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), rp2, pk_a, ac, av))) return rc;
+      if (rc_at) return rc_at;
+      pt.mark("transpose + pack (host), A' uploaded");
+      if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), hm.rp2, hm.pk_a, hm.ac, hm.av))) return rc;
     } else {
       if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &v2,
                             vo.identity ? nullptr : vo.old2new.data())) {
@@ -1357,15 +1360,16 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   B.grid_vec = h->sm_count * FOLP_VEC_CTAS_PER_SM;
   auto at = [](const double* v, int64_t off) { return v ? v + off : nullptr; };
   // primal-indexed input: entries [c0, c0 + nl) of the DEVICE numbering, gathered from the caller's
-  std::vector<double> gathered;
+  std::vector<std::vector<double>> gathered;  // kept until the stream is synchronised at the end of folp_create
+  gathered.reserve(8);
   auto upload_primal = [&](double** dst, const double* src, double fill) -> int {
     if (!src || vo.identity) return dev_upload(h, dst, at(src, c0), nl, fill);
-    gathered.resize(static_cast<size_t>(nl));
-    for (int64_t j = 0; j < nl; ++j) gathered[j] = src[vo.new2old[c0 + j]];
-    int rc_ = dev_upload(h, dst, gathered.data(), nl, fill);
-    if (rc_) return rc_;
-    TRY(cudaStreamSynchronize(h->stream));  // `gathered` is reused by the next vector
-    return FOLP_OK;
+    gathered.emplace_back(static_cast<size_t>(nl));
+    std::vector<double>& g = gathered.back();
+    parallel_for(0, nl, 1 << 16, [&](int64_t lo, int64_t hi, int) {
+      for (int64_t j = lo; j < hi; ++j) g[j] = src[vo.new2old[c0 + j]];
+    });
+    return dev_upload(h, dst, g.data(), nl, fill);
   };
   int rc;
   if ((rc = dev_alloc(h, &B.st, 1))) return rc;
