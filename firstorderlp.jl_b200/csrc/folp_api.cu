@@ -24,6 +24,7 @@
 
 #include "folp_kernels.cuh"
 #include "folp_nccl.h"
+#include "folp_vmm.h"
 
 using namespace folp;
 
@@ -120,6 +121,7 @@ struct MultiCtx {
   // create-time rendezvous of the ranks
   std::vector<void*> regions;
   std::vector<int> peer_ok;
+  std::vector<uint64_t> words;  // world * kVmmWords: the ranks' contributions to an allgather of the multicast setup
   int bar_count = 0;
   uint64_t bar_gen = 0;
   std::condition_variable cv_bar;
@@ -233,6 +235,7 @@ struct folp_handle {
   // peer-memory exchange region {xbar | y_full | sc_recv | scx | flags} and the peers' mappings
   void* region = nullptr;
   void* peer_region[kMaxWorld] = {};
+  VmmRegion vmm;                    // active: the region is cuMemCreate memory bound to an NVSwitch multicast object (folp_vmm.h)
   unsigned long long xchg_seq = 0;  // evaluation-block scalar exchanges done so far (same on every rank)
 };
 
@@ -568,7 +571,8 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const IV
   return upload_matrix(h, M, rows, cols, rowptr, pk, pc, pv);
 }
 
-static void free_handle(folp_handle* h) {
+// collective: called by every rank thread of a single-process multi-GPU solve at the same time
+static void free_handle(folp_handle* h, bool collective = false) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (auto& kv : h->step_graphs) cudaGraphExecDestroy(kv.second);
@@ -581,10 +585,16 @@ static void free_handle(folp_handle* h) {
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_trs) cudaFreeHost(h->h_trs);
   if (h->h_sc) cudaFreeHost(h->h_sc);
-  for (int r = 0; r < kMaxWorld; ++r)
-    if (h->peer_region[r]) cudaIpcCloseMemHandle(h->peer_region[r]);
+  if (h->vmm.h_own) {
+    if (h->vmm.active) vmm_region_unmap(&h->vmm);
+    if (collective) h->shared->barrier();  // handles are shared by value between the ranks of a process
+    vmm_region_release(&h->vmm);
+  } else {
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (h->peer_region[r]) cudaIpcCloseMemHandle(h->peer_region[r]);
+    if (h->region) cudaFree(h->region);
+  }
   if (h->comm && h->nccl && !h->comm_cached) h->nccl->CommDestroy(h->comm);
-  if (h->region) cudaFree(h->region);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -661,12 +671,75 @@ static void set_peer_pointers(folp_handle* h, int r, void* region) {
   B.flag_peer[r] = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
 }
 
-// Single-process multi-GPU: the ranks are threads of this process; every device enables direct
-// peer access to every other one and the region addresses are swapped through host memory.
-static int setup_peer_exchange_in_process(folp_handle* h) {
+// The exchange region has an address: wire the local pointers into it.
+static void wire_region(folp_handle* h) {
+  Bufs& B = h->B;
+  const int P = h->world;
+  const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
+  double* base = static_cast<double*>(h->region);
+  B.xbar = base;
+  B.y_full = base + fx;
+  B.m_pad = static_cast<int>(h->m_pad);
+  B.sc_recv = base + fx + fy;
+  B.scx = base + fx + fy + static_cast<size_t>(P) * kScBlock;
+  B.hx = base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock;
+  B.flags = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
+}
+
+// The region is bound to an NVSwitch multicast object (folp_vmm.h): adopt its mappings.
+static void adopt_multicast_region(folp_handle* h) {
+  Bufs& B = h->B;
+  const int P = h->world;
+  h->region = h->vmm.own;
+  wire_region(h);
+  for (int r = 0; r < P; ++r) set_peer_pointers(h, r, h->vmm.peer[r]);
+  double* mc = static_cast<double*>(h->vmm.mc);
+  B.xbar_mc = mc;
+  B.yfull_mc = mc + static_cast<size_t>(P) * h->n_pad;
+}
+
+static void read_exchange_switches(folp_handle* h) {
+  Bufs& B = h->B;
+  if (const char* d = getenv("FOLP_DEBUG_FLAGS")) B.dbg = atoi(d);
+  if (getenv("FOLP_BULK_PUSH") != nullptr) B.dbg |= 8;
+  if (B.dbg & 8) B.xbar_mc = B.yfull_mc = nullptr;  // the copy-engine pushes address the peers one by one
+}
+
+// Single-process multi-GPU: the ranks are threads of this process. The region becomes a multicast
+// object when the devices sit behind an NVSwitch that offers it; otherwise every device enables direct
+// peer access to every other one and the addresses of plain allocations are swapped through host memory.
+static int setup_peer_exchange_in_process(folp_handle* h, size_t bytes) {
   MultiCtx* mc = h->shared;
   const int P = h->world;
-  int ok = P <= kMaxWorld ? 1 : 0;
+  // has every rank got this far? (a rank that failed earlier passes these two barriers with peer_ok = 0)
+  mc->peer_ok[h->rank] = P <= kMaxWorld ? 1 : 0;
+  h->shared_rendezvous_done = true;
+  mc->barrier();
+  int ok = 1;
+  for (int r = 0; r < P; ++r) ok = ok && mc->peer_ok[r];
+  mc->barrier();
+  if (!ok) {
+    h->err = "single-process multi-GPU: a rank failed before the exchange was set up (or more than 8 devices)";
+    return FOLP_UNSUPPORTED;
+  }
+  // from here on all ranks are alive and move in lockstep
+  std::vector<int> devs(static_cast<size_t>(P));
+  for (int r = 0; r < P; ++r) devs[r] = mc->sub[r]->device;
+  VmmAllgather gather = [&](const uint64_t* mine, uint64_t* all) {
+    memcpy(&mc->words[static_cast<size_t>(h->rank) * kVmmWords], mine, sizeof(uint64_t) * kVmmWords);
+    mc->barrier();
+    memcpy(all, mc->words.data(), sizeof(uint64_t) * kVmmWords * P);
+    mc->barrier();
+    return true;
+  };
+  const char* why = "";
+  if (vmm_region_create(gather, h->rank, P, h->device, devs.data(), bytes, &h->vmm, &why)) {
+    adopt_multicast_region(h);
+    h->B.p2p = 1;
+    read_exchange_switches(h);
+    return FOLP_OK;
+  }
+  if (getenv("FOLP_TIMING") != nullptr && h->rank == 0) fprintf(stderr, "[folp_create] no multicast region: %s\n", why);
   for (int r = 0; r < P && ok; ++r) {
     const int peer = mc->sub[r]->device;
     if (r == h->rank || peer == h->device) continue;
@@ -676,10 +749,14 @@ static int setup_peer_exchange_in_process(folp_handle* h) {
     if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
     cudaGetLastError();
   }
-  if (cudaStreamSynchronize(h->stream) != cudaSuccess) ok = 0;  // the region is zeroed before any peer can write into it
+  // the region is zeroed before any peer can write into it
+  if (ok && (cudaMalloc(&h->region, bytes) != cudaSuccess || cudaMemsetAsync(h->region, 0, bytes, h->stream) != cudaSuccess ||
+             cudaStreamSynchronize(h->stream) != cudaSuccess)) {
+    cudaGetLastError();
+    ok = 0;
+  }
   mc->regions[h->rank] = h->region;
   mc->peer_ok[h->rank] = ok;
-  h->shared_rendezvous_done = true;
   mc->barrier();
   for (int r = 0; r < P; ++r) ok = ok && mc->peer_ok[r];
   if (!ok) {
@@ -687,18 +764,50 @@ static int setup_peer_exchange_in_process(folp_handle* h) {
     mc->barrier();
     return FOLP_UNSUPPORTED;
   }
+  wire_region(h);
   for (int r = 0; r < P; ++r) set_peer_pointers(h, r, mc->regions[r]);
   h->B.p2p = 1;
-  if (const char* d = getenv("FOLP_DEBUG_FLAGS")) h->B.dbg = atoi(d);
-  if (getenv("FOLP_BULK_PUSH") != nullptr) h->B.dbg |= 8;
+  read_exchange_switches(h);
   mc->barrier();
   return FOLP_OK;
 }
 
-static int setup_peer_exchange(folp_handle* h) {
+// Allocates the exchange region (bytes) and makes it reachable from every rank: multicast object,
+// else CUDA IPC of a plain allocation, else (FOLP_NO_P2P, IPC refused) private with NCCL exchanges.
+static int setup_peer_exchange(folp_handle* h, size_t bytes) {
   Bufs& B = h->B;
   const int P = h->world;
-  if (h->shared) return setup_peer_exchange_in_process(h);
+  if (h->shared) return setup_peer_exchange_in_process(h, bytes);
+  {  // NVSwitch multicast region; its create-time agreement rounds ride on the NCCL communicator
+    uint64_t* boot = nullptr;  // device: [kVmmWords] send | [P * kVmmWords] receive
+    TRY(cudaMalloc(&boot, sizeof(uint64_t) * kVmmWords * (static_cast<size_t>(P) + 1)));
+    std::string gather_err;
+    VmmAllgather gather = [&](const uint64_t* mine, uint64_t* all) {
+      static_assert(sizeof(uint64_t) == sizeof(double), "words travel as doubles (copied, never computed on)");
+      if (cudaMemcpyAsync(boot, mine, sizeof(uint64_t) * kVmmWords, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return false;
+      if (h->nccl->AllGather(boot, boot + kVmmWords, kVmmWords, ncclDouble, h->comm, h->stream) != ncclSuccess) return false;
+      if (cudaMemcpyAsync(all, boot + kVmmWords, sizeof(uint64_t) * kVmmWords * P, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return false;
+      return cudaStreamSynchronize(h->stream) == cudaSuccess;
+    };
+    const char* why = "";
+    const bool up = vmm_region_create(gather, h->rank, P, h->device, nullptr, bytes, &h->vmm, &why);
+    cudaFree(boot);
+    if (up) {
+      adopt_multicast_region(h);
+      B.p2p = 1;
+      read_exchange_switches(h);
+      if (B.dbg & 4) {  // probe: gather from private copies of the exchanged vectors
+        B.xbar_priv = h->d_cols;
+        B.yfull_priv = h->d_rows;
+      }
+      return FOLP_OK;
+    }
+    cudaGetLastError();
+    if (getenv("FOLP_TIMING") != nullptr && h->rank == 0) fprintf(stderr, "[folp_create] no multicast region: %s\n", why);
+  }
+  TRY(cudaMalloc(&h->region, bytes));
+  TRY(cudaMemsetAsync(h->region, 0, bytes, h->stream));
+  wire_region(h);
   static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(int) <= kScBlock * sizeof(double), "handle fits a block");
   struct Msg {
     cudaIpcMemHandle_t handle;
@@ -760,8 +869,7 @@ static int setup_peer_exchange(folp_handle* h) {
   }
   for (int r = 0; r < P; ++r) set_peer_pointers(h, r, r == h->rank ? h->region : h->peer_region[r]);
   B.p2p = 1;
-  if (const char* d = getenv("FOLP_DEBUG_FLAGS")) B.dbg = atoi(d);
-  if (getenv("FOLP_BULK_PUSH") != nullptr) B.dbg |= 8;
+  read_exchange_switches(h);
   if (B.dbg & 4) {  // probe: gather from private copies of the exchanged vectors
     B.xbar_priv = h->d_cols;
     B.yfull_priv = h->d_rows;
@@ -1381,27 +1489,17 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   if (P == 1) {
     if ((rc = dev_zeros(h, &B.xbar, n))) return rc;
   } else {
-    // one allocation, so that one CUDA IPC handle exposes everything a peer touches
+    // one allocation, so that one handle (multicast object / CUDA IPC) exposes everything a peer touches
     const size_t fx = static_cast<size_t>(P) * h->n_pad, fy = static_cast<size_t>(P) * h->m_pad;
     const size_t region_doubles = fx + fy + 5 * static_cast<size_t>(P) * kScBlock +
                                   kNumFlagKinds * kMaxWorld + 16;
-    TRY(cudaMalloc(&h->region, region_doubles * sizeof(double)));
-    TRY(cudaMemsetAsync(h->region, 0, region_doubles * sizeof(double), h->stream));
-    double* base = static_cast<double*>(h->region);
-    B.xbar = base;
-    B.y_full = base + fx;
-    B.m_pad = static_cast<int>(h->m_pad);
-    B.sc_recv = base + fx + fy;
-    B.scx = base + fx + fy + static_cast<size_t>(P) * kScBlock;
-    B.hx = base + fx + fy + 3 * static_cast<size_t>(P) * kScBlock;
-    B.flags = reinterpret_cast<unsigned long long*>(base + fx + fy + 5 * static_cast<size_t>(P) * kScBlock);
     if ((rc = dev_alloc(h, &B.dseq, 2))) return rc;
     TRY(cudaMemsetAsync(B.dseq, 0, 2 * sizeof(unsigned long long), h->stream));
     if ((rc = dev_zeros(h, &B.col_tmp, na))) return rc;
     if ((rc = dev_zeros(h, &B.sc_send, kScBlock))) return rc;
     if ((rc = dev_zeros(h, &h->d_rows, fy))) return rc;
     if ((rc = dev_zeros(h, &h->d_cols, fx))) return rc;
-    if ((rc = setup_peer_exchange(h))) return rc;
+    if ((rc = setup_peer_exchange(h, region_doubles * sizeof(double)))) return rc;
     // the cooperative trust-region kernel exchanges its scalars through peer memory
     if (!B.p2p || getenv("FOLP_DIST_TR_MULTIKERNEL") != nullptr) h->tr_grid = 0;
   }
@@ -1554,7 +1652,7 @@ static void destroy_multi(folp_handle* w) {
   if (!mc) return;
   if (!mc->workers.empty()) {
     mc->call([mc](int r) {
-      free_handle(mc->sub[r]);
+      free_handle(mc->sub[r], /*collective=*/true);
       mc->sub[r] = nullptr;
       return 0;
     });
@@ -1565,6 +1663,8 @@ static void destroy_multi(folp_handle* w) {
     }
     for (auto& t : mc->workers) t.join();
   } else {
+    for (folp_handle* q : mc->sub)
+      if (q && q->vmm.active) vmm_region_unmap(&q->vmm);
     for (folp_handle* q : mc->sub) free_handle(q);
   }
   delete mc;
@@ -1602,6 +1702,7 @@ extern "C" int folp_create_multi(const folp_problem* problem, const folp_params*
   mc->rcs.assign(static_cast<size_t>(n_gpus), 0);
   mc->regions.assign(static_cast<size_t>(n_gpus), nullptr);
   mc->peer_ok.assign(static_cast<size_t>(n_gpus), 0);
+  mc->words.assign(static_cast<size_t>(n_gpus) * kVmmWords, 0);
   for (int r = 0; r < n_gpus; ++r) {
     folp_handle* q = new folp_handle();
     q->shared = mc;
@@ -3043,7 +3144,7 @@ extern "C" int folp_counters(folp_handle* h, int64_t* kernel_launches,
 extern "C" int folp_exchange_mode(folp_handle* h) {
   if (!h) return -1;
   if (h->multi) h = h->multi->sub[0];
-  return h->world == 1 ? 0 : (h->B.p2p ? 2 : 1);
+  return h->world == 1 ? 0 : (h->B.p2p ? (h->B.xbar_mc ? 3 : 2) : 1);
 }
 
 extern "C" int folp_shard_info(folp_handle* h, int64_t* row_begin, int64_t* row_end,

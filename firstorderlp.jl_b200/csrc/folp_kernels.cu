@@ -199,6 +199,11 @@ __device__ __forceinline__ double2 k1_ld(const double2* p) {
   return *p;
 #endif
 }
+// One store into the NVSwitch multicast range: the switch replicates it into every rank's region
+// (PTX requires the multimem form on multicast addresses; SASS is a plain STG to the multicast mapping).
+__device__ __forceinline__ void mc_store(double* p, double v) {
+  asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 // cta_first: first PAIR of elements of this CTA (blockIdx.x * blockDim.x); the CTA's threads take
 // consecutive pairs, so a trip of the CTA covers one contiguous tile of 2 * blockDim.x elements.
 // stage (DIST): 2 * blockDim.x double2 of shared memory. With peer memory the tile of xbar is staged
@@ -278,9 +283,14 @@ __device__ __forceinline__ double primal_range(const Bufs& B, const DevState& s,
         bulk_commit();
       }
     } else if (push && act) {  // posted NVLink stores from every thread
+      if (B.xbar_mc != nullptr) {  // one store each, replicated inside the switch
+        mc_store(B.xbar_mc + B.xbar_off + 2 * j, xb.x);
+        mc_store(B.xbar_mc + B.xbar_off + 2 * j + 1, xb.y);
+      } else {
 #pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r)
-        if (r < B.world && r != B.rank) reinterpret_cast<double2*>(B.xbar_peer[r] + B.xbar_off)[j] = xb;
+        for (int r = 0; r < kMaxWorld; ++r)
+          if (r < B.world && r != B.rank) reinterpret_cast<double2*>(B.xbar_peer[r] + B.xbar_off)[j] = xb;
+      }
     }
   }
   if (bulk) {  // everything this CTA handed to the copy engine has been written
@@ -297,9 +307,13 @@ __device__ __forceinline__ double primal_range(const Bufs& B, const DevState& s,
     if (k.do_primal) xn[j] = xp;
     B.xbar[B.xbar_off + j] = xb;
     if (DIST && B.p2p) {
+      if (B.xbar_mc != nullptr) {
+        mc_store(B.xbar_mc + B.xbar_off + j, xb);
+      } else {
 #pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r)
-        if (r < B.world && r != B.rank) B.xbar_peer[r][B.xbar_off + j] = xb;
+        for (int r = 0; r < kMaxWorld; ++r)
+          if (r < B.world && r != B.rank) B.xbar_peer[r][B.xbar_off + j] = xb;
+      }
     }
     acc += d * d;
   }
@@ -492,9 +506,13 @@ struct EpiDualT {
       if (g_bulk) {
         stage[((threadIdx.x >> 5) * 2 + (g_item & 1)) * 32 + (i - g_row0)] = yp;
       } else if (B.p2p && !(B.dbg & 1)) {
+        if (B.yfull_mc != nullptr) {
+          mc_store(B.yfull_mc + at, yp);
+        } else {
 #pragma unroll
-        for (int r = 0; r < kMaxWorld; ++r)
-          if (r < B.world && r != B.rank) B.yfull_peer[r][at] = yp;
+          for (int r = 0; r < kMaxWorld; ++r)
+            if (r < B.world && r != B.rank) B.yfull_peer[r][at] = yp;
+        }
       }
     }
     const double d = yp - yv;
@@ -2381,9 +2399,13 @@ __global__ void __launch_bounds__(kVecThreads) k_push_vec(Bufs B, const double* 
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
     const double v = src[i];
+    if (B.xbar_mc != nullptr) {
+      mc_store((which == 0 ? B.xbar_mc : B.yfull_mc) + off + i, v);
+    } else {
 #pragma unroll
-    for (int r = 0; r < kMaxWorld; ++r)
-      if (r < B.world) (which == 0 ? B.xbar_peer[r] : B.yfull_peer[r])[off + i] = v;
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < B.world) (which == 0 ? B.xbar_peer[r] : B.yfull_peer[r])[off + i] = v;
+    }
   }
   if (last_block_arrive_sys(B.counters + 7) && threadIdx.x == 0) {
     p2p_signal(B, 4, seq);

@@ -55,6 +55,10 @@ struct Bufs {
   const double* yfull_priv = nullptr;  // when set: K3 gathers from this private copy of y_full
   double* xbar_peer[kMaxWorld] = {};
   double* yfull_peer[kMaxWorld] = {};
+  // NVSwitch multicast views of xbar / y_full (folp_vmm.h; nullptr = off): ONE multimem.st lands in every
+  // rank's copy, this rank's included, instead of world-1 unicast stores
+  double* xbar_mc = nullptr;
+  double* yfull_mc = nullptr;
   double* sc_peer[kMaxWorld] = {};
   unsigned long long* flag_peer[kMaxWorld] = {};
   unsigned long long* flags = nullptr;  // local flags [kNumFlagKinds][kMaxWorld]: kind k, source rank r

@@ -349,7 +349,7 @@ class Solver:
         self._check(lib().folp_shard_info(self._h, *[C.byref(x) for x in v]))
         d = dict(zip(("row_begin", "row_end", "col_begin", "col_end", "local_nonzeros"),
                      (x.value for x in v)))
-        d["exchange"] = ("none", "nccl", "peer")[lib().folp_exchange_mode(self._h)]
+        d["exchange"] = ("none", "nccl", "peer", "multicast")[lib().folp_exchange_mode(self._h)]
         return d
 
     def stream(self) -> int:

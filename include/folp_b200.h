@@ -263,7 +263,9 @@ int folp_partition(int64_t num_constraints, int64_t num_variables, int64_t num_n
 
 /* How take_step exchanges data between ranks: 0 = single GPU (none), 1 = NCCL
  * collectives, 2 = peer memory (CUDA IPC over NVLink: K1 pushes its slice of
- * xbar, K2 its rows of y+ into every rank's copy; no NCCL call per attempt). */
+ * xbar, K2 its rows of y+ into every rank's copy; no NCCL call per attempt),
+ * 3 = peer memory bound to an NVSwitch multicast object (NVLS): one multimem.st
+ * per element lands in every rank's copy (FOLP_NO_MULTICAST=1 switches it off). */
 int folp_exchange_mode(folp_handle* h);
 
 /* What this rank holds: rows [row_begin,row_end), primal slice [col_begin,col_end). */

@@ -34,7 +34,11 @@ def parity_checks(check, world, rank):
     rb, cb = folp_b200.lib.partition(problem.constraint_matrix, world)
     assert (info["row_begin"], info["row_end"]) == (rb[rank], rb[rank + 1]), (info, rb)
     assert (info["col_begin"], info["col_end"]) == (cb[rank], cb[rank + 1]), (info, cb)
-    assert info["exchange"] == "peer", info
+    # peer memory; behind an NVSwitch that offers it, bound to a multicast object (FOLP_EXPECT_EXCHANGE pins one)
+    assert info["exchange"] in ("peer", "multicast"), info
+    assert info["exchange"] == os.environ.get("FOLP_EXPECT_EXCHANGE", info["exchange"]), info
+    if rank == 0:
+        print(f"[x{world}] exchange mode: {info['exchange']}", flush=True)
     o.close(); g.close()
 
     for i, make in enumerate([lambda: random_sparse_lp(3000, 2500, 8, seed=5), T.netlib_shaped_lp,
