@@ -376,11 +376,15 @@ def bench_gpu(args):
             _barrier(world)
             t0l = time.perf_counter()
             s3 = Solver(holder, fparams)
+            t1l = time.perf_counter()
             _, _, _, it3, _ = s3.solve(max_evals=1)
+            t2l = time.perf_counter()
             s3.close()
             torch.cuda.synchronize()
-            t_long = _max_over_ranks(time.perf_counter() - t0l, world)
-            long_solve = {"iterations": it3, "seconds": t_long, "value": it3 / t_long}
+            t3l = time.perf_counter()
+            t_long = _max_over_ranks(t3l - t0l, world)
+            long_solve = {"iterations": it3, "seconds": t_long, "value": it3 / t_long,
+                          "seconds_create_solve_destroy": [t1l - t0l, t2l - t1l, t3l - t2l]}
         e2e = {"value": it2 / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
                "long_solve": long_solve,
                "d2h_bytes_per_step": d2h, "iterations": it2, "seconds": t_e2e,

@@ -38,6 +38,21 @@ thread_local std::string g_create_error;
 std::mutex g_comm_mutex;
 std::map<std::tuple<int, int, int>, ncclComm_t> g_comm_cache;
 
+// Multicast exchange regions outlive handles for the same reason: creating the multicast object, adding the
+// devices and binding memory programs the NVSwitch and costs 40-110 ms per folp_create (2 GPUs, measured), more
+// than the rest of a small handle's set-up. One-process-per-GPU mode only; a later handle of the same
+// (world, rank, device) whose region fits reuses the mapping after zero-filling it (the ranks agree on the
+// entry by its creation number: all ranks create their handles in the same order). FOLP_NO_REGION_CACHE=1
+// disables it. Entries live until the process exits.
+struct VmmCacheEntry {
+  VmmRegion r;
+  uint64_t id = 0;
+  bool busy = false;
+};
+std::mutex g_vmm_mutex;
+std::vector<VmmCacheEntry> g_vmm_cache;
+uint64_t g_vmm_next_id = 1;
+
 double now_sec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -236,6 +251,7 @@ struct folp_handle {
   void* region = nullptr;
   void* peer_region[kMaxWorld] = {};
   VmmRegion vmm;                    // active: the region is cuMemCreate memory bound to an NVSwitch multicast object (folp_vmm.h)
+  uint64_t vmm_cache_id = 0;        // != 0: the region belongs to the process-wide cache (g_vmm_cache)
   unsigned long long xchg_seq = 0;  // evaluation-block scalar exchanges done so far (same on every rank)
 };
 
@@ -585,7 +601,11 @@ static void free_handle(folp_handle* h, bool collective = false) {
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_trs) cudaFreeHost(h->h_trs);
   if (h->h_sc) cudaFreeHost(h->h_sc);
-  if (h->vmm.h_own) {
+  if (h->vmm_cache_id) {  // back to the cache, mapped as it is
+    std::lock_guard<std::mutex> lock(g_vmm_mutex);
+    for (VmmCacheEntry& e : g_vmm_cache)
+      if (e.id == h->vmm_cache_id) e.busy = false;
+  } else if (h->vmm.h_own) {
     if (h->vmm.active) vmm_region_unmap(&h->vmm);
     if (collective) h->shared->barrier();  // handles are shared by value between the ranks of a process
     vmm_region_release(&h->vmm);
@@ -790,7 +810,61 @@ static int setup_peer_exchange(folp_handle* h, size_t bytes) {
       return cudaStreamSynchronize(h->stream) == cudaSuccess;
     };
     const char* why = "";
-    const bool up = vmm_region_create(gather, h->rank, P, h->device, nullptr, bytes, &h->vmm, &why);
+    bool up = false;
+    const bool use_cache = getenv("FOLP_NO_REGION_CACHE") == nullptr;
+    {  // a cached region of an earlier handle, if every rank holds the same one
+      uint64_t mine[kVmmWords] = {0, 0, 0, 0};
+      std::vector<uint64_t> all(static_cast<size_t>(P) * kVmmWords, 0);
+      if (use_cache && getenv("FOLP_NO_MULTICAST") == nullptr && getenv("FOLP_NO_P2P") == nullptr) {
+        const char* force = getenv("FOLP_MULTICAST");
+        std::lock_guard<std::mutex> lock(g_vmm_mutex);
+        if (force ? atoi(force) != 0 : P >= 4)  // the default of vmm_region_create
+          for (VmmCacheEntry& e : g_vmm_cache)
+            if (!e.busy && e.r.world == P && e.r.rank == h->rank && e.r.device == h->device && e.r.size >= bytes) {
+              mine[0] = e.id;
+              mine[1] = e.r.size;
+              break;
+            }
+      }
+      if (!gather(mine, all.data())) {
+        cudaFree(boot);
+        h->err = "exchange of the ranks at create time failed";
+        return FOLP_NCCL_ERROR;
+      }
+      bool same = mine[0] != 0;
+      for (int r = 0; r < P; ++r) same = same && all[static_cast<size_t>(r) * kVmmWords] == mine[0] && all[static_cast<size_t>(r) * kVmmWords + 1] == mine[1];
+      if (same) {
+        {
+          std::lock_guard<std::mutex> lock(g_vmm_mutex);
+          for (VmmCacheEntry& e : g_vmm_cache)
+            if (e.id == mine[0]) { e.busy = true; h->vmm = e.r; }
+        }
+        h->vmm_cache_id = mine[0];
+        // zero-filled before any rank of the new handle can push into it
+        const bool zeroed = cudaMemsetAsync(h->vmm.own, 0, bytes, h->stream) == cudaSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess;
+        mine[0] = zeroed ? 1 : 0;
+        bool ok = gather(mine, all.data());
+        for (int r = 0; r < P; ++r) ok = ok && all[static_cast<size_t>(r) * kVmmWords] == 1;
+        if (!ok) {
+          cudaFree(boot);
+          h->err = "zero-filling the cached exchange region failed";
+          return FOLP_CUDA_ERROR;
+        }
+        up = true;
+      }
+    }
+    if (!up) {
+      up = vmm_region_create(gather, h->rank, P, h->device, nullptr, bytes, &h->vmm, &why);
+      if (up && use_cache) {
+        std::lock_guard<std::mutex> lock(g_vmm_mutex);
+        VmmCacheEntry e;
+        e.r = h->vmm;
+        e.id = g_vmm_next_id++;
+        e.busy = true;
+        g_vmm_cache.push_back(e);
+        h->vmm_cache_id = e.id;
+      }
+    }
     cudaFree(boot);
     if (up) {
       adopt_multicast_region(h);
