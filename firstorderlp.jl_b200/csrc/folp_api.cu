@@ -113,6 +113,103 @@ struct NoInit {
 };
 using IVec = std::vector<int, NoInit<int>>;
 using DVec = std::vector<double, NoInit<double>>;
+
+// ---------------------------------------------------------------------------
+// Process-wide PINNED host scratch for folp_create on one GPU. A create of the 1e6 x 1e6 x 1e7 problem writes
+// ~620 MB of host scratch (transposition buckets, the unpacked CSR of A, both packed matrices, the renumbered
+// vectors): as fresh heap pages that is ~150 K page faults per call, and the uploads leave pageable memory
+// through the driver's staging at 6-8 GB/s. The scratch is therefore kept between creates, pinned
+// (cudaHostAlloc, portable): no faults, and every upload is an asynchronous DMA that overlaps the packing.
+// The FIRST create of a process that wants it runs on ordinary vectors and, when it is over, starts a
+// background thread that pins a pool of the wanted size (pinning 600 MB takes ~0.2 s; started during the
+// create it made that create 0.2 s slower); later creates lease it if it is free and large enough. FOLP_NO_HOST_POOL=1 switches it off, FOLP_HOST_POOL_MB caps it (default 1536).
+// ---------------------------------------------------------------------------
+struct HostPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  char* base = nullptr;
+  size_t cap = 0;
+  bool busy = false, growing = false;
+  std::thread grower;
+  ~HostPool() {  // process exit: a running cudaHostAlloc finishes (or fails with "unloading") before the statics go
+    if (grower.joinable()) grower.join();
+  }
+};
+HostPool g_host_pool;
+
+// Bump allocator over a lease of the pool (64-byte aligned blocks; nullptr when there is no lease or no room).
+struct HostCarver {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  template <class T>
+  T* take(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 63) / 64 * 64;
+    if (!base || used + bytes > cap) return nullptr;
+    T* q = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return q;
+  }
+};
+
+// Leases the pool for one create (RAII). want = bytes this create would carve.
+struct HostPoolLease {
+  HostCarver carver;
+  bool held = false;
+  void acquire(size_t want, int device) {
+    if (getenv("FOLP_NO_HOST_POOL") != nullptr || want < (static_cast<size_t>(32) << 20)) return;
+    size_t limit = static_cast<size_t>(1536) << 20;
+    if (const char* e = getenv("FOLP_HOST_POOL_MB")) limit = static_cast<size_t>(atoll(e)) << 20;
+    HostPool& P = g_host_pool;
+    std::lock_guard<std::mutex> lock(P.mu);
+    if (!P.busy && P.base && P.cap >= want) {
+      P.busy = true;
+      held = true;
+      carver.base = P.base;
+      carver.cap = P.cap;
+      return;
+    }
+    if (P.growing || P.busy || want > limit || P.cap >= want) return;
+    P.growing = true;
+    grow_bytes = std::min(limit, want + want / 8);  // pinned once this create is over (destructor)
+    grow_device = device;
+  }
+  size_t grow_bytes = 0;
+  int grow_device = 0;
+  void start_growth() {
+    HostPool& P = g_host_pool;
+    std::lock_guard<std::mutex> lock(P.mu);
+    if (P.grower.joinable()) P.grower.join();  // a finished earlier growth
+    const size_t bytes = grow_bytes;
+    const int device = grow_device;
+    P.grower = std::thread([bytes, device] {
+      HostPool& Q = g_host_pool;
+      void* q = nullptr;
+      const bool ok = cudaSetDevice(device) == cudaSuccess && cudaHostAlloc(&q, bytes, cudaHostAllocPortable) == cudaSuccess;
+      void* old = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(Q.mu);
+        Q.cv.wait(lk, [&] { return !Q.busy; });
+        if (ok) {
+          old = Q.base;
+          Q.base = static_cast<char*>(q);
+          Q.cap = bytes;
+        }
+        Q.growing = false;
+      }
+      if (old) cudaFreeHost(old);
+    });
+  }
+  ~HostPoolLease() {
+    if (grow_bytes) start_growth();  // in the background, while the caller goes on to solve
+    if (!held) return;
+    HostPool& P = g_host_pool;
+    {
+      std::lock_guard<std::mutex> lock(P.mu);
+      P.busy = false;
+    }
+    P.cv.notify_all();
+  }
+};
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -529,8 +626,10 @@ static void fill_packed(const PackedMatrix& pk, const IVec& rowptr, GetCol col, 
 }
 
 // Uploads a packed matrix.
+// sync = false: the host arrays outlive the copies (pinned scratch leased for the whole create, which ends
+// with a synchronisation of the stream)
 static int upload_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const IVec& rowptr,
-                         const PackedMatrix& pk, const IVec& colidx, const DVec& vals) {
+                         const PackedMatrix& pk, const int* colidx, const double* vals, bool sync = true) {
   M->rows = rows;
   M->cols = cols;
   M->nnz = rowptr[rows];
@@ -563,15 +662,16 @@ static int upload_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const I
   TRY(cudaMemcpyAsync(M->rowptr, rowptr.data(), (static_cast<size_t>(rows) + 1) * sizeof(int),
                       cudaMemcpyHostToDevice, h->stream));
   if (M->nnz) {
-    TRY(cudaMemcpyAsync(M->colidx, colidx.data(), static_cast<size_t>(M->nnz) * sizeof(int),
+    TRY(cudaMemcpyAsync(M->colidx, colidx, static_cast<size_t>(M->nnz) * sizeof(int),
                         cudaMemcpyHostToDevice, h->stream));
-    TRY(cudaMemcpyAsync(M->vals, vals.data(), static_cast<size_t>(M->nnz) * sizeof(double),
+    TRY(cudaMemcpyAsync(M->vals, vals, static_cast<size_t>(M->nnz) * sizeof(double),
                         cudaMemcpyHostToDevice, h->stream));
   }
   if (!tiles.empty())
     TRY(cudaMemcpyAsync(M->tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice,
                         h->stream));
-  TRY(cudaStreamSynchronize(h->stream));  // host vectors die with the caller's scope
+  // rowptr, tiles and slot_row_len are pageable: those copies have left the host when the calls return
+  if (sync) TRY(cudaStreamSynchronize(h->stream));  // host vectors die with the caller's scope
   return FOLP_OK;
 }
 
@@ -584,7 +684,7 @@ static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const IV
   DVec pv(vals.size());
   fill_packed(pk, rowptr, [&](int k) { return colidx[k]; }, [&](int k) { return vals[k]; }, pc.data(),
               pv.data());
-  return upload_matrix(h, M, rows, cols, rowptr, pk, pc, pv);
+  return upload_matrix(h, M, rows, cols, rowptr, pk, pc.data(), pv.data());
 }
 
 // collective: called by every rank thread of a single-process multi-GPU solve at the same time
@@ -597,10 +697,7 @@ static void free_handle(folp_handle* h, bool collective = false) {
     else cudaFree(p);
   }
   if (h->shared && h->stream) cudaStreamSynchronize(h->stream);
-  if (h->hs) cudaFreeHost(h->hs);
-  if (h->h_red) cudaFreeHost(h->h_red);
-  if (h->h_trs) cudaFreeHost(h->h_trs);
-  if (h->h_sc) cudaFreeHost(h->h_sc);
+  if (h->hs) cudaFreeHost(h->hs);  // one block: hs | h_red | h_trs | h_sc
   if (h->vmm_cache_id) {  // back to the cache, mapped as it is
     std::lock_guard<std::mutex> lock(g_vmm_mutex);
     for (VmmCacheEntry& e : g_vmm_cache)
@@ -969,13 +1066,22 @@ static int setup_peer_exchange(folp_handle* h, size_t bytes) {
 template <class RowOf, class ValOf>
 static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, RowOf row_of,
                              ValOf val_of, IVec* rp2_out, IVec* ci2_out, DVec* v2_out,
-                             const int* col_id = nullptr) {
+                             const int* col_id = nullptr, HostCarver* carver = nullptr, int** ci_ext = nullptr,
+                             double** v_ext = nullptr) {
+  // carver + ci_ext / v_ext: column indices and values go to carved (pinned, already faulted-in) memory and
+  // are returned through the pointers; *ci2_out / *v2_out stay empty then
   IVec& rp2 = *rp2_out;
-  IVec& ci2 = *ci2_out;
-  DVec& v2 = *v2_out;
   rp2.resize(static_cast<size_t>(m) + 1);
-  ci2.resize(static_cast<size_t>(nnz));
-  v2.resize(static_cast<size_t>(nnz));
+  int* ci2 = carver && ci_ext ? carver->take<int>(static_cast<size_t>(nnz)) : nullptr;
+  double* v2 = carver && v_ext ? carver->take<double>(static_cast<size_t>(nnz)) : nullptr;
+  if (!ci2 || !v2) {
+    ci2_out->resize(static_cast<size_t>(nnz));
+    v2_out->resize(static_cast<size_t>(nnz));
+    ci2 = ci2_out->data();
+    v2 = v2_out->data();
+  }
+  if (ci_ext) *ci_ext = ci2;
+  if (v_ext) *v_ext = v2;
   if (m == 0) { rp2[0] = 0; return nnz == 0; }
   unsigned hw = std::thread::hardware_concurrency();
   const int T = static_cast<int>(std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, kMaxHostThreadsU),
@@ -996,7 +1102,12 @@ static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, 
   }
   const int64_t NB = ((m - 1) >> S) + 1;
   struct Entry { int row, col; double val; };
-  std::vector<Entry, NoInit<Entry>> buf(static_cast<size_t>(nnz));
+  std::vector<Entry, NoInit<Entry>> buf_own;
+  Entry* buf = carver ? carver->take<Entry>(static_cast<size_t>(nnz)) : nullptr;
+  if (!buf) {
+    buf_own.resize(static_cast<size_t>(nnz));
+    buf = buf_own.data();
+  }
   std::vector<int64_t> cnt(static_cast<size_t>(NB) * T, 0);  // [b * T + t]
   std::atomic<int> bad{0};
   std::vector<std::thread> th;
@@ -1123,29 +1234,36 @@ static void order_variables(int64_t n, const IVec& rp, VarOrder* vo) {
   if (const char* w = getenv("FOLP_VAR_SORT_WINDOW")) window = std::max<int64_t>(64, atoll(w) / 32 * 32);
   vo->new2old.resize(static_cast<size_t>(n));
   constexpr int kCap = 2 * kNarrowMax;  // longer columns are warp-per-row items anyway: one bucket
-  bool changed = false;
-  for (int64_t w0 = 0; w0 < n; w0 += window) {
-    const int64_t w1 = std::min<int64_t>(n, w0 + window);
-    int start[kCap + 2] = {0};
-    auto bucket = [&](int64_t j) { return kCap - std::min<int>(kCap, rp[j + 1] - rp[j]); };  // decreasing length
-    for (int64_t j = w0; j < w1; ++j) start[bucket(j) + 1] += 1;
-    for (int b = 0; b <= kCap; ++b) start[b + 1] += start[b];
-    // The groups of a sorted window run from the longest rows to the shortest, and k_spmv hands work
-    // item i to warp i % warps_total: with a window of 64 groups and 4736 warps a warp would meet the
-    // SAME rank of every window it visits -- always the longest group, or always the shortest
-    // (measured: A'*y 79 us instead of 64). The order of the window's full groups is therefore rotated
-    // by a per-window pseudo-random amount, so that every warp meets all ranks.
-    const int64_t full = (w1 - w0) / 32;  // groups of exactly 32 variables; a shorter tail stays last
-    const int64_t rot = full > 1 ? static_cast<int64_t>((static_cast<uint64_t>(w0 / window) * 2654435761ull >> 7) % full) : 0;
-    for (int64_t j = w0; j < w1; ++j) {
-      int64_t at = start[bucket(j)]++;  // rank inside the window
-      if (at < full * 32) at = ((at / 32 + rot) % full) * 32 + at % 32;
-      at += w0;
-      vo->new2old[at] = static_cast<int>(j);
-      changed = changed || at != j;
+  std::atomic<bool> changed{false};
+  const int64_t nwin = (n + window - 1) / window;
+  // windows are independent: spread over the host threads (the result does not depend on their number)
+  parallel_for(0, nwin, 64, [&](int64_t wlo, int64_t whi, int) {
+    bool any = false;
+    for (int64_t wi = wlo; wi < whi; ++wi) {
+      const int64_t w0 = wi * window;
+      const int64_t w1 = std::min<int64_t>(n, w0 + window);
+      int start[kCap + 2] = {0};
+      auto bucket = [&](int64_t j) { return kCap - std::min<int>(kCap, rp[j + 1] - rp[j]); };  // decreasing length
+      for (int64_t j = w0; j < w1; ++j) start[bucket(j) + 1] += 1;
+      for (int b = 0; b <= kCap; ++b) start[b + 1] += start[b];
+      // The groups of a sorted window run from the longest rows to the shortest, and k_spmv hands work
+      // item i to warp i % warps_total: with a window of 64 groups and 4736 warps a warp would meet the
+      // SAME rank of every window it visits -- always the longest group, or always the shortest
+      // (measured: A'*y 79 us instead of 64). The order of the window's full groups is therefore rotated
+      // by a per-window pseudo-random amount, so that every warp meets all ranks.
+      const int64_t full = (w1 - w0) / 32;  // groups of exactly 32 variables; a shorter tail stays last
+      const int64_t rot = full > 1 ? static_cast<int64_t>((static_cast<uint64_t>(w0 / window) * 2654435761ull >> 7) % full) : 0;
+      for (int64_t j = w0; j < w1; ++j) {
+        int64_t at = start[bucket(j)]++;  // rank inside the window
+        if (at < full * 32) at = ((at / 32 + rot) % full) * 32 + at % 32;
+        at += w0;
+        vo->new2old[at] = static_cast<int>(j);
+        any = any || at != j;
+      }
     }
-  }
-  if (!changed) {
+    if (any) changed.store(true, std::memory_order_relaxed);
+  });
+  if (!changed.load()) {
     vo->new2old.clear();
     return;
   }
@@ -1154,12 +1272,15 @@ static void order_variables(int64_t n, const IVec& rp, VarOrder* vo) {
   vo->rp_new.resize(static_cast<size_t>(n) + 1);
   vo->src_start.resize(static_cast<size_t>(n) + 1);
   vo->rp_new[0] = 0;
-  for (int64_t j = 0; j < n; ++j) {
-    const int o = vo->new2old[j];
-    vo->old2new[o] = static_cast<int>(j);
-    vo->rp_new[j + 1] = vo->rp_new[j] + (rp[o + 1] - rp[o]);
-    vo->src_start[j] = rp[o];
-  }
+  parallel_for(0, n, 1 << 15, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t j = lo; j < hi; ++j) {
+      const int o = vo->new2old[j];
+      vo->old2new[o] = static_cast<int>(j);
+      vo->rp_new[j + 1] = rp[o + 1] - rp[o];  // lengths; summed below
+      vo->src_start[j] = rp[o];
+    }
+  });
+  for (int64_t j = 0; j < n; ++j) vo->rp_new[j + 1] += vo->rp_new[j];
   vo->src_start[n] = 0;
 }
 
@@ -1168,23 +1289,42 @@ static void order_variables(int64_t n, const IVec& rp, VarOrder* vo) {
 // CSR of A and packs that. No CUDA call. False if a row index is out of range.
 struct HostMatrices {
   PackedMatrix pk_t, pk_a;
-  IVec atc, ac, rp2;
-  DVec atv, av;
+  IVec rp2;
+  // packed column indices / values of A' and A: carved from the pinned scratch (pooled) or owned
+  int *atc = nullptr, *ac = nullptr;
+  double *atv = nullptr, *av = nullptr;
+  bool pooled = false;
+  IVec own_atc, own_ac;
+  DVec own_atv, own_av;
 };
 // at_ready (optional) runs on the second thread as soon as A' is packed (folp_create uploads it from
 // there while this thread is still transposing).
 static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, const VarOrder& vo, int warps_total,
-                                  HostMatrices* out, const std::function<void()>& at_ready = nullptr) {
+                                  HostMatrices* out, const std::function<void()>& at_ready = nullptr,
+                                  HostCarver* carver = nullptr) {
   const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
   const int base = p->index_base;
   const int64_t* src_row = p->rowval;
   const double* src_val = p->nzval;
   auto row_of = [=](int64_t k) { return src_row[k] - base; };  // may be out of range until checked
   auto val_of = [=](int64_t k) { return src_val[k]; };
-  out->atc.resize(static_cast<size_t>(nnz));
-  out->atv.resize(static_cast<size_t>(nnz));
-  out->ac.resize(static_cast<size_t>(nnz));
-  out->av.resize(static_cast<size_t>(nnz));
+  if (carver) {
+    out->atc = carver->take<int>(static_cast<size_t>(nnz));
+    out->atv = carver->take<double>(static_cast<size_t>(nnz));
+    out->ac = carver->take<int>(static_cast<size_t>(nnz));
+    out->av = carver->take<double>(static_cast<size_t>(nnz));
+  }
+  out->pooled = out->atc && out->atv && out->ac && out->av;
+  if (!out->pooled) {
+    out->own_atc.resize(static_cast<size_t>(nnz));
+    out->own_atv.resize(static_cast<size_t>(nnz));
+    out->own_ac.resize(static_cast<size_t>(nnz));
+    out->own_av.resize(static_cast<size_t>(nnz));
+    out->atc = out->own_atc.data();
+    out->atv = out->own_atv.data();
+    out->ac = out->own_ac.data();
+    out->av = out->own_av.data();
+  }
   const bool timing = getenv("FOLP_TIMING") != nullptr;
   const double t0 = now_sec();
   double t_side_plan = 0, t_side = 0;
@@ -1193,21 +1333,23 @@ static bool prepare_host_matrices(const folp_problem* p, const IVec& rp, const V
     plan_tiles(static_cast<int>(n), rp_t, warps_total, &out->pk_t);
     t_side_plan = now_sec();
     fill_packed(out->pk_t, rp_t, [=](int k) { return static_cast<int>(row_of(k)); }, val_of,
-                out->atc.data(), out->atv.data(), vo.identity ? nullptr : vo.src_start.data());
+                out->atc, out->atv, vo.identity ? nullptr : vo.src_start.data());
     t_side = now_sec();
     if (at_ready) at_ready();
   });
-  IVec ci2;
-  DVec v2;
-  const bool ok = transpose_to_csr(n, m, nnz, rp, row_of, val_of, &out->rp2, &ci2, &v2,
-                                   vo.identity ? nullptr : vo.old2new.data());
+  IVec ci2_own;
+  DVec v2_own;
+  int* ci2 = nullptr;
+  double* v2 = nullptr;
+  const bool ok = transpose_to_csr(n, m, nnz, rp, row_of, val_of, &out->rp2, &ci2_own, &v2_own,
+                                   vo.identity ? nullptr : vo.old2new.data(), out->pooled ? carver : nullptr, &ci2, &v2);
   const double t1 = now_sec();
   double t2 = t1;
   if (ok) {
     plan_tiles(static_cast<int>(m), out->rp2, warps_total, &out->pk_a);
     t2 = now_sec();
     fill_packed(out->pk_a, out->rp2, [&](int k) { return ci2[k]; }, [&](int k) { return v2[k]; },
-                out->ac.data(), out->av.data());
+                out->ac, out->av);
   }
   const double t3 = now_sec();
   side.join();
@@ -1253,6 +1395,13 @@ struct PhaseTimer {
 static int create_impl(folp_handle* h, const folp_problem* p, const folp_params* q,
                        const folp_dist* dist) {
   PhaseTimer pt;
+  // pinned host scratch leased for this create (one GPU); released on return, after the copies out of it have
+  // completed (StreamGuard below is destroyed first)
+  HostPoolLease host_pool;
+  struct StreamGuard {
+    folp_handle* h;
+    ~StreamGuard() { if (h->stream) cudaStreamSynchronize(h->stream); }
+  } stream_guard{h};
   const int64_t n = p->num_variables, m = p->num_constraints, nnz = p->num_nonzeros;
   if (n < 0 || m < 0 || nnz < 0 || p->num_equalities < 0 || p->num_equalities > m ||
       (p->index_base != 0 && p->index_base != 1)) {
@@ -1332,10 +1481,17 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   TRY(cudaEventCreate(&h->ev0));
   TRY(cudaEventCreate(&h->ev1));
   TRY(static_cast<cudaError_t>(spmv_configure()));
-  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->hs), sizeof(DevState)));
-  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_red), sizeof(double) * 4 * kMaxScalars));
-  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_trs), sizeof(TrState) * kTrSlots));
-  TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_sc), sizeof(double) * h->world * kScBlock));
+  {  // the four pinned mirrors in one allocation (each cudaMallocHost costs ~1.5 ms)
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t b0 = up(sizeof(DevState)), b1 = up(sizeof(double) * 4 * kMaxScalars), b2 = up(sizeof(TrState) * kTrSlots),
+                 b3 = up(sizeof(double) * h->world * kScBlock);
+    char* block = nullptr;
+    TRY(cudaMallocHost(reinterpret_cast<void**>(&block), b0 + b1 + b2 + b3));
+    h->hs = reinterpret_cast<DevState*>(block);
+    h->h_red = reinterpret_cast<double*>(block + b0);
+    h->h_trs = reinterpret_cast<TrState*>(block + b0 + b1);
+    h->h_sc = reinterpret_cast<double*>(block + b0 + b1 + b2);
+  }
 
   if (h->world > 1 && !h->shared) {
     h->nccl = nccl_api(&h->err);
@@ -1371,12 +1527,21 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   VarOrder vo;  // device numbering of the variables (order_variables)
   {
     IVec rp(static_cast<size_t>(n) + 1);
-    for (int64_t j = 0; j <= n; ++j) rp[j] = nnz ? static_cast<int>(p->colptr[j] - base) : 0;
-    for (int64_t j = 0; j < n; ++j)
-      if (rp[j] > rp[j + 1] || rp[j] < 0 || rp[j + 1] > nnz) {
+    {
+      std::atomic<int> bad{0};
+      rp[n] = nnz ? static_cast<int>(p->colptr[n] - base) : 0;
+      parallel_for(0, n, 1 << 16, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t j = lo; j < hi; ++j) {
+          const int64_t a = nnz ? p->colptr[j] - base : 0, b = nnz ? p->colptr[j + 1] - base : 0;
+          rp[j] = static_cast<int>(a);
+          if (a > b || a < 0 || b > nnz) bad.store(1, std::memory_order_relaxed);
+        }
+      });
+      if (bad.load()) {
         h->err = "colptr is not monotone";
         return FOLP_INVALID_ARGUMENT;
       }
+    }
     const int64_t* src_row = p->rowval;
     const double* src_val = p->nzval;
     auto row_of = [=](int64_t k) { return src_row[k] - base; };  // may be out of range until checked
@@ -1385,15 +1550,12 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
     IVec rp2, ci2;
     DVec v2;
     int rc;
-    order_variables(n, rp, &vo);
-    if (!vo.identity) h->new2old = vo.new2old;
-    const IVec& rp_t = vo.identity ? rp : vo.rp_new;  // column pointers in the device numbering
-    if (P == 1) {
-      h->row_begin[1] = m;
-      h->n_pad = n; h->m_pad = m;
-      h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
-      {  // device memory of the whole handle in one allocation, reserved up front from upper bounds so that
-         // A' can be uploaded while A is still being transposed (dev_alloc falls back to cudaMalloc when full)
+    int rc_arena = FOLP_OK;
+    std::thread arena_thread;  // one GPU: the arena's cudaMalloc runs beside the renumbering of the variables
+    if (P == 1) arena_thread = std::thread([&] {
+      cudaSetDevice(h->device);
+      // device memory of the whole handle in one allocation, reserved up front from upper bounds so that
+      // A' can be uploaded while A is still being transposed (dev_alloc falls back to cudaMalloc when full)
         auto mat_bound = [&](int64_t rows, int64_t nz) {
           const int64_t tiles = rows / 32 + 2 * (nz / 33) + nz / kChunkNnz + 3 * static_cast<int64_t>(warps_total) + 64;
           return static_cast<size_t>(4 * (rows + 17) + 12 * (nz + 32) + 32 * tiles + 8 * (rows + 16) +
@@ -1403,21 +1565,34 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         const size_t q_bytes = has_q ? mat_bound(n, qnnz) + static_cast<size_t>(5 * 8 * (n + 48)) : 0;
         const size_t vec_bytes = static_cast<size_t>(8) * (27 * (n + 48) + 21 * (m + 48)) +
                                  sizeof(double) * kNumSlots * kMaxScalars * kMaxPartialBlocks + (1 << 17);
-        if ((rc = arena_reserve(h, mat_bound(n, nnz) + mat_bound(m, nnz) + q_bytes + vec_bytes))) return rc;
-      }
+        rc_arena = arena_reserve(h, mat_bound(n, nnz) + mat_bound(m, nnz) + q_bytes + vec_bytes);
+    });
+    order_variables(n, rp, &vo);
+    if (arena_thread.joinable()) arena_thread.join();
+    if (rc_arena) return rc_arena;
+    if (!vo.identity) h->new2old = vo.new2old;
+    const IVec& rp_t = vo.identity ? rp : vo.rp_new;  // column pointers in the device numbering
+    if (P == 1) {
+      h->row_begin[1] = m;
+      h->n_pad = n; h->m_pad = m;
+      h->n = n; h->m = m; h->nnz = nnz; h->neq = p->num_equalities;
       HostMatrices hm;
       int rc_at = FOLP_OK;
+      // pinned scratch of the process, if it is free: transposition buckets (16 B / nonzero), unpacked CSR of A
+      // and both packed matrices (12 B each), the renumbered copies of up to 8 primal vectors
+      host_pool.acquire(static_cast<size_t>(nnz) * 52 + static_cast<size_t>(n) * 64 + (1 << 16), h->device);
+      HostCarver* carver = host_pool.held ? &host_pool.carver : nullptr;
       const bool ok = prepare_host_matrices(p, rp, vo, warps_total, &hm, [&] {
         cudaSetDevice(h->device);  // second thread: A' goes to the device while the first one transposes
-        rc_at = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp_t, hm.pk_t, hm.atc, hm.atv);
-      });
+        rc_at = upload_matrix(h, &h->At, static_cast<int>(n), static_cast<int>(m), rp_t, hm.pk_t, hm.atc, hm.atv, !hm.pooled);
+      }, carver);
       if (!ok) {
         h->err = "row index out of range";
         return FOLP_INVALID_ARGUMENT;
       }
       if (rc_at) return rc_at;
       pt.mark("transpose + pack (host), A' uploaded");
-      if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), hm.rp2, hm.pk_a, hm.ac, hm.av))) return rc;
+      if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), hm.rp2, hm.pk_a, hm.ac, hm.av, !hm.pooled))) return rc;
     } else {
       if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &v2,
                             vo.identity ? nullptr : vo.old2new.data())) {
@@ -1546,12 +1721,15 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
   gathered.reserve(8);
   auto upload_primal = [&](double** dst, const double* src, double fill) -> int {
     if (!src || vo.identity) return dev_upload(h, dst, at(src, c0), nl, fill);
-    gathered.emplace_back(static_cast<size_t>(nl));
-    std::vector<double>& g = gathered.back();
+    double* g = host_pool.held ? host_pool.carver.take<double>(static_cast<size_t>(nl)) : nullptr;
+    if (!g) {
+      gathered.emplace_back(static_cast<size_t>(nl));
+      g = gathered.back().data();
+    }
     parallel_for(0, nl, 1 << 16, [&](int64_t lo, int64_t hi, int) {
       for (int64_t j = lo; j < hi; ++j) g[j] = src[vo.new2old[c0 + j]];
     });
-    return dev_upload(h, dst, g.data(), nl, fill);
+    return dev_upload(h, dst, g, nl, fill);
   };
   int rc;
   if ((rc = dev_alloc(h, &B.st, 1))) return rc;
@@ -3059,7 +3237,7 @@ extern "C" int folp_debug_time_spmv(folp_handle* h, int transpose, int reps, dou
 }
 
 // Walks a packed matrix lane by lane with k_spmv's slot arithmetic (host, test hooks only).
-static int emulate_packed_spmv(const PackedMatrix& pk, const IVec& rp, const IVec& ci, const DVec& v,
+static int emulate_packed_spmv(const PackedMatrix& pk, const IVec& rp, const int* ci, const double* v,
                                int64_t rows, const double* x, double* y, int64_t warps_total,
                                int64_t* stats) {
   int64_t n_sorted = 0, n_rounds = 0;
@@ -3165,7 +3343,7 @@ extern "C" int folp_debug_host_spmv(int64_t rows, int64_t cols, const int64_t* r
   // packed straight from the caller's Int64 arrays, as folp_create does for A'
   fill_packed(pk, rp, [=](int k) { return static_cast<int>(colidx[k]); }, [=](int k) { return vals[k]; },
               ci.data(), v.data());
-  return emulate_packed_spmv(pk, rp, ci, v, rows, x, y, warps_total, stats);
+  return emulate_packed_spmv(pk, rp, ci.data(), v.data(), rows, x, y, warps_total, stats);
 }
 
 // Test hook without any CUDA call: runs the host half of folp_create on a folp_problem (transposition

@@ -41,9 +41,20 @@ def parity_checks(check, world, rank):
         print(f"[x{world}] exchange mode: {info['exchange']}", flush=True)
     o.close(); g.close()
 
+    quick = os.environ.get("FOLP_DIST_QUICK") is not None  # a short list (expensive boxes): one check per stage
     for i, make in enumerate([lambda: random_sparse_lp(3000, 2500, 8, seed=5), T.netlib_shaped_lp,
                               T._ragged_lp, lambda: T.pagerank_lp(3000)]):
+        if quick and i not in (0, 3):
+            continue
         check(f"spmv[{i}]", lambda make=make: T.test_spmv_matches_oracle(make))
+    if quick:
+        check("single_attempt[ragged]", lambda: T.test_single_attempt_parity(T._ragged_lp))
+        check("eval_records[ADAPTIVE_NORMALIZED]",
+              lambda: T.test_eval_records_match_oracle(RestartScheme.ADAPTIVE_NORMALIZED))
+        check("full_solve[random]", lambda: T.test_full_solve_matches_oracle(
+            lambda: random_sparse_lp(2000, 1500, 8, seed=41), 1e-6))
+        check("example_lp", T.test_example_lp_exact_record)
+        return
     check("single_attempt[random]", lambda: T.test_single_attempt_parity(
         lambda: random_sparse_lp(4000, 3000, 10, seed=11)))
     check("single_attempt[ragged]", lambda: T.test_single_attempt_parity(T._ragged_lp))
