@@ -675,16 +675,26 @@ static int upload_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const I
   return FOLP_OK;
 }
 
-// plan + pack (from unpacked CSR scratch) + upload
+// plan + pack (from unpacked CSR scratch) + upload. carver (optional): the packed arrays are carved from
+// the leased pinned scratch and uploaded asynchronously (they live until the create returns).
 static int build_matrix(folp_handle* h, SpmvMat* M, int rows, int cols, const IVec& rowptr,
-                        const IVec& colidx, const DVec& vals) {
+                        const int* colidx, const double* vals, HostCarver* carver = nullptr) {
   PackedMatrix pk;
   plan_tiles(rows, rowptr, h->sm_count * kSpmvCtasPerSm * kSpmvWarps, &pk);
-  IVec pc(colidx.size());
-  DVec pv(vals.size());
-  fill_packed(pk, rowptr, [&](int k) { return colidx[k]; }, [&](int k) { return vals[k]; }, pc.data(),
-              pv.data());
-  return upload_matrix(h, M, rows, cols, rowptr, pk, pc.data(), pv.data());
+  const size_t nz = static_cast<size_t>(rowptr[rows]);
+  int* pc = carver ? carver->take<int>(nz) : nullptr;
+  double* pv = carver ? carver->take<double>(nz) : nullptr;
+  const bool pooled = pc && pv;
+  IVec pc_own;
+  DVec pv_own;
+  if (!pooled) {
+    pc_own.resize(nz);
+    pv_own.resize(nz);
+    pc = pc_own.data();
+    pv = pv_own.data();
+  }
+  fill_packed(pk, rowptr, [=](int k) { return colidx[k]; }, [=](int k) { return vals[k]; }, pc, pv);
+  return upload_matrix(h, M, rows, cols, rowptr, pk, pc, pv, !pooled);
 }
 
 // collective: called by every rank thread of a single-process multi-GPU solve at the same time
@@ -1103,6 +1113,7 @@ static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, 
   const int64_t NB = ((m - 1) >> S) + 1;
   struct Entry { int row, col; double val; };
   std::vector<Entry, NoInit<Entry>> buf_own;
+  const size_t carver_mark = carver ? carver->used : 0;  // buf is dead when this function returns: its room is handed back
   Entry* buf = carver ? carver->take<Entry>(static_cast<size_t>(nnz)) : nullptr;
   if (!buf) {
     buf_own.resize(static_cast<size_t>(nnz));
@@ -1174,6 +1185,7 @@ static bool transpose_to_csr(int64_t n, int64_t m, int64_t nnz, const IVec& rp, 
     }
   });
   rp2[m] = static_cast<int>(nnz);
+  if (carver) carver->used = carver_mark;
   return true;
 }
 
@@ -1594,8 +1606,16 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       pt.mark("transpose + pack (host), A' uploaded");
       if ((rc = upload_matrix(h, &h->A, static_cast<int>(m), static_cast<int>(n), hm.rp2, hm.pk_a, hm.ac, hm.av, !hm.pooled))) return rc;
     } else {
+      // every rank transposes the whole matrix and keeps its shard: the transposition's scratch (buckets 16 B,
+      // unpacked CSR 12 B per nonzero) comes from the process's pinned pool when it is free (no page faults;
+      // one process per GPU only -- the rank threads of a single process would contend for the one pool)
+      // ... and so do this rank's packed shards (12 B per local nonzero each) and the remapped slice of A'
+      if (!h->shared) host_pool.acquire(static_cast<size_t>(nnz) * 28 + (static_cast<size_t>(nnz) / P + n + m) * 40 + (1 << 20), h->device);
+      HostCarver* carver = host_pool.held ? &host_pool.carver : nullptr;
+      int* ci2p = nullptr;
+      double* v2p = nullptr;
       if (!transpose_to_csr(n, m, nnz, rp, row_of, val_of, &rp2, &ci2, &v2,
-                            vo.identity ? nullptr : vo.old2new.data())) {
+                            vo.identity ? nullptr : vo.old2new.data(), carver, &ci2p, &v2p)) {
         h->err = "row index out of range";
         return FOLP_INVALID_ARGUMENT;
       }
@@ -1633,9 +1653,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       h->nnz = k1 - k0;
       IVec lrp(static_cast<size_t>(h->m) + 1);
       for (int64_t i = 0; i <= h->m; ++i) lrp[i] = rp2[h->row0 + i] - k0;
-      IVec lci(ci2.begin() + k0, ci2.begin() + k1);
-      DVec lv(v2.begin() + k0, v2.begin() + k1);
-      if ((rc = build_matrix(h, &h->A, static_cast<int>(h->m), static_cast<int>(n), lrp, lci, lv))) return rc;
+      if ((rc = build_matrix(h, &h->A, static_cast<int>(h->m), static_cast<int>(n), lrp, ci2p + k0, v2p + k0, carver))) return rc;
       // (A[:, slice])': the local columns of the caller's CSC, i.e. n_local rows of full length.
       // Their column indices (= global rows of A) are remapped into the padded rank-major
       // layout of y_full: row i of rank q -> q * m_pad + (i - row_begin[q]).
@@ -1649,16 +1667,26 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
       for (int q = 0; q < P; ++q)
         for (int64_t i = h->row_begin[q]; i < h->row_begin[q + 1]; ++i)
           owner_off[i] = static_cast<int>(q * h->m_pad + (i - h->row_begin[q]));
-      IVec tci(static_cast<size_t>(t1 - t0));
-      DVec tv(static_cast<size_t>(t1 - t0));
-      for (int64_t j = h->col0; j < c1; ++j) {
-        const int src = vo.identity ? rp[j] : vo.src_start[j];
-        for (int k = rp_t[j]; k < rp_t[j + 1]; ++k) {
-          tci[k - t0] = owner_off[row_of(src + (k - rp_t[j]))];  // rows were range-checked above
-          tv[k - t0] = src_val[src + (k - rp_t[j])];
-        }
+      IVec tci_own;
+      DVec tv_own;
+      int* tci = carver ? carver->take<int>(static_cast<size_t>(t1 - t0)) : nullptr;
+      double* tv = carver ? carver->take<double>(static_cast<size_t>(t1 - t0)) : nullptr;
+      if (!tci || !tv) {
+        tci_own.resize(static_cast<size_t>(t1 - t0));
+        tv_own.resize(static_cast<size_t>(t1 - t0));
+        tci = tci_own.data();
+        tv = tv_own.data();
       }
-      if ((rc = build_matrix(h, &h->At, static_cast<int>(h->n), static_cast<int>(P * h->m_pad), trp, tci, tv)))
+      parallel_for(h->col0, c1, 1 << 12, [&](int64_t jlo, int64_t jhi, int) {
+        for (int64_t j = jlo; j < jhi; ++j) {
+          const int src = vo.identity ? rp[j] : vo.src_start[j];
+          for (int k = rp_t[j]; k < rp_t[j + 1]; ++k) {
+            tci[k - t0] = owner_off[row_of(src + (k - rp_t[j]))];  // rows were range-checked above
+            tv[k - t0] = src_val[src + (k - rp_t[j])];
+          }
+        }
+      });
+      if ((rc = build_matrix(h, &h->At, static_cast<int>(h->n), static_cast<int>(P * h->m_pad), trp, tci, tv, carver)))
         return rc;
       h->nnz = (k1 - k0) + (t1 - t0);
     }
@@ -1697,7 +1725,7 @@ static int create_impl(folp_handle* h, const folp_problem* p, const folp_params*
         qv[pos] = p->q_nzval[k];
       }
     int rcq;
-    if ((rcq = build_matrix(h, &h->Q, static_cast<int>(n), static_cast<int>(n), qrp, qci, qv))) return rcq;
+    if ((rcq = build_matrix(h, &h->Q, static_cast<int>(n), static_cast<int>(n), qrp, qci.data(), qv.data()))) return rcq;
   }
 
   // ---- vectors: primal-indexed arrays hold the local slice, dual-indexed arrays the local rows ----
