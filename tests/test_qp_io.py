@@ -42,6 +42,26 @@ def test_read_mps_qp():  # :44-49
     _assert_qp(qp, [0.0, 1.0], [1.0, 2.0], [[2.0, 2.0], [2.0, 4.0]], [2.0, -1.0], 0.0, [[-1.0, -1.0]], [-3.0], 0)
 
 
+REFERENCE_TESTS = "/root/reference/test"  # present in the build container only; never on the GPU box
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_TESTS), reason="the reference tree is not here")
+@pytest.mark.parametrize("name, Q", [("trivial_lp_model.mps", np.zeros((2, 2))),
+                                     ("trivial_qp_model.mps", [[2.0, 2.0], [2.0, 4.0]])])
+def test_read_the_reference_s_own_fixtures(name, Q):
+    """The goldens above are re-written files; where the reference is at hand its OWN fixtures
+    (section order, QUADOBJ triangle, spacing as QPSReader's authors wrote them) must parse to the
+    structs of test/test_qp_io.jl:15-35 too, plain and gzipped."""
+    path = os.path.join(REFERENCE_TESTS, name)
+    qp = fio.qps_reader_to_standard_form(path)
+    _assert_qp(qp, [0.0, 1.0], [1.0, 2.0], Q, [2.0, -1.0], 0.0, [[-1.0, -1.0]], [-3.0], 0)
+    # and our golden of the same model describes the same problem
+    ours = fio.qps_reader_to_standard_form(os.path.join(GOLDEN, name))
+    _assert_qp(ours, qp.variable_lower_bound, qp.variable_upper_bound, qp.objective_matrix.toarray(),
+               qp.objective_vector, qp.objective_constant, qp.constraint_matrix.toarray(), qp.right_hand_side,
+               qp.num_equalities)
+
+
 def test_read_mps_gz(tmp_path):  # :51-64
     src = open(os.path.join(GOLDEN, "trivial_qp_model.mps")).read()
     path = tmp_path / "model.mps.gz"
