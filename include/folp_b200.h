@@ -191,7 +191,7 @@ typedef struct folp_eval {
   /* ConvergenceInformation */
   double primal_objective;
   double dual_objective;
-  double corrected_dual_objective;   /* dual_objective if l_inf_dual_residual == 0.0 exactly, else -Inf (isu.jl:197-206).
+  double corrected_dual_objective;   /* dual_objective if l_inf_dual_residual == 0.0 exactly, else -Inf (isu.jl:203-212).
                                       * The residual is formed from the SCALED products times D/E, not from the original
                                       * matrix: where the reference's residual is a rounding-sized nonzero (or the other
                                       * way round) this exact test can fall on the other side. Tolerance-sensitive. */
